@@ -1,0 +1,207 @@
+/* shamb200.h — C ABI of the B200-native SPH timestep backend (libshamb200.so).
+ *
+ * The reference (Shamrock, /root/reference, commit 3ddd3ab4) has no FFI for this path: it is
+ * extended by C++ templates compiled in, by pybind11 modules and by solvergraph INode subclasses
+ * (SURVEY.md §8b).  This header is therefore the boundary a Shamrock maintainer would bind
+ * against (INTEGRATION.md shows the INode / pybind stubs).  Every entry point cites the reference
+ * function it replaces (paths relative to /root/reference/src).
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes, no C++ or torch types.
+ *  - "d_" pointers are DEVICE pointers owned by the caller; the library never frees them.
+ *    Output arrays reachable through shamb200_tree / shamb200_csr views are owned by the context
+ *    arena and stay valid until the next call that rebuilds them or the context is destroyed.
+ *  - vec3 fields are arrays of doubles with a stride given in doubles (3 = packed 24 B as in
+ *    the reference's serialised form, 4 = 32 B like sycl::vec<f64,3>).
+ *  - every function returns 0 on success, a negative code on error; shamb200_last_error()
+ *    returns the message (thread local).  No exception crosses the boundary.  There is no CPU
+ *    fallback: without a CUDA device every compute entry point fails with SHAMB200_ERR_CUDA.
+ *  - one context per GPU, driven by one host thread; all work of a context is enqueued on the
+ *    context's stream (shamb200_ctx_stream) unless a function says it synchronises.
+ */
+#ifndef SHAMB200_H
+#define SHAMB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SHAMB200_OK 0
+#define SHAMB200_ERR_INVALID -1
+#define SHAMB200_ERR_CUDA -2
+#define SHAMB200_ERR_OVERFLOW -3
+#define SHAMB200_ERR_NCCL -4
+#define SHAMB200_ERR_RUNTIME -5
+
+typedef struct shamb200_ctx shamb200_ctx;
+typedef struct shamb200_model shamb200_model;
+
+/* SPH kernels: shammath/include/shammath/sphkernels.hpp:29-82 (M4), :265-346 (M6) */
+enum { SHAMB200_KERNEL_M4 = 0, SHAMB200_KERNEL_M6 = 1 };
+/* sort backends of shamalgs::algorithm::sort_by_key (shamalgs/src/primitives/sort_by_keys.cpp:36-44):
+ * BITONIC reproduces the reference's network bit for bit (incl. the order inside equal-key runs);
+ * RADIX is a stable LSD radix sort (same keys, ties in input order). */
+enum { SHAMB200_SORT_BITONIC = 0, SHAMB200_SORT_RADIX = 1 };
+enum { SHAMB200_EOS_ADIABATIC = 0, SHAMB200_EOS_ISOTHERMAL = 1, SHAMB200_EOS_LOCALLY_ISOTHERMAL_LP07 = 2 };
+enum { SHAMB200_AV_NONE = 0, SHAMB200_AV_CONSTANT = 1, SHAMB200_AV_MM97 = 2, SHAMB200_AV_CD10 = 3, SHAMB200_AV_CONSTANT_DISC = 4 };
+enum { SHAMB200_BC_FREE = 0, SHAMB200_BC_PERIODIC = 1 };
+
+const char *shamb200_last_error(void);
+/* library / build information ("sm_100a", strict-fp flag, ...) */
+const char *shamb200_build_info(void);
+/* number of CUDA kernels launched by this library since the last reset (process wide) */
+uint64_t shamb200_launch_count(void);
+void shamb200_reset_launch_count(void);
+
+/* ---- context --------------------------------------------------------------------------------
+ * replaces: shamsys::instance (device + queue selection, shamsys/src/NodeInstance.cpp) and
+ * sham::DeviceScheduler for this path.  `stream` may be NULL (the context creates its own). */
+int shamb200_ctx_create(int device, void *cuda_stream, shamb200_ctx **out);
+int shamb200_ctx_destroy(shamb200_ctx *ctx);
+void *shamb200_ctx_stream(shamb200_ctx *ctx);
+int shamb200_ctx_synchronize(shamb200_ctx *ctx);
+
+/* ---- tree (shamtree::CompressedLeafBVH<u32, f64_3, 3>) ----------------------------------------
+ * Device-resident output of rebuild_from_positions; contract of SURVEY.md §3.3. */
+typedef struct shamb200_tree {
+    uint32_t obj_cnt;      /* M                                    */
+    uint32_t morton_count; /* P2 = roundup_pow2(M)                 */
+    uint32_t leaf_count;   /* L                                    */
+    uint32_t int_count;    /* I = L - 1                            */
+    double bmin[3], bmax[3];
+    const uint32_t *d_sorted_morton;   /* [P2] (pad = 0xFFFFFFFF)  */
+    const uint32_t *d_sort_index_map;  /* [P2] map_morton_id_to_obj_id */
+    const uint32_t *d_reduc_index_map; /* [L+2] leaf starts, then M, then 0 */
+    const uint32_t *d_reduced_morton;  /* [L]                      */
+    const uint32_t *d_lchild_id, *d_rchild_id, *d_endrange; /* [I] */
+    const uint8_t *d_lchild_flag, *d_rchild_flag;           /* [I] 1 = leaf */
+    const double *d_aabb_min, *d_aabb_max; /* [(I+L)*3] packed, internal cells first */
+} shamb200_tree;
+
+/* replaces shamtree::CompressedLeafBVH::rebuild_from_positions (shamtree/src/CompressedLeafBVH.cpp:79-95):
+ * Morton codes (MortonCodeSet.cpp:61-128) -> key/value sort (MortonCodeSortedSet.cpp:24-49) ->
+ * leaf compression (MortonReducedSet.cpp:24-72, kernels/reduction_alg.cpp) -> Karras tree
+ * (KarrasRadixTree.cpp:46-183) -> AABBs (KarrasRadixTreeAABB.cpp:93-135).
+ * Synchronises once (the leaf count is needed on the host, as in the reference). */
+int shamb200_tree_build(shamb200_ctx *ctx, const double *d_xyz, size_t stride_dbl, uint32_t obj_cnt,
+                        const double bmin[3], const double bmax[3], uint32_t reduction_level,
+                        int sort_mode, shamb200_tree *out);
+/* same, with the bounding box computed like modules::BuildTrees::build_merged_pos_trees
+ * (shammodels/sph/src/modules/BuildTrees.cpp:37-56): min/max of the positions widened by one ulp */
+int shamb200_tree_build_auto_bbox(shamb200_ctx *ctx, const double *d_xyz, size_t stride_dbl,
+                                  uint32_t obj_cnt, uint32_t reduction_level, int sort_mode,
+                                  shamb200_tree *out);
+/* replaces shamtree::compute_tree_field_max_field<f64> (KarrasRadixTreeField.hpp:189-222) followed by
+ * the `*= htol` of Solver::compute_presteps_rint (shammodels/sph/src/Solver.cpp:1322-1356).
+ * d_out: [(I+L)] doubles, caller owned. */
+int shamb200_tree_field_max(shamb200_ctx *ctx, const shamb200_tree *tree, const double *d_field,
+                            double scale, double *d_out);
+
+/* ---- neighbour cache (shamrock::tree::ObjectCache, shamtree/include/shamtree/TreeTraversal.hpp:375-485) */
+typedef struct shamb200_csr {
+    uint32_t obj_cnt;            /* N                         */
+    uint32_t sum_neigh_cnt;      /* K (u32 like the reference) */
+    const uint32_t *d_cnt_neigh;   /* [N] */
+    const uint32_t *d_scanned_cnt; /* [N] exclusive scan */
+    const uint32_t *d_index_neigh_map; /* [K] */
+} shamb200_csr;
+
+/* replaces modules::NeighbourCache::start_neighbors_cache_2stages / start_neighbors_cache
+ * (shammodels/sph/src/modules/NeighbourCache.cpp:223-604 / :30-220).  d_rint = output of
+ * shamb200_tree_field_max(h, htol).  Lists are bit-identical to the reference's (ascending rank in
+ * the sorted Morton array).  Synchronises (list sizing).  Fails with SHAMB200_ERR_OVERFLOW when the
+ * total count does not fit u32 (the reference's sum_neigh_cnt is u32). */
+int shamb200_neigh_cache_build(shamb200_ctx *ctx, const shamb200_tree *tree, const double *d_xyz,
+                               size_t stride_dbl, const double *d_hpart, const double *d_rint,
+                               uint32_t obj_cnt, double Rkern, double h_tolerance, int two_stage,
+                               shamb200_csr *out);
+
+/* ---- smoothing length, density ------------------------------------------------------------------
+ * replaces modules::IterateSmoothingLengthDensity::_impl_evaluate_internal (one Newton sweep,
+ * shammodels/sph/src/modules/IterateSmoothingLengthDensity.cpp:28-120).  d_h_new / d_eps in place. */
+int shamb200_h_iterate(shamb200_ctx *ctx, int kernel, const shamb200_csr *csr, const double *d_xyz,
+                       size_t stride_dbl, const double *d_h_old, double *d_h_new, double *d_eps,
+                       double gpart_mass, double h_evol_max, double h_evol_iter_max);
+/* replaces modules::LoopSmoothingLengthIter (LoopSmoothingLengthIter.cpp:29-84): up to max_sweeps
+ * sweeps with the max-eps test after each; out3 = {max_eps, min_eps, sweeps done}. */
+int shamb200_h_iterate_loop(shamb200_ctx *ctx, int kernel, const shamb200_csr *csr, const double *d_xyz,
+                            size_t stride_dbl, const double *d_h_old, double *d_h_new, double *d_eps,
+                            double gpart_mass, double h_evol_max, double h_evol_iter_max,
+                            double epsilon_h, uint32_t max_sweeps, double out3[3]);
+/* replaces modules::NodeComputeOmega (shammodels/sph/src/modules/ComputeOmega.cpp:25-74) */
+int shamb200_compute_omega(shamb200_ctx *ctx, int kernel, const shamb200_csr *csr, const double *d_xyz,
+                           size_t stride_dbl, const double *d_hpart, double *d_omega, double gpart_mass);
+
+/* ---- model (shammodels::sph::Model<f64_3, Kernel> / Solver::evolve_once) -------------------------
+ * Host-side drop-in: owns the patch data on the device and runs the whole step on the GPU.
+ * Mirrors shammodels/sph/include/shammodels/sph/Model.hpp:55-1076 and Solver.cpp:1942-3272 for
+ * the configuration subset of SURVEY.md §8.  All pointers here are HOST pointers. */
+typedef struct shamb200_solver_config {
+    int32_t kernel;  /* SHAMB200_KERNEL_*                                  */
+    int32_t eos;     /* SHAMB200_EOS_*                                     */
+    int32_t av;      /* SHAMB200_AV_*                                      */
+    int32_t bc;      /* SHAMB200_BC_*                                      */
+    double gpart_mass;
+    double gamma, cs0, eos_q, eos_r0;
+    double alpha_u, alpha_AV, beta_AV, alpha_min, alpha_max, sigma_decay;
+    double cfl_cour, cfl_force, cfl_multiplier_stiffness;
+    double htol_up_coarse_cycle, htol_up_fine_cycle, epsilon_h;
+    uint32_t h_iter_per_subcycles, h_max_subcycles_count, tree_reduction_level;
+    int32_t use_two_stage_search;
+    int32_t combined_dtdiv_divcurlv_compute;
+    int32_t sort_mode;   /* SHAMB200_SORT_*                                */
+    int32_t has_point_mass;
+    double pm_mass, pm_racc, constant_G;
+    int32_t n_kill_spheres;
+    int32_t keep_step_data; /* keep per-step intermediates for shamb200_model_get (tests) */
+    double kill_center[4][3];
+    double kill_radius[4];
+} shamb200_solver_config;
+
+/* defaults of SolverConfig (shammodels/sph/include/shammodels/sph/SolverConfig.hpp:584-630,
+ * config/AVConfig.hpp:46-140) */
+void shamb200_solver_config_default(shamb200_solver_config *cfg);
+
+int shamb200_model_create(shamb200_ctx *ctx, const shamb200_solver_config *cfg, shamb200_model **out);
+int shamb200_model_destroy(shamb200_model *m);
+int shamb200_model_set_config(shamb200_model *m, const shamb200_solver_config *cfg);
+/* Model::resize_simulation_box + a static patch grid (nx*ny*nz, powers of two) on the 2^21 integer
+ * patch grid of PatchScheduler; patches are dealt to ranks in id order, contiguously. */
+int shamb200_model_set_box(shamb200_model *m, const double bmin[3], const double bmax[3], uint32_t nx,
+                           uint32_t ny, uint32_t nz);
+/* multi-GPU: rank/size of this process and the NCCL unique id (128 bytes, from
+ * shamb200_nccl_unique_id on rank 0, broadcast by the caller).  Optional (single GPU otherwise). */
+int shamb200_nccl_unique_id(void *out128);
+int shamb200_model_init_comm(shamb200_model *m, int rank, int world_size, const void *nccl_id128);
+/* append particles (host arrays; vxyz / uint may be NULL = 0).  Each rank passes particles of any
+ * patch; only those owned by a local patch are kept (setup generators call this with the same
+ * deterministic stream on every rank). */
+int shamb200_model_push_particles(shamb200_model *m, uint64_t n, const double *xyz, const double *vxyz,
+                                  const double *hpart, const double *uint_);
+uint32_t shamb200_model_patch_count(shamb200_model *m);       /* global number of patches   */
+int shamb200_model_patch_is_local(shamb200_model *m, uint32_t ip);
+uint32_t shamb200_model_patch_size(shamb200_model *m, uint32_t ip); /* 0 for remote patches  */
+/* field access by name, patch by patch (ctx.collect_data() equivalent).  Names: main layout
+ * (SolverConfig.cpp:24-121) xyz vxyz axyz axyz_ext hpart uint duint alpha_AV divv dtdivv curlv
+ * soundspeed; with keep_step_data also step.* / tree.* / cache.* (see DESIGN.md).
+ * get: returns the byte size, copies when cap_bytes is large enough; -1 if unknown. */
+int64_t shamb200_model_get(shamb200_model *m, uint32_t ip, const char *name, void *out, int64_t cap_bytes);
+int shamb200_model_set_field(shamb200_model *m, uint32_t ip, const char *name, const double *in, uint64_t count);
+/* Solver::evolve_once (Solver.cpp:1942).  Runs one full step; synchronises at the end. */
+int shamb200_model_evolve_once(shamb200_model *m);
+/* state: {time, next dt, cfl_multiplier, eps_v, h_subcycles, h_iters_last, corrector_iter,
+ *         npart(global), t_step seconds (host wall), rate(part/s, this rank), K (local neighbour count)} */
+int shamb200_model_state(shamb200_model *m, double out[12]);
+int shamb200_model_set_next_dt(shamb200_model *m, double dt);
+int shamb200_model_set_time(shamb200_model *m, double t);
+int shamb200_model_set_cfl_multiplier(shamb200_model *m, double v);
+/* per-stage device time of the last step (CUDA events), names separated by ';' in *names */
+int shamb200_model_stage_times(shamb200_model *m, const char **names, const double **ms, uint32_t *count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHAMB200_H */

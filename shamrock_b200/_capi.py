@@ -1,0 +1,318 @@
+"""ctypes binding of libshamb200.so (include/shamb200.h).  No CPU fallback: importing works without a
+GPU (symbols can be inspected), every compute entry point needs a CUDA device."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libshamb200.so")
+
+KERNELS = {"M4": 0, "M6": 1}
+SORT_MODES = {"bitonic": 0, "radix": 1}
+EOS = {"adiabatic": 0, "isothermal": 1, "locally_isothermal_lp07": 2}
+AV = {"none": 0, "constant": 1, "varying_mm97": 2, "varying_cd10": 3, "constant_disc": 4}
+BC = {"free": 0, "periodic": 1}
+
+
+class ShamB200Error(RuntimeError):
+    pass
+
+
+class TreeView(C.Structure):
+    _fields_ = [
+        ("obj_cnt", C.c_uint32), ("morton_count", C.c_uint32), ("leaf_count", C.c_uint32),
+        ("int_count", C.c_uint32), ("bmin", C.c_double * 3), ("bmax", C.c_double * 3),
+        ("d_sorted_morton", C.c_void_p), ("d_sort_index_map", C.c_void_p),
+        ("d_reduc_index_map", C.c_void_p), ("d_reduced_morton", C.c_void_p),
+        ("d_lchild_id", C.c_void_p), ("d_rchild_id", C.c_void_p), ("d_endrange", C.c_void_p),
+        ("d_lchild_flag", C.c_void_p), ("d_rchild_flag", C.c_void_p),
+        ("d_aabb_min", C.c_void_p), ("d_aabb_max", C.c_void_p),
+    ]
+
+
+class CsrView(C.Structure):
+    _fields_ = [
+        ("obj_cnt", C.c_uint32), ("sum_neigh_cnt", C.c_uint32), ("d_cnt_neigh", C.c_void_p),
+        ("d_scanned_cnt", C.c_void_p), ("d_index_neigh_map", C.c_void_p),
+    ]
+
+
+class SolverConfig(C.Structure):
+    _fields_ = [
+        ("kernel", C.c_int32), ("eos", C.c_int32), ("av", C.c_int32), ("bc", C.c_int32),
+        ("gpart_mass", C.c_double),
+        ("gamma", C.c_double), ("cs0", C.c_double), ("eos_q", C.c_double), ("eos_r0", C.c_double),
+        ("alpha_u", C.c_double), ("alpha_AV", C.c_double), ("beta_AV", C.c_double),
+        ("alpha_min", C.c_double), ("alpha_max", C.c_double), ("sigma_decay", C.c_double),
+        ("cfl_cour", C.c_double), ("cfl_force", C.c_double), ("cfl_multiplier_stiffness", C.c_double),
+        ("htol_up_coarse_cycle", C.c_double), ("htol_up_fine_cycle", C.c_double), ("epsilon_h", C.c_double),
+        ("h_iter_per_subcycles", C.c_uint32), ("h_max_subcycles_count", C.c_uint32),
+        ("tree_reduction_level", C.c_uint32),
+        ("use_two_stage_search", C.c_int32), ("combined_dtdiv_divcurlv_compute", C.c_int32),
+        ("sort_mode", C.c_int32), ("has_point_mass", C.c_int32),
+        ("pm_mass", C.c_double), ("pm_racc", C.c_double), ("constant_G", C.c_double),
+        ("n_kill_spheres", C.c_int32), ("keep_step_data", C.c_int32),
+        ("kill_center", (C.c_double * 3) * 4), ("kill_radius", C.c_double * 4),
+    ]
+
+
+# every symbol include/shamb200.h declares (checked by tests/test_capi_symbols.py)
+SYMBOLS = [
+    "shamb200_last_error", "shamb200_build_info", "shamb200_launch_count", "shamb200_reset_launch_count",
+    "shamb200_ctx_create", "shamb200_ctx_destroy", "shamb200_ctx_stream", "shamb200_ctx_synchronize",
+    "shamb200_tree_build", "shamb200_tree_build_auto_bbox", "shamb200_tree_field_max",
+    "shamb200_neigh_cache_build", "shamb200_h_iterate", "shamb200_h_iterate_loop", "shamb200_compute_omega",
+    "shamb200_solver_config_default", "shamb200_model_create", "shamb200_model_destroy",
+    "shamb200_model_set_config", "shamb200_model_set_box", "shamb200_nccl_unique_id",
+    "shamb200_model_init_comm", "shamb200_model_push_particles", "shamb200_model_patch_count",
+    "shamb200_model_patch_is_local", "shamb200_model_patch_size", "shamb200_model_get",
+    "shamb200_model_set_field", "shamb200_model_evolve_once", "shamb200_model_state",
+    "shamb200_model_set_next_dt", "shamb200_model_set_time", "shamb200_model_set_cfl_multiplier",
+    "shamb200_model_stage_times",
+]
+
+_lib = None
+
+
+def lib():
+    """Load libshamb200.so; fails loudly when it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ShamB200Error(
+                f"{LIB_PATH} is missing: build it with `python -m shamrock_b200.build` "
+                "(nvcc, sm_100a).  shamrock_b200 has no CPU fallback.")
+        L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        L.shamb200_last_error.restype = C.c_char_p
+        L.shamb200_build_info.restype = C.c_char_p
+        L.shamb200_launch_count.restype = C.c_uint64
+        L.shamb200_ctx_stream.restype = C.c_void_p
+        L.shamb200_model_get.restype = C.c_int64
+        L.shamb200_model_patch_count.restype = C.c_uint32
+        L.shamb200_model_patch_size.restype = C.c_uint32
+        L.shamb200_ctx_create.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.shamb200_model_create.argtypes = [C.c_void_p, C.POINTER(SolverConfig), C.POINTER(C.c_void_p)]
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise ShamB200Error(f"[{rc}] " + lib().shamb200_last_error().decode())
+
+
+def default_config():
+    cfg = SolverConfig()
+    lib().shamb200_solver_config_default(C.byref(cfg))
+    return cfg
+
+
+def launch_count():
+    return int(lib().shamb200_launch_count())
+
+
+def reset_launch_count():
+    lib().shamb200_reset_launch_count()
+
+
+class Context:
+    """One per GPU (shamb200_ctx)."""
+
+    def __init__(self, device=0, stream=None):
+        h = C.c_void_p()
+        check(lib().shamb200_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().shamb200_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self):
+        return lib().shamb200_ctx_stream(self.h)
+
+    def synchronize(self):
+        check(lib().shamb200_ctx_synchronize(self.h))
+
+    # ---- stage-level entry points on device pointers (torch tensors carry the memory) ----------
+    def tree_build(self, xyz_t, obj_cnt, bmin=None, bmax=None, reduction_level=3, sort_mode="bitonic",
+                   stride_dbl=3):
+        tv = TreeView()
+        if bmin is None:
+            check(lib().shamb200_tree_build_auto_bbox(
+                self.h, C.c_void_p(xyz_t.data_ptr()), C.c_size_t(stride_dbl), C.c_uint32(obj_cnt),
+                C.c_uint32(reduction_level), SORT_MODES[sort_mode], C.byref(tv)))
+        else:
+            b0 = (C.c_double * 3)(*bmin)
+            b1 = (C.c_double * 3)(*bmax)
+            check(lib().shamb200_tree_build(
+                self.h, C.c_void_p(xyz_t.data_ptr()), C.c_size_t(stride_dbl), C.c_uint32(obj_cnt), b0, b1,
+                C.c_uint32(reduction_level), SORT_MODES[sort_mode], C.byref(tv)))
+        return tv
+
+    def tree_field_max(self, tv, field_t, scale, out_t):
+        check(lib().shamb200_tree_field_max(self.h, C.byref(tv), C.c_void_p(field_t.data_ptr()),
+                                            C.c_double(scale), C.c_void_p(out_t.data_ptr())))
+
+    def neigh_cache_build(self, tv, xyz_t, h_t, rint_t, obj_cnt, Rkern, htol, two_stage=True, stride_dbl=3):
+        cv = CsrView()
+        check(lib().shamb200_neigh_cache_build(
+            self.h, C.byref(tv), C.c_void_p(xyz_t.data_ptr()), C.c_size_t(stride_dbl),
+            C.c_void_p(h_t.data_ptr()), C.c_void_p(rint_t.data_ptr()), C.c_uint32(obj_cnt),
+            C.c_double(Rkern), C.c_double(htol), int(two_stage), C.byref(cv)))
+        return cv
+
+    def h_iterate(self, kernel, cv, xyz_t, h_old_t, h_new_t, eps_t, pmass, h_evol_max, h_evol_iter_max,
+                  stride_dbl=3):
+        check(lib().shamb200_h_iterate(
+            self.h, KERNELS[kernel], C.byref(cv), C.c_void_p(xyz_t.data_ptr()), C.c_size_t(stride_dbl),
+            C.c_void_p(h_old_t.data_ptr()), C.c_void_p(h_new_t.data_ptr()), C.c_void_p(eps_t.data_ptr()),
+            C.c_double(pmass), C.c_double(h_evol_max), C.c_double(h_evol_iter_max)))
+
+    def h_iterate_loop(self, kernel, cv, xyz_t, h_old_t, h_new_t, eps_t, pmass, h_evol_max, h_evol_iter_max,
+                       epsilon_h, max_sweeps, stride_dbl=3):
+        out = (C.c_double * 3)()
+        check(lib().shamb200_h_iterate_loop(
+            self.h, KERNELS[kernel], C.byref(cv), C.c_void_p(xyz_t.data_ptr()), C.c_size_t(stride_dbl),
+            C.c_void_p(h_old_t.data_ptr()), C.c_void_p(h_new_t.data_ptr()), C.c_void_p(eps_t.data_ptr()),
+            C.c_double(pmass), C.c_double(h_evol_max), C.c_double(h_evol_iter_max), C.c_double(epsilon_h),
+            C.c_uint32(max_sweeps), out))
+        return dict(max_eps=out[0], min_eps=out[1], sweeps=int(out[2]))
+
+    def compute_omega(self, kernel, cv, xyz_t, h_t, omega_t, pmass, stride_dbl=3):
+        check(lib().shamb200_compute_omega(
+            self.h, KERNELS[kernel], C.byref(cv), C.c_void_p(xyz_t.data_ptr()), C.c_size_t(stride_dbl),
+            C.c_void_p(h_t.data_ptr()), C.c_void_p(omega_t.data_ptr()), C.c_double(pmass)))
+
+
+_U32 = {"sorted_morton", "sort_index_map", "reduc_index_map", "reduced_morton", "lchild_id", "rchild_id",
+        "endrange", "cnt_neigh", "scanned_cnt", "index_neigh_map"}
+_U8 = {"lchild_flag", "rchild_flag"}
+_VEC3 = {"xyz", "vxyz", "axyz", "axyz_ext", "curlv", "mxyz", "g_v", "g_a", "aabb_min", "aabb_max"}
+
+
+class Model:
+    """shamb200_model: device-resident patches + evolve_once (host buffers in / out)."""
+
+    def __init__(self, ctx, cfg):
+        self.ctx = ctx
+        self.cfg = cfg
+        h = C.c_void_p()
+        check(lib().shamb200_model_create(ctx.h, C.byref(cfg), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().shamb200_model_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_config(self, cfg):
+        self.cfg = cfg
+        check(lib().shamb200_model_set_config(self.h, C.byref(cfg)))
+
+    def set_box(self, bmin, bmax, grid=(1, 1, 1)):
+        check(lib().shamb200_model_set_box(self.h, (C.c_double * 3)(*bmin), (C.c_double * 3)(*bmax),
+                                           *[C.c_uint32(g) for g in grid]))
+
+    def init_comm(self, rank, world, nccl_id):
+        buf = (C.c_char * 128).from_buffer_copy(bytes(nccl_id))
+        check(lib().shamb200_model_init_comm(self.h, int(rank), int(world), buf))
+
+    def push_particles(self, xyz, vxyz, h, u):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+        n = len(xyz)
+
+        def p(a, nv):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=np.float64).reshape(n * nv)
+            keep.append(a)
+            return a.ctypes.data_as(C.c_void_p)
+
+        keep = [xyz]
+        check(lib().shamb200_model_push_particles(self.h, C.c_uint64(n), xyz.ctypes.data_as(C.c_void_p),
+                                                  p(vxyz, 3), p(h, 1), p(u, 1)))
+
+    @property
+    def patch_count(self):
+        return lib().shamb200_model_patch_count(self.h)
+
+    def patch_is_local(self, ip):
+        return bool(lib().shamb200_model_patch_is_local(self.h, C.c_uint32(ip)))
+
+    def patch_size(self, ip):
+        return lib().shamb200_model_patch_size(self.h, C.c_uint32(ip))
+
+    def get(self, ip, name):
+        base = name.split(".")[-1]
+        dt = np.uint32 if base in _U32 else (np.uint8 if base in _U8 else np.float64)
+        nb = lib().shamb200_model_get(self.h, C.c_uint32(ip), name.encode(), None, C.c_int64(0))
+        if nb == -1:
+            raise KeyError(name)
+        if nb < 0:
+            raise ShamB200Error(lib().shamb200_last_error().decode())
+        out = np.empty(nb // np.dtype(dt).itemsize, dtype=dt)
+        if nb:
+            r = lib().shamb200_model_get(self.h, C.c_uint32(ip), name.encode(), out.ctypes.data_as(C.c_void_p),
+                                         C.c_int64(nb))
+            if r < 0:
+                raise ShamB200Error(lib().shamb200_last_error().decode())
+        if base in _VEC3:
+            out = out.reshape(-1, 3)
+        return out
+
+    def set_field(self, ip, name, arr):
+        a = np.ascontiguousarray(arr, dtype=np.float64).reshape(-1)
+        check(lib().shamb200_model_set_field(self.h, C.c_uint32(ip), name.encode(),
+                                             a.ctypes.data_as(C.c_void_p), C.c_uint64(a.size)))
+
+    def evolve_once(self):
+        check(lib().shamb200_model_evolve_once(self.h))
+        return self.state()
+
+    def state(self):
+        o = (C.c_double * 12)()
+        check(lib().shamb200_model_state(self.h, o))
+        keys = ("time", "dt", "cfl_multiplier", "eps_v", "h_subcycles", "h_iters_last", "corrector_iter",
+                "npart", "t_step", "rate", "K_local", "n_local")
+        return dict(zip(keys, list(o)))
+
+    def set_next_dt(self, dt):
+        check(lib().shamb200_model_set_next_dt(self.h, C.c_double(dt)))
+
+    def set_time(self, t):
+        check(lib().shamb200_model_set_time(self.h, C.c_double(t)))
+
+    def set_cfl_multiplier(self, v):
+        check(lib().shamb200_model_set_cfl_multiplier(self.h, C.c_double(v)))
+
+    def stage_times(self):
+        names = C.c_char_p()
+        ms = C.POINTER(C.c_double)()
+        cnt = C.c_uint32()
+        check(lib().shamb200_model_stage_times(self.h, C.byref(names), C.byref(ms), C.byref(cnt)))
+        ns = names.value.decode().split(";") if names.value else []
+        return {n: ms[i] for i, n in enumerate(ns[: cnt.value])}
+
+
+def nccl_unique_id():
+    buf = (C.c_char * 128)()
+    rc = lib().shamb200_nccl_unique_id(buf)
+    if rc != 0:
+        raise ShamB200Error("cannot create a NCCL unique id")
+    return bytes(buf)

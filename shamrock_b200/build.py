@@ -1,0 +1,83 @@
+"""Build libshamb200.so (hand-written CUDA for sm_100a) in-tree with nvcc.
+
+    python -m shamrock_b200.build [--force]
+
+The tree / neighbour / streaming kernels are always compiled with -fmad=false (bit-exact integer
+and comparison results).  The SPH loops are compiled strict by default (bit-identical to the CPU
+oracle); SHAMB200_FAST_MATH=1 allows FMA contraction in sph.cu only (1e-10 relative contract).
+"""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "_build")
+LIB = os.path.join(HERE, "libshamb200.so")
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off"]
+SOURCES = {
+    "tree.cu": ["-fmad=false"],
+    "neigh.cu": ["-fmad=false"],
+    "stream_kernels.cu": ["-fmad=false"],
+    "sph.cu": None,  # strict / fast decided below
+    "solver.cu": ["-fmad=false"],
+    "solver_comm.cu": ["-fmad=false"],
+    "capi.cu": ["-fmad=false"],
+}
+
+
+def _nvcc():
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if c and (os.path.isabs(c) and os.path.exists(c) or not os.path.isabs(c)):
+            return c
+    return "nvcc"
+
+
+def _host_cxx():
+    # the image exports CXX=/opt/gcc/bin/g++ which lacks some runtime pieces; use the distro g++
+    return "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [
+        os.path.join(HERE, "..", "include", "shamb200.h"), os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    os.makedirs(OBJ, exist_ok=True)
+    fast = os.environ.get("SHAMB200_FAST_MATH", "0") == "1"
+    nvcc = _nvcc()
+
+    def compile_one(item):
+        src, flags = item
+        if flags is None:
+            flags = ["-fmad=true", "-DSB_FAST_MATH"] if fast else ["-fmad=false"]
+        obj = os.path.join(OBJ, src.replace(".cu", ".o"))
+        cmd = [nvcc, "-ccbin", _host_cxx()] + ARCH + COMMON + flags + ["-c", os.path.join(CSRC, src), "-o", obj]
+        if verbose:
+            print(" ".join(cmd))
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+        objs = list(ex.map(compile_one, SOURCES.items()))
+    cmd = [nvcc, "-ccbin", _host_cxx()] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

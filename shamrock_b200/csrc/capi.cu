@@ -1,0 +1,317 @@
+// capi.cu — the extern "C" boundary declared in include/shamb200.h.
+#include "solver.cuh"
+#include <cstring>
+
+using namespace sb;
+
+
+namespace {
+thread_local std::string g_err;
+
+template<class F>
+int guard(F &&f) {
+    try {
+        f();
+        return SHAMB200_OK;
+    } catch (const CudaError &e) {
+        g_err = e.what();
+        return SHAMB200_ERR_CUDA;
+    } catch (const std::overflow_error &e) {
+        g_err = e.what();
+        return SHAMB200_ERR_OVERFLOW;
+    } catch (const std::invalid_argument &e) {
+        g_err = e.what();
+        return SHAMB200_ERR_INVALID;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return SHAMB200_ERR_RUNTIME;
+    }
+}
+
+void fill_tree_view(const TreeBuffers &t, shamb200_tree *out) {
+    out->obj_cnt      = t.M;
+    out->morton_count = t.P2;
+    out->leaf_count   = t.L;
+    out->int_count    = t.I;
+    for (int d = 0; d < 3; d++) {
+        out->bmin[d] = t.bmin[d];
+        out->bmax[d] = t.bmax[d];
+    }
+    out->d_sorted_morton   = t.morton.p;
+    out->d_sort_index_map  = t.index_map.p;
+    out->d_reduc_index_map = t.reduc_index_map.p;
+    out->d_reduced_morton  = t.reduced_morton.p;
+    out->d_lchild_id       = t.lchild.p;
+    out->d_rchild_id       = t.rchild.p;
+    out->d_endrange        = t.endrange.p;
+    out->d_lchild_flag     = t.lflag.p;
+    out->d_rchild_flag     = t.rflag.p;
+    out->d_aabb_min        = t.aabb_min.p;
+    out->d_aabb_max        = t.aabb_max.p;
+}
+} // namespace
+
+extern "C" {
+
+const char *shamb200_last_error(void) { return g_err.c_str(); }
+const char *shamb200_build_info(void) {
+#ifdef SB_FAST_MATH
+    return "shamb200 sm_100a fp=fast(fma) tree=strict";
+#else
+    return "shamb200 sm_100a fp=strict(no-fma, bit-exact with the oracle)";
+#endif
+}
+uint64_t shamb200_launch_count(void) { return g_launch_count; }
+void shamb200_reset_launch_count(void) { g_launch_count = 0; }
+
+int shamb200_ctx_create(int device, void *cuda_stream, shamb200_ctx **out) {
+    return guard([&] {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            throw CudaError(
+                std::string("no CUDA device available (") + cudaGetErrorString(e)
+                + "): shamb200 has no CPU fallback");
+        if (device < 0 || device >= ndev)
+            throw std::invalid_argument("invalid device index");
+        SB_CUDA_CHECK(cudaSetDevice(device));
+        auto *c     = new shamb200_ctx();
+        c->c.device = device;
+        if (cuda_stream) {
+            c->c.stream     = (cudaStream_t) cuda_stream;
+            c->c.own_stream = false;
+        } else {
+            SB_CUDA_CHECK(cudaStreamCreateWithFlags(&c->c.stream, cudaStreamNonBlocking));
+            c->c.own_stream = true;
+        }
+        *out = c;
+    });
+}
+int shamb200_ctx_destroy(shamb200_ctx *ctx) {
+    return guard([&] {
+        if (!ctx)
+            return;
+        cudaSetDevice(ctx->c.device);
+        cudaStreamSynchronize(ctx->c.stream);
+        if (ctx->c.own_stream)
+            cudaStreamDestroy(ctx->c.stream);
+        delete ctx;
+    });
+}
+void *shamb200_ctx_stream(shamb200_ctx *ctx) { return ctx ? (void *) ctx->c.stream : nullptr; }
+int shamb200_ctx_synchronize(shamb200_ctx *ctx) {
+    return guard([&] { SB_CUDA_CHECK(cudaStreamSynchronize(ctx->c.stream)); });
+}
+
+int shamb200_tree_build(
+    shamb200_ctx *ctx, const double *d_xyz, size_t stride_dbl, uint32_t obj_cnt, const double bmin[3],
+    const double bmax[3], uint32_t reduction_level, int sort_mode, shamb200_tree *out) {
+    return guard([&] {
+        SB_CUDA_CHECK(cudaSetDevice(ctx->c.device));
+        tree_build(ctx->c.stream, ctx->c.api_tree, d_xyz, stride_dbl, obj_cnt, bmin, bmax, false, reduction_level, sort_mode);
+        fill_tree_view(ctx->c.api_tree, out);
+    });
+}
+int shamb200_tree_build_auto_bbox(
+    shamb200_ctx *ctx, const double *d_xyz, size_t stride_dbl, uint32_t obj_cnt, uint32_t reduction_level,
+    int sort_mode, shamb200_tree *out) {
+    return guard([&] {
+        SB_CUDA_CHECK(cudaSetDevice(ctx->c.device));
+        tree_build(ctx->c.stream, ctx->c.api_tree, d_xyz, stride_dbl, obj_cnt, nullptr, nullptr, true, reduction_level, sort_mode);
+        fill_tree_view(ctx->c.api_tree, out);
+    });
+}
+int shamb200_tree_field_max(
+    shamb200_ctx *ctx, const shamb200_tree *tree, const double *d_field, double scale, double *d_out) {
+    return guard([&] {
+        if (tree->d_sort_index_map != ctx->c.api_tree.index_map.p)
+            throw std::invalid_argument("the tree view is stale (not the last tree built by this context)");
+        tree_field_max(ctx->c.stream, ctx->c.api_tree, d_field, scale, d_out, 1);
+    });
+}
+
+int shamb200_neigh_cache_build(
+    shamb200_ctx *ctx, const shamb200_tree *tree, const double *d_xyz, size_t stride_dbl, const double *d_hpart,
+    const double *d_rint, uint32_t obj_cnt, double Rkern, double h_tolerance, int two_stage, shamb200_csr *out) {
+    return guard([&] {
+        if (tree->d_sort_index_map != ctx->c.api_tree.index_map.p)
+            throw std::invalid_argument("the tree view is stale (not the last tree built by this context)");
+        neigh_cache_build(
+            ctx->c.stream, ctx->c.api_tree, ctx->c.api_nb, d_xyz, stride_dbl, d_hpart, d_rint, obj_cnt, Rkern,
+            h_tolerance, two_stage != 0, 1);
+        out->obj_cnt           = ctx->c.api_nb.N;
+        out->sum_neigh_cnt     = ctx->c.api_nb.K;
+        out->d_cnt_neigh       = ctx->c.api_nb.cnt.p;
+        out->d_scanned_cnt     = ctx->c.api_nb.scanned.p;
+        out->d_index_neigh_map = ctx->c.api_nb.list.p;
+    });
+}
+
+static void ctx_reset_red(Ctx &c) {
+    c.red.ensure(8);
+    c.h_red.ensure(8);
+    c.h_red.p[0] = 0;
+    c.h_red.p[1] = 0xFFFFFFFFFFFFFFFFull;
+    SB_CUDA_CHECK(cudaMemcpyAsync(c.red.p, c.h_red.p, 2 * sizeof(u64), cudaMemcpyHostToDevice, c.stream));
+}
+
+int shamb200_h_iterate(
+    shamb200_ctx *ctx, int kernel, const shamb200_csr *csr, const double *d_xyz, size_t stride_dbl,
+    const double *d_h_old, double *d_h_new, double *d_eps, double gpart_mass, double h_evol_max,
+    double h_evol_iter_max) {
+    return guard([&] {
+        ctx_reset_red(ctx->c);
+        CsrView c{csr->d_cnt_neigh, csr->d_scanned_cnt, csr->d_index_neigh_map, csr->obj_cnt};
+        h_iterate(ctx->c.stream, kernel, c, d_xyz, stride_dbl, nullptr, 0, d_h_old, d_h_new, d_eps, gpart_mass, h_evol_max, h_evol_iter_max, ctx->c.red.p);
+    });
+}
+int shamb200_h_iterate_loop(
+    shamb200_ctx *ctx, int kernel, const shamb200_csr *csr, const double *d_xyz, size_t stride_dbl,
+    const double *d_h_old, double *d_h_new, double *d_eps, double gpart_mass, double h_evol_max,
+    double h_evol_iter_max, double epsilon_h, uint32_t max_sweeps, double out3[3]) {
+    return guard([&] {
+        CsrView c{csr->d_cnt_neigh, csr->d_scanned_cnt, csr->d_index_neigh_map, csr->obj_cnt};
+        f64 mx = std::numeric_limits<f64>::max(), mn = -1;
+        u32 it = 0;
+        for (; it < max_sweeps; it++) {
+            ctx_reset_red(ctx->c);
+            h_iterate(ctx->c.stream, kernel, c, d_xyz, stride_dbl, nullptr, 0, d_h_old, d_h_new, d_eps, gpart_mass, h_evol_max, h_evol_iter_max, ctx->c.red.p);
+            SB_CUDA_CHECK(cudaMemcpyAsync(ctx->c.h_red.p + 2, ctx->c.red.p, 2 * sizeof(u64), cudaMemcpyDeviceToHost, ctx->c.stream));
+            SB_CUDA_CHECK(cudaStreamSynchronize(ctx->c.stream));
+            mx = ordered_to_f64(ctx->c.h_red.p[2]);
+            mn = ordered_to_f64(ctx->c.h_red.p[3]);
+            if (mx < epsilon_h)
+                break;
+        }
+        out3[0] = mx;
+        out3[1] = mn;
+        out3[2] = f64(it);
+    });
+}
+int shamb200_compute_omega(
+    shamb200_ctx *ctx, int kernel, const shamb200_csr *csr, const double *d_xyz, size_t stride_dbl,
+    const double *d_hpart, double *d_omega, double gpart_mass) {
+    return guard([&] {
+        CsrView c{csr->d_cnt_neigh, csr->d_scanned_cnt, csr->d_index_neigh_map, csr->obj_cnt};
+        compute_omega(ctx->c.stream, kernel, c, d_xyz, stride_dbl, nullptr, 0, d_hpart, d_omega, gpart_mass);
+    });
+}
+
+// ---- model --------------------------------------------------------------------------------------
+void shamb200_solver_config_default(shamb200_solver_config *cfg) {
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->kernel     = SHAMB200_KERNEL_M4;
+    cfg->eos        = SHAMB200_EOS_ADIABATIC;
+    cfg->av         = SHAMB200_AV_CONSTANT;
+    cfg->bc         = SHAMB200_BC_FREE;
+    cfg->gpart_mass = 0;
+    cfg->gamma      = 5. / 3.;
+    cfg->cs0        = 1;
+    cfg->eos_q      = 0;
+    cfg->eos_r0     = 1;
+    cfg->alpha_u    = 1;
+    cfg->alpha_AV   = 1;
+    cfg->beta_AV    = 2;
+    cfg->alpha_min  = 0.1;
+    cfg->alpha_max  = 1;
+    cfg->sigma_decay = 0.1;
+    cfg->cfl_cour    = 0.3;
+    cfg->cfl_force   = 0.25;
+    cfg->cfl_multiplier_stiffness = 2;
+    cfg->htol_up_coarse_cycle     = 1.1;
+    cfg->htol_up_fine_cycle       = 1.1;
+    cfg->epsilon_h                = 1e-6;
+    cfg->h_iter_per_subcycles     = 50;
+    cfg->h_max_subcycles_count    = 100;
+    cfg->tree_reduction_level     = 3;
+    cfg->use_two_stage_search     = 1;
+    cfg->sort_mode                = SHAMB200_SORT_BITONIC;
+    cfg->constant_G               = 1;
+}
+
+int shamb200_model_create(shamb200_ctx *ctx, const shamb200_solver_config *cfg, shamb200_model **out) {
+    return guard([&] {
+        if (!ctx)
+            throw std::invalid_argument("null context");
+        *out = new shamb200_model(&ctx->c, *cfg);
+    });
+}
+int shamb200_model_destroy(shamb200_model *m) {
+    return guard([&] {
+        if (m) {
+            cudaSetDevice(m->m.ctx->device);
+            cudaStreamSynchronize(m->m.ctx->stream);
+            comm_destroy(m->m);
+            delete m;
+        }
+    });
+}
+int shamb200_model_set_config(shamb200_model *m, const shamb200_solver_config *cfg) {
+    return guard([&] { m->m.cfg = *cfg; });
+}
+int shamb200_model_set_box(shamb200_model *m, const double bmin[3], const double bmax[3], uint32_t nx, uint32_t ny, uint32_t nz) {
+    return guard([&] { m->m.set_box(bmin, bmax, nx, ny, nz); });
+}
+int shamb200_model_push_particles(shamb200_model *m, uint64_t n, const double *xyz, const double *vxyz, const double *hpart, const double *uint_) {
+    return guard([&] { m->m.push_particles(n, xyz, vxyz, hpart, uint_); });
+}
+uint32_t shamb200_model_patch_count(shamb200_model *m) { return (uint32_t) m->m.patches.size(); }
+int shamb200_model_patch_is_local(shamb200_model *m, uint32_t ip) {
+    return ip < m->m.patches.size() && m->m.is_local(m->m.patches[ip]);
+}
+uint32_t shamb200_model_patch_size(shamb200_model *m, uint32_t ip) {
+    if (ip >= m->m.patches.size() || !m->m.is_local(m->m.patches[ip]))
+        return 0;
+    return m->m.patches[ip].f.n;
+}
+int64_t shamb200_model_get(shamb200_model *m, uint32_t ip, const char *name, void *out, int64_t cap_bytes) {
+    int64_t r = -1;
+    int rc    = guard([&] { r = m->m.get(ip, name, out, cap_bytes); });
+    return rc == SHAMB200_OK ? r : -2;
+}
+int shamb200_model_set_field(shamb200_model *m, uint32_t ip, const char *name, const double *in, uint64_t count) {
+    return guard([&] { m->m.set_field(ip, name, in, count); });
+}
+int shamb200_model_evolve_once(shamb200_model *m) {
+    return guard([&] { m->m.evolve_once(); });
+}
+int shamb200_model_state(shamb200_model *m, double out[12]) {
+    return guard([&] {
+        Model &M = m->m;
+        u64 nloc = 0;
+        for (auto &p : M.patches)
+            if (M.is_local(p))
+                nloc += p.f.n;
+        out[0]  = M.time;
+        out[1]  = M.dt;
+        out[2]  = M.cfl_multiplier;
+        out[3]  = M.eps_v;
+        out[4]  = M.h_subcycles;
+        out[5]  = M.h_iters_last;
+        out[6]  = M.corrector_iter;
+        out[7]  = f64(M.npart_all);
+        out[8]  = M.t_step;
+        out[9]  = M.t_step > 0 ? f64(nloc) / M.t_step : 0;
+        out[10] = f64(M.K_local);
+        out[11] = f64(nloc);
+    });
+}
+int shamb200_model_set_next_dt(shamb200_model *m, double dt) {
+    return guard([&] { m->m.dt = dt; });
+}
+int shamb200_model_set_time(shamb200_model *m, double t) {
+    return guard([&] { m->m.time = t; });
+}
+int shamb200_model_set_cfl_multiplier(shamb200_model *m, double v) {
+    return guard([&] { m->m.cfl_multiplier = v; });
+}
+int shamb200_model_stage_times(shamb200_model *m, const char **names, const double **ms, uint32_t *count) {
+    return guard([&] {
+        *names = m->m.timer.names_joined.c_str();
+        *ms    = m->m.timer.values.data();
+        *count = (uint32_t) m->m.timer.values.size();
+    });
+}
+
+// NCCL entry points live in solver_comm.cu
+} // extern "C"

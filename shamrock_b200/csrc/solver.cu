@@ -1,0 +1,930 @@
+// solver.cu — Solver::evolve_once on the GPU: the host-side driver of the B200 SPH step.
+//
+// Follows shammodels/sph/src/Solver.cpp:1942-3272 (evolve_once), :1060-1304 (sph_prestep),
+// :1394-1633 (communicate_merge_ghosts_fields), shammodels/sph/src/BasicSPHGhosts.cpp:261-579 and
+// shammodels/sph/include/shammodels/sph/{BasicSPHGhosts,SPHUtilities}.hpp (ghost zones) — paths
+// relative to /root/reference/src.  Every device operation is a hand-written kernel of this
+// library; there is no CPU fallback for any stage.
+#include "solver.cuh"
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+namespace sb {
+
+static constexpr u64 PATCH_GRID = 1ull << 21; // PatchScheduler::max_axis_patch_coord_length
+
+// ---------------------------------------------------------------------------------------------
+// PatchFields
+// ---------------------------------------------------------------------------------------------
+std::vector<PatchFields::Ref> PatchFields::all() {
+    return {{"xyz", &xyz, 3},         {"vxyz", &vxyz, 3},   {"axyz", &axyz, 3},
+            {"axyz_ext", &axyz_ext, 3}, {"hpart", &hpart, 1}, {"uint", &uint_, 1},
+            {"duint", &duint, 1},     {"alpha_AV", &alpha_AV, 1}, {"divv", &divv, 1},
+            {"dtdivv", &dtdivv, 1},   {"curlv", &curlv, 3}, {"soundspeed", &soundspeed, 1}};
+}
+void PatchFields::reserve(u32 cap, cudaStream_t s) {
+    for (auto &r : all())
+        r.buf->ensure_keep(size_t(cap) * r.nvar, size_t(n) * r.nvar, s, 1.25);
+}
+
+// ---------------------------------------------------------------------------------------------
+// StageTimer
+// ---------------------------------------------------------------------------------------------
+void StageTimer::begin_step() { marks.clear(); }
+void StageTimer::mark(cudaStream_t s, const char *name) {
+    int idx = int(marks.size());
+    if (idx >= int(pool.size())) {
+        cudaEvent_t e;
+        SB_CUDA_CHECK(cudaEventCreate(&e));
+        pool.push_back(e);
+    }
+    SB_CUDA_CHECK(cudaEventRecord(pool[idx], s));
+    marks.emplace_back(name, idx);
+}
+void StageTimer::end_step(cudaStream_t s) {
+    mark(s, "end");
+    SB_CUDA_CHECK(cudaEventSynchronize(pool[marks.back().second]));
+    acc.clear();
+    order.clear();
+    for (size_t k = 0; k + 1 < marks.size(); k++) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, pool[marks[k].second], pool[marks[k + 1].second]);
+        if (!acc.count(marks[k].first))
+            order.push_back(marks[k].first);
+        acc[marks[k].first] += ms;
+    }
+    names_joined.clear();
+    values.clear();
+    for (auto &n : order) {
+        if (!names_joined.empty())
+            names_joined += ";";
+        names_joined += n;
+        values.push_back(acc[n]);
+    }
+}
+StageTimer::~StageTimer() {
+    for (auto e : pool)
+        cudaEventDestroy(e);
+}
+
+// ---------------------------------------------------------------------------------------------
+// small device helpers local to the solver
+// ---------------------------------------------------------------------------------------------
+/// red slots: 0 eps max, 1 eps min, 2 eps_v² max, 3 Σv² (f64 bits), 4 cfl min, 8.. per-patch h max
+__global__ void reset_red_kernel(u64 *red, int n) {
+    int i = threadIdx.x;
+    if (i >= n)
+        return;
+    u64 v = 0; // max accumulators (ordered encoding: 0 is below every double) and the f64 sum
+    if (i == 1 || i == 4)
+        v = 0xFFFFFFFFFFFFFFFFull; // min accumulators
+    red[i] = v;
+}
+constexpr int RED_SLOTS = 8 + 256;
+
+void Model::reset_red() {
+    red.ensure(RED_SLOTS);
+    h_red.ensure(RED_SLOTS);
+    reset_red_kernel<<<1, 512, 0, s()>>>(red.p, RED_SLOTS);
+    SB_COUNT_LAUNCH();
+}
+void Model::read_red(int n) {
+    SB_CUDA_CHECK(cudaMemcpyAsync(h_red.p, red.p, size_t(n) * sizeof(u64), cudaMemcpyDeviceToHost, s()));
+    SB_CUDA_CHECK(cudaStreamSynchronize(s()));
+}
+static f64 bits_to_f64(u64 b) {
+    f64 d;
+    std::memcpy(&d, &b, 8);
+    return d;
+}
+
+/// counts[b] = number of particles inside box b ([lo,hi) per axis); boxes: nb*6 doubles
+__global__ void __launch_bounds__(256) count_in_boxes_kernel(
+    u32 n, const f64 *__restrict__ xyz, u32 nb, const f64 *__restrict__ boxes, u32 *__restrict__ counts) {
+    extern __shared__ u32 sc[];
+    for (u32 j = threadIdx.x; j < nb; j += blockDim.x)
+        sc[j] = 0;
+    __syncthreads();
+    for (u64 i = u64(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += u64(gridDim.x) * blockDim.x) {
+        f64 x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+        for (u32 b = 0; b < nb; b++) {
+            const f64 *q = boxes + 6 * b;
+            if (q[0] <= x && x < q[3] && q[1] <= y && y < q[4] && q[2] <= z && z < q[5])
+                atomicAdd(&sc[b], 1u);
+        }
+    }
+    __syncthreads();
+    for (u32 j = threadIdx.x; j < nb; j += blockDim.x)
+        if (sc[j])
+            atomicAdd(&counts[j], sc[j]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// setup
+// ---------------------------------------------------------------------------------------------
+void Model::set_box(const f64 bmin[3], const f64 bmax[3], u32 nx, u32 ny, u32 nz) {
+    auto pow2 = [](u32 v) { return v && !(v & (v - 1)); };
+    if (!pow2(nx) || !pow2(ny) || !pow2(nz))
+        throw std::invalid_argument("the patch grid must be made of powers of two");
+    for (int d = 0; d < 3; d++) {
+        box_min[d] = bmin[d];
+        box_max[d] = bmax[d];
+    }
+    patches.clear();
+    u32 nn[3]  = {nx, ny, nz};
+    u32 np     = nx * ny * nz;
+    patches.resize(np);
+    for (u32 z = 0; z < nz; z++)
+        for (u32 y = 0; y < ny; y++)
+            for (u32 x = 0; x < nx; x++) {
+                u32 k     = x + nx * (y + ny * z);
+                PatchD &p = patches[k];
+                p.id      = k;
+                u32 c[3]  = {x, y, z};
+                for (int d = 0; d < 3; d++) {
+                    u64 sz    = PATCH_GRID / nn[d];
+                    p.cmin[d] = sz * c[d];
+                    p.cmax[d] = sz * (c[d] + 1) - 1;
+                    // CoordRangeTransform<u64_3,f64_3> "multiply": obj = f64(pc) * fact + bmin
+                    f64 fact = (box_max[d] - box_min[d]) / f64(PATCH_GRID);
+                    p.lo[d]  = f64(p.cmin[d]) * fact + box_min[d];
+                    p.hi[d]  = f64(p.cmax[d] + 1) * fact + box_min[d];
+                }
+                // contiguous blocks of patches per rank (ids ascending)
+                p.owner = int((u64(k) * u64(world)) / np);
+            }
+    std::vector<f64> hb(size_t(np) * 6);
+    for (u32 k = 0; k < np; k++)
+        for (int d = 0; d < 3; d++) {
+            hb[6 * k + d]     = patches[k].lo[d];
+            hb[6 * k + 3 + d] = patches[k].hi[d];
+        }
+    d_boxes.ensure(hb.size());
+    SB_CUDA_CHECK(cudaMemcpyAsync(d_boxes.p, hb.data(), hb.size() * sizeof(f64), cudaMemcpyHostToDevice, s()));
+    SB_CUDA_CHECK(cudaStreamSynchronize(s()));
+}
+
+void Model::push_particles(u64 n, const f64 *xyz, const f64 *vxyz, const f64 *h, const f64 *u) {
+    if (patches.empty())
+        throw std::runtime_error("the box size is not set, please resize the box to the domain size");
+    // host-side binning (setup path, not the hot path)
+    size_t np = patches.size();
+    std::vector<std::vector<u64>> bins(np);
+    for (u64 i = 0; i < n; i++) {
+        int own = -1;
+        for (size_t k = 0; k < np; k++) {
+            const PatchD &p = patches[k];
+            if (p.lo[0] <= xyz[3 * i] && xyz[3 * i] < p.hi[0] && p.lo[1] <= xyz[3 * i + 1]
+                && xyz[3 * i + 1] < p.hi[1] && p.lo[2] <= xyz[3 * i + 2] && xyz[3 * i + 2] < p.hi[2]) {
+                own = int(k);
+                break;
+            }
+        }
+        if (own < 0) {
+            if (np == 1)
+                own = 0;
+            else
+                throw std::runtime_error("particle outside of the simulation box");
+        }
+        bins[own].push_back(i);
+    }
+    for (size_t k = 0; k < np; k++) {
+        PatchD &p = patches[k];
+        if (!is_local(p) || bins[k].empty())
+            continue;
+        u32 add  = u32(bins[k].size());
+        u32 newn = p.f.n + add;
+        p.f.reserve(newn, s());
+        auto up = [&](DevBuf<f64> &buf, int nv, const f64 *src) {
+            host_tmp.assign(size_t(add) * nv, 0.);
+            if (src)
+                for (u32 q = 0; q < add; q++)
+                    for (int c = 0; c < nv; c++)
+                        host_tmp[size_t(q) * nv + c] = src[bins[k][q] * nv + c];
+            SB_CUDA_CHECK(cudaMemcpyAsync(
+                buf.p + size_t(p.f.n) * nv, host_tmp.data(), host_tmp.size() * sizeof(f64),
+                cudaMemcpyHostToDevice, s()));
+            SB_CUDA_CHECK(cudaStreamSynchronize(s()));
+        };
+        for (auto &r : p.f.all()) {
+            const f64 *src = nullptr;
+            std::string nm(r.name);
+            if (nm == "xyz")
+                src = xyz;
+            else if (nm == "vxyz")
+                src = vxyz;
+            else if (nm == "hpart")
+                src = h;
+            else if (nm == "uint")
+                src = u;
+            up(*r.buf, r.nvar, src);
+        }
+        p.f.n = newn;
+    }
+}
+
+void Model::set_field(u32 ip, const std::string &name, const f64 *in, u64 count) {
+    PatchD &p = patches.at(ip);
+    if (!is_local(p))
+        throw std::invalid_argument("patch is not local");
+    for (auto &r : p.f.all())
+        if (name == r.name) {
+            if (count != u64(p.f.n) * r.nvar)
+                throw std::invalid_argument("field size mismatch for " + name);
+            SB_CUDA_CHECK(cudaMemcpyAsync(r.buf->p, in, count * sizeof(f64), cudaMemcpyHostToDevice, s()));
+            SB_CUDA_CHECK(cudaStreamSynchronize(s()));
+            return;
+        }
+    throw std::invalid_argument("unknown field " + name);
+}
+
+// ---------------------------------------------------------------------------------------------
+// field access (ctx.collect_data equivalent + step internals for the parity tests)
+// ---------------------------------------------------------------------------------------------
+template<class T>
+static int64_t copy_dev(cudaStream_t s, const T *d, size_t n, void *out, int64_t cap) {
+    int64_t nb = int64_t(n * sizeof(T));
+    if (out && cap >= nb && nb > 0) {
+        SB_CUDA_CHECK(cudaMemcpyAsync(out, d, size_t(nb), cudaMemcpyDeviceToHost, s));
+        SB_CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+    return nb;
+}
+
+int64_t Model::get(u32 ip, const std::string &name, void *out, int64_t cap) {
+    if (ip >= patches.size())
+        return -1;
+    PatchD &p = patches[ip];
+    if (!is_local(p))
+        return 0;
+    for (auto &r : p.f.all())
+        if (name == r.name)
+            return copy_dev(s(), r.buf->p, size_t(p.f.n) * r.nvar, out, cap);
+    PatchStep &st = p.st;
+    auto packc    = [&](const Pack4 *P, u32 cnt, int first, int nc) -> int64_t {
+        int64_t nb = int64_t(size_t(cnt) * nc * sizeof(f64));
+        if (out && cap >= nb && nb > 0) {
+            field_tmp.ensure(size_t(cnt) * nc);
+            unpack_comp(s(), cnt, P, first, nc, field_tmp.p);
+            return copy_dev(s(), field_tmp.p, size_t(cnt) * nc, out, cap);
+        }
+        return nb;
+    };
+    if (name == "step.mxyz") return packc(st.A.p, st.m, 0, 3);
+    if (name == "step.mh") return cfg.keep_step_data ? copy_dev(s(), st.mh_snapshot.p, st.m, out, cap) : -1;
+    if (name == "step.g_h") return packc(st.A.p, st.m, 3, 1);
+    if (name == "step.g_v") return packc(st.B.p, st.m, 0, 3);
+    if (name == "step.g_u") return packc(st.B.p, st.m, 3, 1);
+    if (name == "step.pressure") return packc(st.C.p, st.m, 0, 1);
+    if (name == "step.g_omega") return packc(st.C.p, st.m, 1, 1);
+    if (name == "step.soundspeed") return packc(st.C.p, st.m, 2, 1);
+    if (name == "step.g_alpha") return packc(st.C.p, st.m, 3, 1);
+    if (name == "step.g_a") return packc(st.D.p, st.m, 0, 3);
+    if (name == "step.rint") return copy_dev(s(), st.rint.p, size_t(st.tree.I) + st.tree.L, out, cap);
+    if (name == "step.omega") return copy_dev(s(), st.omega.p, st.n, out, cap);
+    if (name == "step.alpha_updated") return copy_dev(s(), st.alpha_updated.p, st.n, out, cap);
+    if (name == "step.vsig") return copy_dev(s(), st.vsig.p, st.n, out, cap);
+    if (name == "step.cfl_dt") return copy_dev(s(), st.cfl_dt.p, st.n, out, cap);
+    const TreeBuffers &t = st.tree;
+    if (name == "tree.sorted_morton") return copy_dev(s(), t.morton.p, t.P2, out, cap);
+    if (name == "tree.sort_index_map") return copy_dev(s(), t.index_map.p, t.P2, out, cap);
+    if (name == "tree.reduc_index_map") return copy_dev(s(), t.reduc_index_map.p, size_t(t.L) + 2, out, cap);
+    if (name == "tree.reduced_morton") return copy_dev(s(), t.reduced_morton.p, t.L, out, cap);
+    if (name == "tree.lchild_id") return copy_dev(s(), t.lchild.p, t.I, out, cap);
+    if (name == "tree.rchild_id") return copy_dev(s(), t.rchild.p, t.I, out, cap);
+    if (name == "tree.lchild_flag") return copy_dev(s(), t.lflag.p, t.I, out, cap);
+    if (name == "tree.rchild_flag") return copy_dev(s(), t.rflag.p, t.I, out, cap);
+    if (name == "tree.endrange") return copy_dev(s(), t.endrange.p, t.I, out, cap);
+    if (name == "tree.aabb_min") return copy_dev(s(), t.aabb_min.p, (size_t(t.I) + t.L) * 3, out, cap);
+    if (name == "tree.aabb_max") return copy_dev(s(), t.aabb_max.p, (size_t(t.I) + t.L) * 3, out, cap);
+    if (name == "cache.cnt_neigh") return copy_dev(s(), st.nb.cnt.p, st.nb.N, out, cap);
+    if (name == "cache.scanned_cnt") return copy_dev(s(), st.nb.scanned.p, st.nb.N, out, cap);
+    if (name == "cache.index_neigh_map") return copy_dev(s(), st.nb.list.p, st.nb.K, out, cap);
+    return -1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// particle removal / migration (order preserving)
+// ---------------------------------------------------------------------------------------------
+/// keep the particles whose `flag` is set, in order (PatchDataLayer::keep_ids semantics)
+void Model::keep_flagged(PatchD &p, u32 *out_kept) {
+    u32 n = p.f.n;
+    pos.ensure(n);
+    exclusive_scan<u8>(s(), flag.p, pos.p, n, scan_tmp, red.p + 5);
+    SB_CUDA_CHECK(cudaMemcpyAsync(h_red.p + 5, red.p + 5, sizeof(u64), cudaMemcpyDeviceToHost, s()));
+    SB_CUDA_CHECK(cudaStreamSynchronize(s()));
+    u32 kept = u32(h_red.p[5]);
+    if (out_kept)
+        *out_kept = kept;
+    if (kept == n)
+        return;
+    owner_tmp.ensure(n);
+    scatter_ids(s(), n, flag.p, pos.p, owner_tmp.p);
+    for (auto &r : p.f.all()) {
+        field_tmp.ensure(size_t(kept) * r.nvar + 1);
+        gather_field(s(), kept, r.nvar, owner_tmp.p, r.buf->p, field_tmp.p);
+        SB_CUDA_CHECK(cudaMemcpyAsync(
+            r.buf->p, field_tmp.p, size_t(kept) * r.nvar * sizeof(f64), cudaMemcpyDeviceToDevice, s()));
+    }
+    p.f.n = kept;
+}
+
+/// ExternalForces::point_mass_accrete_particles (ExternalForces.cpp:593-700)
+void Model::point_mass_accrete_particles() {
+    if (!cfg.has_point_mass)
+        return;
+    const f64 c[3] = {0, 0, 0};
+    for (auto &p : patches) {
+        if (!is_local(p) || !p.f.n)
+            continue;
+        flag.ensure(p.f.n);
+        flag_sphere(s(), p.f.n, p.f.xyz.p, c, cfg.pm_racc, 0, flag.p);
+        keep_flagged(p);
+    }
+}
+/// "part killing step" (Solver.cpp:526-578)
+void Model::kill_particles() {
+    for (int k = 0; k < cfg.n_kill_spheres; k++)
+        for (auto &p : patches) {
+            if (!is_local(p) || !p.f.n)
+                continue;
+            flag.ensure(p.f.n);
+            flag_sphere(s(), p.f.n, p.f.xyz.p, cfg.kill_center[k], cfg.kill_radius[k], 1, flag.p);
+            keep_flagged(p);
+        }
+}
+/// ExternalForces::compute_ext_forces_indep_v (ExternalForces.cpp:49-323)
+void Model::compute_ext_forces_indep_v() {
+    for (auto &p : patches) {
+        if (!is_local(p) || !p.f.n)
+            continue;
+        SB_CUDA_CHECK(cudaMemsetAsync(p.f.axyz_ext.p, 0, size_t(p.f.n) * 3 * sizeof(f64), s()));
+        if (cfg.has_point_mass)
+            ext_force_point_mass(s(), p.f.n, p.f.xyz.p, p.f.axyz_ext.p, cfg.pm_mass, cfg.constant_G);
+    }
+}
+
+/// Solver::apply_position_boundary (Solver.cpp:938-981)
+void Model::apply_position_boundary() {
+    if (cfg.bc == SHAMB200_BC_PERIODIC)
+        for (auto &p : patches)
+            if (is_local(p) && p.f.n)
+                periodic_wrap(s(), p.f.n, p.f.xyz.p, box_min, box_max);
+    reattribute_patch_objects();
+}
+
+/// ReattributeDataUtility::reatribute_patch_objects (ReattributeDataUtility.hpp:40-230)
+void Model::reattribute_patch_objects() {
+    size_t np = patches.size();
+    if (np == 1)
+        return; // single patch: periodic → everything is inside after the wrap; free → no constraint
+    if (world > 1)
+        throw std::runtime_error("particle migration between ranks: see solver_comm.cu");
+    // owners and stay flags per patch
+    struct Mig {
+        u32 src, dst, count;
+        DevBuf<u32> ids;
+    };
+    std::vector<Mig> migs;
+    std::vector<DevBuf<u32>> owners(np);
+    std::vector<u32> kept(np, 0);
+    bool any = false;
+    for (size_t k = 0; k < np; k++) {
+        PatchD &p = patches[k];
+        if (!p.f.n)
+            continue;
+        flag.ensure(p.f.n);
+        owners[k].ensure(p.f.n);
+        patch_owner(s(), p.f.n, p.f.xyz.p, u32(np), d_boxes.p, u32(k), flag.p, owners[k].p);
+        pos.ensure(p.f.n);
+        exclusive_scan<u8>(s(), flag.p, pos.p, p.f.n, scan_tmp, red.p + 5);
+        SB_CUDA_CHECK(cudaMemcpyAsync(h_red.p + 5, red.p + 5, sizeof(u64), cudaMemcpyDeviceToHost, s()));
+        SB_CUDA_CHECK(cudaStreamSynchronize(s()));
+        kept[k] = u32(h_red.p[5]);
+        if (kept[k] == p.f.n)
+            continue;
+        any = true;
+        for (size_t d = 0; d < np; d++) {
+            if (d == k)
+                continue;
+            flag_equal(s(), p.f.n, owners[k].p, u32(d), flag.p);
+            exclusive_scan<u8>(s(), flag.p, pos.p, p.f.n, scan_tmp, red.p + 5);
+            SB_CUDA_CHECK(cudaMemcpyAsync(h_red.p + 5, red.p + 5, sizeof(u64), cudaMemcpyDeviceToHost, s()));
+            SB_CUDA_CHECK(cudaStreamSynchronize(s()));
+            u32 cnt = u32(h_red.p[5]);
+            if (!cnt)
+                continue;
+            Mig m;
+            m.src   = u32(k);
+            m.dst   = u32(d);
+            m.count = cnt;
+            m.ids.ensure(cnt);
+            scatter_ids(s(), p.f.n, flag.p, pos.p, m.ids.p);
+            migs.push_back(std::move(m));
+        }
+        // particles owned by nobody (outside the box with free boundaries) cannot be attributed
+        u32 moved = 0;
+        for (auto &m : migs)
+            if (m.src == k)
+                moved += m.count;
+        if (kept[k] + moved != p.f.n)
+            throw std::runtime_error("a new id could not be computed");
+    }
+    if (!any)
+        return;
+    // stage the migrants (all fields) before compacting the sources
+    struct Staged {
+        std::vector<DevBuf<f64>> f;
+    };
+    std::vector<Staged> staged(migs.size());
+    for (size_t q = 0; q < migs.size(); q++) {
+        PatchD &src = patches[migs[q].src];
+        auto refs   = src.f.all();
+        staged[q].f.resize(refs.size());
+        for (size_t r = 0; r < refs.size(); r++) {
+            staged[q].f[r].ensure(size_t(migs[q].count) * refs[r].nvar);
+            gather_field(s(), migs[q].count, refs[r].nvar, migs[q].ids.p, refs[r].buf->p, staged[q].f[r].p);
+        }
+    }
+    for (size_t k = 0; k < np; k++) {
+        PatchD &p = patches[k];
+        if (!p.f.n || kept[k] == p.f.n)
+            continue;
+        flag_equal(s(), p.f.n, owners[k].p, u32(k), flag.p);
+        keep_flagged(p);
+    }
+    // append: sender ascending, then receiver (multimap order of part_exchange)
+    for (size_t q = 0; q < migs.size(); q++) {
+        PatchD &dst = patches[migs[q].dst];
+        u32 newn    = dst.f.n + migs[q].count;
+        dst.f.reserve(newn, s());
+        auto refs = dst.f.all();
+        for (size_t r = 0; r < refs.size(); r++)
+            SB_CUDA_CHECK(cudaMemcpyAsync(
+                refs[r].buf->p + size_t(dst.f.n) * refs[r].nvar, staged[q].f[r].p,
+                size_t(migs[q].count) * refs[r].nvar * sizeof(f64), cudaMemcpyDeviceToDevice, s()));
+        dst.f.n = newn;
+    }
+    SB_CUDA_CHECK(cudaStreamSynchronize(s()));
+}
+
+// ---------------------------------------------------------------------------------------------
+// ghost zones
+// ---------------------------------------------------------------------------------------------
+/// SPHUtilities::build_interf_cache + BasicSPHGhostHandler::find_interfaces / gen_id_table_interfaces
+void Model::build_ghost_cache() {
+    const size_t np = patches.size();
+    const f64 Rkern = cfg.kernel == SHAMB200_KERNEL_M4 ? 2.0 : 3.0;
+    if (np > 256)
+        throw std::runtime_error("too many patches");
+    // interactR_patch = max(h) * htol * Rkern  (SPHUtilities.hpp:84-92)
+    reset_red();
+    for (size_t k = 0; k < np; k++)
+        if (is_local(patches[k]) && patches[k].f.n)
+            max_reduce(s(), patches[k].f.n, patches[k].f.hpart.p, red.p + 8 + k);
+    read_red(8 + int(np));
+    std::vector<f64> interactR(np, std::numeric_limits<f64>::lowest());
+    std::vector<u32> pcount(np, 0);
+    for (size_t k = 0; k < np; k++)
+        if (is_local(patches[k]) && patches[k].f.n) {
+            interactR[k] = ordered_to_f64(h_red.p[8 + k]) * cfg.htol_up_coarse_cycle * Rkern;
+            pcount[k]    = patches[k].f.n;
+        }
+    // (multi-rank: interactR / pcount are all-gathered in solver_comm.cu)
+
+    f64 bsize[3] = {box_max[0] - box_min[0], box_max[1] - box_min[1], box_max[2] - box_min[2]};
+    int rep      = (cfg.bc == SHAMB200_BC_PERIODIC) ? 1 : 0;
+    std::vector<Iface> cand;
+    for (i32 xoff = -rep; xoff <= rep; xoff++)
+        for (i32 yoff = -rep; yoff <= rep; yoff++)
+            for (i32 zoff = -rep; zoff <= rep; zoff++) {
+                f64 off[3] = {xoff * bsize[0], yoff * bsize[1], zoff * bsize[2]};
+                for (size_t sd = 0; sd < np; sd++) {
+                    if (!pcount[sd])
+                        continue;
+                    const PatchD &S = patches[sd];
+                    for (size_t rc = 0; rc < np; rc++) {
+                        if (!pcount[rc])
+                            continue;
+                        if (rc == sd && xoff == 0 && yoff == 0 && zoff == 0)
+                            continue;
+                        const PatchD &R = patches[rc];
+                        f64 Rr          = interactR[rc];
+                        bool ok         = true;
+                        Iface itf;
+                        for (int d = 0; d < 3; d++) {
+                            f64 elo = R.lo[d] - Rr, ehi = R.hi[d] + Rr;
+                            f64 so_lo = S.lo[d] + off[d], so_hi = S.hi[d] + off[d];
+                            f64 ilo = std::fmax(elo, so_lo), ihi = std::fmin(ehi, so_hi);
+                            if (!(ihi >= ilo))
+                                ok = false;
+                            f64 moff      = -off[d];
+                            itf.cut_lo[d] = std::fmax(S.lo[d], elo + moff);
+                            itf.cut_hi[d] = std::fmin(S.hi[d], ehi + moff);
+                            itf.offset[d] = off[d];
+                        }
+                        if (!ok)
+                            continue;
+                        itf.sender   = u32(sd);
+                        itf.receiver = u32(rc);
+                        itf.ioff[0]  = xoff;
+                        itf.ioff[1]  = yoff;
+                        itf.ioff[2]  = zoff;
+                        cand.push_back(std::move(itf));
+                    }
+                }
+            }
+    // multimap<(sender,receiver)> order, equal keys in insertion (offset loop) order
+    std::stable_sort(cand.begin(), cand.end(), [&](const Iface &a, const Iface &b) {
+        if (patches[a.sender].id != patches[b.sender].id)
+            return patches[a.sender].id < patches[b.sender].id;
+        return patches[a.receiver].id < patches[b.receiver].id;
+    });
+    // counts of every candidate with a local sender: one kernel per sender patch
+    std::vector<u32> counts(cand.size(), 0);
+    for (size_t sd = 0; sd < np; sd++) {
+        if (!is_local(patches[sd]) || !patches[sd].f.n)
+            continue;
+        std::vector<size_t> mine;
+        for (size_t q = 0; q < cand.size(); q++)
+            if (cand[q].sender == sd)
+                mine.push_back(q);
+        if (mine.empty())
+            continue;
+        std::vector<f64> hb(mine.size() * 6);
+        for (size_t j = 0; j < mine.size(); j++)
+            for (int d = 0; d < 3; d++) {
+                hb[6 * j + d]     = cand[mine[j]].cut_lo[d];
+                hb[6 * j + 3 + d] = cand[mine[j]].cut_hi[d];
+            }
+        field_tmp.ensure(hb.size());
+        box_counts.ensure(mine.size());
+        SB_CUDA_CHECK(cudaMemcpyAsync(field_tmp.p, hb.data(), hb.size() * sizeof(f64), cudaMemcpyHostToDevice, s()));
+        SB_CUDA_CHECK(cudaMemsetAsync(box_counts.p, 0, mine.size() * sizeof(u32), s()));
+        u32 n       = patches[sd].f.n;
+        unsigned nb = (unsigned) std::min<u64>(u64(kNumSM) * 8, (u64(n) + 255) / 256);
+        count_in_boxes_kernel<<<nb, 256, mine.size() * sizeof(u32), s()>>>(
+            n, patches[sd].f.xyz.p, u32(mine.size()), field_tmp.p, box_counts.p);
+        SB_COUNT_LAUNCH();
+        std::vector<u32> hc(mine.size());
+        SB_CUDA_CHECK(cudaMemcpyAsync(hc.data(), box_counts.p, mine.size() * sizeof(u32), cudaMemcpyDeviceToHost, s()));
+        SB_CUDA_CHECK(cudaStreamSynchronize(s()));
+        for (size_t j = 0; j < mine.size(); j++)
+            counts[mine[j]] = hc[j];
+    }
+    // keep the non-empty interfaces ("prevent sending empty patches"), build their id lists
+    ifaces.clear();
+    std::vector<u32> ghost_run(np, 0);
+    for (size_t q = 0; q < cand.size(); q++) {
+        if (!counts[q])
+            continue;
+        Iface itf   = std::move(cand[q]);
+        itf.count   = counts[q];
+        itf.dst_off = ghost_run[itf.receiver];
+        ghost_run[itf.receiver] += itf.count;
+        PatchD &S = patches[itf.sender];
+        if (is_local(S)) {
+            flag.ensure(S.f.n);
+            pos.ensure(S.f.n);
+            flag_in_box(s(), S.f.n, S.f.xyz.p, itf.cut_lo, itf.cut_hi, flag.p);
+            exclusive_scan<u8>(s(), flag.p, pos.p, S.f.n, scan_tmp, red.p + 5);
+            itf.ids.ensure(itf.count);
+            scatter_ids(s(), S.f.n, flag.p, pos.p, itf.ids.p);
+        }
+        ifaces.push_back(std::move(itf));
+    }
+    for (size_t k = 0; k < np; k++) {
+        patches[k].st.n = patches[k].f.n;
+        patches[k].st.m = patches[k].f.n + ghost_run[k];
+    }
+}
+
+/// BasicSPHGhostHandler::build_comm_merge_positions (BasicSPHGhosts.hpp:294-321,476-514)
+void Model::merge_position_ghost() {
+    for (auto &p : patches) {
+        if (!is_local(p) || !p.f.n)
+            continue;
+        PatchStep &st = p.st;
+        st.A.ensure(st.m, 1.1);
+        pack_xyzh(s(), st.n, p.f.xyz.p, p.f.hpart.p, st.A.p);
+    }
+    for (auto &itf : ifaces) {
+        PatchD &R = patches[itf.receiver];
+        PatchD &S = patches[itf.sender];
+        if (is_local(R) && is_local(S))
+            ghost_xyzh(s(), itf.count, itf.ids.p, S.f.xyz.p, S.f.hpart.p, itf.offset, R.st.A.p + R.st.n + itf.dst_off);
+    }
+    if (cfg.keep_step_data)
+        for (auto &p : patches)
+            if (is_local(p) && p.f.n) {
+                p.st.mh_snapshot.ensure(p.st.m);
+                unpack_comp(s(), p.st.m, p.st.A.p, 3, 1, p.st.mh_snapshot.p);
+            }
+}
+
+/// modules::BuildTrees::build_merged_pos_trees (BuildTrees.cpp:26-66)
+void Model::build_merged_pos_trees() {
+    for (auto &p : patches)
+        if (is_local(p) && p.f.n)
+            tree_build(
+                s(), p.st.tree, reinterpret_cast<const f64 *>(p.st.A.p), 4, p.st.m, nullptr, nullptr, true,
+                cfg.tree_reduction_level, cfg.sort_mode);
+}
+/// Solver::compute_presteps_rint (Solver.cpp:1322-1356)
+void Model::compute_presteps_rint() {
+    for (auto &p : patches)
+        if (is_local(p) && p.f.n) {
+            p.st.rint.ensure(size_t(p.st.tree.I) + p.st.tree.L);
+            tree_field_max(
+                s(), p.st.tree, reinterpret_cast<const f64 *>(p.st.A.p) + 3, cfg.htol_up_coarse_cycle,
+                p.st.rint.p, 4);
+        }
+}
+/// Solver::start_neighbors_cache (Solver.cpp:1364-1386)
+void Model::start_neighbors_cache() {
+    const f64 Rkern = cfg.kernel == SHAMB200_KERNEL_M4 ? 2.0 : 3.0;
+    K_local         = 0;
+    for (auto &p : patches)
+        if (is_local(p) && p.f.n) {
+            const f64 *A = reinterpret_cast<const f64 *>(p.st.A.p);
+            neigh_cache_build(
+                s(), p.st.tree, p.st.nb, A, 4, A + 3, p.st.rint.p, p.st.n, Rkern, cfg.htol_up_coarse_cycle,
+                cfg.use_two_stage_search != 0, 4);
+            K_local += p.st.nb.K;
+        }
+}
+
+static CsrView csr_of(const PatchStep &st) { return CsrView{st.nb.cnt.p, st.nb.scanned.p, st.nb.list.p, st.nb.N}; }
+
+/// Solver::sph_prestep (Solver.cpp:1060-1304)
+void Model::sph_prestep() {
+    u32 hstep_cnt = 0;
+    for (; hstep_cnt < cfg.h_max_subcycles_count; hstep_cnt++) {
+        timer.mark(s(), "ghost_cache");
+        build_ghost_cache();
+        timer.mark(s(), "merge_position_ghost");
+        merge_position_ghost();
+        timer.mark(s(), "build_trees");
+        build_merged_pos_trees();
+        timer.mark(s(), "rint");
+        compute_presteps_rint();
+        timer.mark(s(), "neigh_cache");
+        start_neighbors_cache();
+        timer.mark(s(), "h_iteration");
+        if (cfg.gpart_mass == 0)
+            throw std::runtime_error(
+                "invalid gpart_mass 0, this configuration can not converge.\nPlease set it using either "
+                "model.set_particle_mass(pmass) or cfg.set_particle_mass(pmass)");
+        for (auto &p : patches)
+            if (is_local(p) && p.f.n) {
+                PatchStep &st = p.st;
+                st.eps.ensure(st.n);
+                st.h_old.ensure(st.n);
+                fill<f64>(s(), st.eps.p, st.n, 100.);
+                SB_CUDA_CHECK(cudaMemcpyAsync(st.h_old.p, p.f.hpart.p, size_t(st.n) * sizeof(f64), cudaMemcpyDeviceToDevice, s()));
+            }
+        f64 local_max_eps = std::numeric_limits<f64>::max();
+        f64 local_min_eps = -1;
+        u32 iter_h        = 0;
+        for (; iter_h < cfg.h_iter_per_subcycles; iter_h++) {
+            reset_red();
+            for (auto &p : patches)
+                if (is_local(p) && p.f.n) {
+                    PatchStep &st = p.st;
+                    h_iterate(
+                        s(), cfg.kernel, csr_of(st), reinterpret_cast<const f64 *>(st.A.p), 4, st.tree.index_map.p,
+                        st.m, st.h_old.p, p.f.hpart.p, st.eps.p, cfg.gpart_mass, cfg.htol_up_coarse_cycle,
+                        cfg.htol_up_fine_cycle, red.p);
+                }
+            read_red(2);
+            local_max_eps = ordered_to_f64(h_red.p[0]);
+            local_min_eps = ordered_to_f64(h_red.p[1]);
+            if (local_max_eps < cfg.epsilon_h)
+                break;
+        }
+        h_iters_last         = iter_h;
+        bool should_rerun_gz = local_min_eps < 0;
+        bool below_tol       = local_max_eps < cfg.epsilon_h;
+        bool converged       = below_tol && !should_rerun_gz;
+        // (multi-rank: are_all_rank_true in solver_comm.cu)
+        if (!converged)
+            continue;
+        break;
+    }
+    h_subcycles = hstep_cnt + 1;
+    timer.mark(s(), "omega");
+    for (auto &p : patches)
+        if (is_local(p) && p.f.n) {
+            PatchStep &st = p.st;
+            st.omega.ensure(st.n);
+            compute_omega(
+                s(), cfg.kernel, csr_of(st), reinterpret_cast<const f64 *>(st.A.p), 4, st.tree.index_map.p, st.m,
+                p.f.hpart.p, st.omega.p, cfg.gpart_mass);
+        }
+}
+
+/// Solver::communicate_merge_ghosts_fields (Solver.cpp:1394-1633)
+void Model::communicate_merge_ghosts_fields() {
+    const bool has_a = cfg.av == SHAMB200_AV_CD10;
+    for (auto &p : patches) {
+        if (!is_local(p) || !p.f.n)
+            continue;
+        PatchStep &st = p.st;
+        st.B.ensure(st.m, 1.1);
+        st.C.ensure(st.m, 1.1);
+        if (has_a)
+            st.D.ensure(st.m, 1.1);
+        pack_fields(
+            s(), st.n, nullptr, p.f.hpart.p, p.f.vxyz.p, p.f.uint_.p, st.omega.p, has_a ? p.f.axyz.p : nullptr,
+            st.A.p, st.B.p, st.C.p, st.D.p);
+    }
+    for (auto &itf : ifaces) {
+        PatchD &R = patches[itf.receiver];
+        PatchD &S = patches[itf.sender];
+        if (is_local(R) && is_local(S)) {
+            u32 o = R.st.n + itf.dst_off;
+            pack_fields(
+                s(), itf.count, itf.ids.p, S.f.hpart.p, S.f.vxyz.p, S.f.uint_.p, S.st.omega.p,
+                has_a ? S.f.axyz.p : nullptr, R.st.A.p + o, R.st.B.p + o, R.st.C.p + o, has_a ? R.st.D.p + o : nullptr);
+        }
+    }
+}
+
+/// alpha_AV ghost exchange (Solver.cpp:2325-2368)
+void Model::exchange_alpha_ghosts() {
+    for (auto &p : patches)
+        if (is_local(p) && p.f.n)
+            pack_alpha(s(), p.st.n, nullptr, p.st.alpha_updated.p, p.st.C.p);
+    for (auto &itf : ifaces) {
+        PatchD &R = patches[itf.receiver];
+        PatchD &S = patches[itf.sender];
+        if (is_local(R) && is_local(S))
+            pack_alpha(s(), itf.count, itf.ids.p, S.st.alpha_updated.p, R.st.C.p + R.st.n + itf.dst_off);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the step
+// ---------------------------------------------------------------------------------------------
+void Model::evolve_once() {
+    auto wall0 = std::chrono::steady_clock::now();
+    SB_CUDA_CHECK(cudaSetDevice(ctx->device));
+    timer.begin_step();
+    const f64 t_current = time;
+    const f64 dt_       = dt;
+    const bool has_alpha  = cfg.av == SHAMB200_AV_MM97 || cfg.av == SHAMB200_AV_CD10;
+    const bool has_curl   = cfg.av == SHAMB200_AV_CD10;
+    const bool has_dtdivv = cfg.av == SHAMB200_AV_CD10;
+    const bool has_cs_field = has_alpha || cfg.eos == SHAMB200_EOS_LOCALLY_ISOTHERMAL_LP07;
+    red.ensure(RED_SLOTS);
+    h_red.ensure(RED_SLOTS);
+
+    timer.mark(s(), "predictor");
+    point_mass_accrete_particles();
+    for (auto &p : patches)
+        if (is_local(p) && p.f.n)
+            leapfrog_predictor(s(), p.f.n, dt_, p.f.xyz.p, p.f.vxyz.p, p.f.axyz.p, p.f.uint_.p, p.f.duint.p);
+    kill_particles();
+    compute_ext_forces_indep_v();
+    timer.mark(s(), "position_boundary");
+    apply_position_boundary();
+    npart_all = 0;
+    for (auto &p : patches)
+        if (is_local(p))
+            npart_all += p.f.n;
+    // (multi-rank: allreduce sum in solver_comm.cu)
+
+    sph_prestep();
+
+    SphParams sp{cfg.gpart_mass, cfg.alpha_u, cfg.alpha_AV, cfg.beta_AV};
+    f64 next_cfl              = 0;
+    u32 corrector_iter_cnt    = 0;
+    bool need_rerun_corrector = false;
+    do {
+        if (corrector_iter_cnt == 50)
+            throw std::runtime_error(
+                "the corrector has made over 50 loops, either their is a bug, either you are using a dt that "
+                "is too large");
+        timer.mark(s(), "ghost_fields");
+        communicate_merge_ghosts_fields();
+        for (auto &p : patches)
+            if (is_local(p) && p.f.n && has_alpha) {
+                p.st.alpha_updated.ensure(p.st.n);
+                SB_CUDA_CHECK(cudaMemcpyAsync(
+                    p.st.alpha_updated.p, p.f.alpha_AV.p, size_t(p.st.n) * sizeof(f64), cudaMemcpyDeviceToDevice, s()));
+            }
+        timer.mark(s(), "divv_curlv_dtdivv");
+        for (auto &p : patches) {
+            if (!is_local(p) || !p.f.n)
+                continue;
+            PatchStep &st = p.st;
+            if (has_dtdivv) {
+                if (cfg.combined_dtdiv_divcurlv_compute) {
+                    compute_dtdivv(
+                        s(), cfg.kernel, csr_of(st), st.A.p, st.B.p, st.D.p, st.tree.index_map.p, st.m, cfg.gpart_mass,
+                        true, p.f.divv.p, p.f.curlv.p, p.f.dtdivv.p);
+                } else {
+                    compute_divv_curlv(
+                        s(), cfg.kernel, csr_of(st), st.A.p, st.B.p, st.C.p, st.tree.index_map.p, st.m, cfg.gpart_mass,
+                        p.f.divv.p, has_curl ? p.f.curlv.p : nullptr);
+                    compute_dtdivv(
+                        s(), cfg.kernel, csr_of(st), st.A.p, st.B.p, st.D.p, st.tree.index_map.p, st.m, cfg.gpart_mass,
+                        false, p.f.divv.p, p.f.curlv.p, p.f.dtdivv.p);
+                }
+            } else if (has_alpha) {
+                compute_divv_curlv(
+                    s(), cfg.kernel, csr_of(st), st.A.p, st.B.p, st.C.p, st.tree.index_map.p, st.m, cfg.gpart_mass,
+                    p.f.divv.p, has_curl ? p.f.curlv.p : nullptr);
+            }
+        }
+        timer.mark(s(), "av_eos");
+        if (has_alpha) {
+            for (auto &p : patches)
+                if (is_local(p) && p.f.n)
+                    update_av(
+                        s(), cfg.av, p.st.n, dt_, cfg.sigma_decay, cfg.alpha_min, cfg.alpha_max, p.f.divv.p,
+                        p.f.curlv.p, p.f.dtdivv.p, p.f.soundspeed.p, p.f.hpart.p, p.f.alpha_AV.p, p.st.alpha_updated.p);
+            exchange_alpha_ghosts();
+        }
+        for (auto &p : patches)
+            if (is_local(p) && p.f.n)
+                compute_eos(
+                    s(), cfg.kernel, cfg.eos, p.st.A.p, p.st.B.p, p.st.C.p, p.st.m, cfg.gpart_mass, cfg.gamma, cfg.cs0,
+                    cfg.eos_q, cfg.eos_r0);
+        timer.mark(s(), "forces");
+        reset_red();
+        for (auto &p : patches) {
+            if (!is_local(p) || !p.f.n)
+                continue;
+            PatchStep &st = p.st;
+            st.a_old.ensure(size_t(st.n) * 3);
+            st.du_old.ensure(st.n);
+            SB_CUDA_CHECK(cudaMemcpyAsync(st.a_old.p, p.f.axyz.p, size_t(st.n) * 3 * sizeof(f64), cudaMemcpyDeviceToDevice, s()));
+            SB_CUDA_CHECK(cudaMemcpyAsync(st.du_old.p, p.f.duint.p, size_t(st.n) * sizeof(f64), cudaMemcpyDeviceToDevice, s()));
+            compute_forces(
+                s(), cfg.kernel, cfg.av, csr_of(st), st.A.p, st.B.p, st.C.p, st.tree.index_map.p, st.m, sp,
+                p.f.axyz_ext.p, p.f.axyz.p, p.f.duint.p);
+        }
+        timer.mark(s(), "corrector");
+        for (auto &p : patches)
+            if (is_local(p) && p.f.n)
+                leapfrog_corrector(
+                    s(), p.st.n, dt_ / 2, p.f.vxyz.p, p.f.axyz.p, p.st.a_old.p, p.f.uint_.p, p.f.duint.p, p.st.du_old.p,
+                    red.p + 2, reinterpret_cast<f64 *>(red.p + 3));
+        read_red(5);
+        f64 rank_veps_v = std::sqrt(ordered_to_f64(h_red.p[2]));
+        f64 sum_vsq     = bits_to_f64(h_red.p[3]);
+        // (multi-rank: allreduce sum / max in solver_comm.cu)
+        f64 vmean_sq   = sum_vsq / f64(npart_all);
+        f64 vmean      = std::sqrt(vmean_sq);
+        f64 rank_eps_v = rank_veps_v / vmean;
+        if (vmean <= 0)
+            rank_eps_v = 0;
+        eps_v = rank_eps_v;
+        if (eps_v > 1e-2) {
+            need_rerun_corrector = true;
+            cfl_multiplier       = cfl_multiplier / 2;
+        } else {
+            need_rerun_corrector = false;
+        }
+        if (!need_rerun_corrector) {
+            timer.mark(s(), "vsig_cfl");
+            f64 C_cour  = cfg.cfl_cour * cfl_multiplier;
+            f64 C_force = cfg.cfl_force * cfl_multiplier;
+            reset_red();
+            for (auto &p : patches) {
+                if (!is_local(p) || !p.f.n)
+                    continue;
+                PatchStep &st = p.st;
+                if (has_alpha)
+                    SB_CUDA_CHECK(cudaMemcpyAsync(
+                        p.f.alpha_AV.p, st.alpha_updated.p, size_t(st.n) * sizeof(f64), cudaMemcpyDeviceToDevice, s()));
+                st.vsig.ensure(st.n);
+                st.cfl_dt.ensure(st.n);
+                compute_vsig_cfl(
+                    s(), cfg.kernel, csr_of(st), st.A.p, st.B.p, st.C.p, st.tree.index_map.p, st.m, p.f.axyz.p, C_cour,
+                    C_force, st.vsig.p, st.cfl_dt.p, red.p + 4);
+                if (has_cs_field)
+                    unpack_cs(s(), st.n, st.C.p, p.f.soundspeed.p);
+            }
+            read_red(5);
+            next_cfl = ordered_to_f64(h_red.p[4]);
+            // (multi-rank: allreduce min in solver_comm.cu)
+        }
+        corrector_iter_cnt++;
+    } while (need_rerun_corrector);
+    corrector_iter = corrector_iter_cnt;
+    timer.end_step(s());
+    SB_CUDA_CHECK(cudaStreamSynchronize(s()));
+
+    dt   = next_cfl;
+    time = t_current + dt_;
+    f64 stiff      = cfg.cfl_multiplier_stiffness;
+    cfl_multiplier = (cfl_multiplier * stiff + 1.) / (stiff + 1.);
+    t_step         = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
+}
+
+} // namespace sb

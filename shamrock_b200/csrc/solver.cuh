@@ -1,0 +1,155 @@
+// solver.cuh — host side of the B200 SPH step: device-resident patch data + Solver::evolve_once.
+// Mirrors shammodels::sph::Solver / Model (shammodels/sph/include/shammodels/sph/{Solver,Model}.hpp)
+// for the configuration subset of SURVEY.md §8.
+#pragma once
+#include "../../include/shamb200.h"
+#include "neigh.cuh"
+#include "sph.cuh"
+#include "stream_kernels.cuh"
+#include "tree.cuh"
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace sb {
+
+struct Ctx {
+    int device          = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream     = false;
+    // arenas of the stage-level C ABI (shamb200_tree_build / shamb200_neigh_cache_build)
+    TreeBuffers api_tree;
+    NeighBuffers api_nb;
+    DevBuf<u64> red;
+    PinnedBuf<u64> h_red;
+};
+
+/// main patch data layout (SolverConfig.cpp:24-121), device resident, packed vec3 (3 doubles)
+struct PatchFields {
+    u32 n = 0;
+    DevBuf<f64> xyz, vxyz, axyz, axyz_ext, curlv;                         // 3n
+    DevBuf<f64> hpart, uint_, duint, alpha_AV, divv, dtdivv, soundspeed; // n
+    struct Ref {
+        const char *name;
+        DevBuf<f64> *buf;
+        int nvar;
+    };
+    std::vector<Ref> all();
+    void reserve(u32 cap, cudaStream_t s); ///< grow keeping the first n objects
+};
+
+struct Iface {
+    u32 sender, receiver; ///< indices in Model::patches
+    f64 offset[3];
+    i32 ioff[3];
+    f64 cut_lo[3], cut_hi[3];
+    u32 count   = 0;
+    u32 dst_off = 0; ///< offset inside the receiver's ghost range
+    DevBuf<u32> ids;
+};
+
+struct PatchStep {
+    u32 n = 0, m = 0;
+    DevBuf<Pack4> A, B, C, D;
+    TreeBuffers tree;
+    DevBuf<f64> rint;
+    NeighBuffers nb;
+    DevBuf<f64> omega, alpha_updated, vsig, cfl_dt, eps, h_old, a_old, du_old;
+    DevBuf<f64> mh_snapshot; ///< pre-iteration merged h (keep_step_data only)
+};
+
+struct PatchD {
+    u64 id = 0;
+    u64 cmin[3], cmax[3];
+    f64 lo[3], hi[3];
+    int owner = 0;
+    PatchFields f;
+    PatchStep st;
+};
+
+struct StageTimer {
+    std::vector<cudaEvent_t> pool;
+    std::vector<std::pair<std::string, int>> marks; // (name, event index)
+    std::map<std::string, double> acc;
+    std::vector<std::string> order;
+    std::string names_joined;
+    std::vector<double> values;
+    void begin_step();
+    void mark(cudaStream_t s, const char *name);
+    void end_step(cudaStream_t s);
+    ~StageTimer();
+};
+
+struct Model {
+    Ctx *ctx;
+    shamb200_solver_config cfg;
+    f64 box_min[3] = {0, 0, 0}, box_max[3] = {1, 1, 1};
+    std::vector<PatchD> patches;
+    int rank = 0, world = 1;
+    void *nccl_comm = nullptr;
+    f64 time = 0, dt = 0, cfl_multiplier = 1e-2; // Solver.hpp:131-147
+    // log of the last step
+    f64 eps_v = 0, t_step = 0;
+    u32 h_subcycles = 0, h_iters_last = 0, corrector_iter = 0;
+    u64 npart_all = 0, K_local = 0;
+    std::vector<Iface> ifaces;
+    StageTimer timer;
+    // scratch
+    DevBuf<u8> flag;
+    DevBuf<u32> pos, scan_tmp, owner_tmp;
+    DevBuf<u64> red;
+    PinnedBuf<u64> h_red;
+    DevBuf<f64> field_tmp, d_boxes;
+    DevBuf<u32> box_counts;
+    std::vector<f64> host_tmp;
+
+    explicit Model(Ctx *c, const shamb200_solver_config &cf) : ctx(c), cfg(cf) {}
+    cudaStream_t s() const { return ctx->stream; }
+    bool is_local(const PatchD &p) const { return p.owner == rank; }
+
+    void set_box(const f64 bmin[3], const f64 bmax[3], u32 nx, u32 ny, u32 nz);
+    void push_particles(u64 n, const f64 *xyz, const f64 *vxyz, const f64 *h, const f64 *u);
+    void evolve_once();
+    int64_t get(u32 ip, const std::string &name, void *out, int64_t cap);
+    void set_field(u32 ip, const std::string &name, const f64 *in, u64 count);
+
+    // pieces of the step (names follow the reference's Solver methods)
+    void keep_flagged(PatchD &p, u32 *out_kept = nullptr);
+    void point_mass_accrete_particles();
+    void kill_particles();
+    void compute_ext_forces_indep_v();
+    void apply_position_boundary();
+    void reattribute_patch_objects();
+    void build_ghost_cache();
+    void merge_position_ghost();
+    void build_merged_pos_trees();
+    void compute_presteps_rint();
+    void start_neighbors_cache();
+    void sph_prestep();
+    void communicate_merge_ghosts_fields();
+    void exchange_alpha_ghosts();
+    void reset_red();
+    void read_red(int n);
+};
+
+// NCCL plumbing (solver_comm.cu)
+void comm_unique_id(void *out128);
+void comm_init(Model &m, int rank, int world, const void *id128);
+void comm_allreduce_f64(Model &m, f64 *d_buf, size_t n, int op); ///< op: 0 sum, 1 max, 2 min
+void comm_allreduce_u64(Model &m, u64 *d_buf, size_t n, int op);
+void comm_group_start(Model &m);
+void comm_group_end(Model &m);
+void comm_send(Model &m, const void *d, size_t bytes, int peer);
+void comm_recv(Model &m, void *d, size_t bytes, int peer);
+void comm_destroy(Model &m);
+
+} // namespace sb
+
+struct shamb200_ctx {
+    sb::Ctx c;
+};
+struct shamb200_model {
+    sb::Model m;
+    shamb200_model(sb::Ctx *c, const shamb200_solver_config &cf) : m(c, cf) {}
+};

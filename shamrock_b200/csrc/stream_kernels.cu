@@ -1,0 +1,376 @@
+// stream_kernels.cu — the streaming (non neighbour-list) kernels of the SPH step: leapfrog
+// predictor / corrector, periodic wrap, point-mass force, ghost selection / gather, pack building,
+// order-preserving compaction of the patch fields.
+//
+// Reference behaviour restated (paths relative to /root/reference/src):
+//   shammodels/common/include/shammodels/common/modules/ForwardEuler.hpp:62-69 (predictor nodes,
+//   sequence shammodels/sph/src/Solver.cpp:390-524), shamrock/src/math/integrators.cpp:88-119
+//   (corrector), :207-236 (position modulo), shammodels/common/src/modules/
+//   AddForceCentralGravPotential.cpp:38-48, shammodels/sph/src/BasicSPHGhosts.cpp:526-531
+//   (get_ids_where on the cut volume), shammodels/sph/include/shammodels/sph/BasicSPHGhosts.hpp:294-321
+//   (append_subset_to + apply_offset), shamrock/src/patch/PatchDataField.cpp:300-331 (remove_ids).
+// Compiled with -fmad=false (bit-exact with the oracle).
+#include "stream_kernels.cuh"
+
+namespace sb {
+
+// ---- leapfrog predictor: v+=½dt a ; u+=½dt du ; x+=dt v ; v+=½dt a ; u+=½dt du -----------------
+__global__ void __launch_bounds__(256) predictor_kernel(
+    u32 n, f64 dt, f64 dt_half, f64 *__restrict__ xyz, f64 *__restrict__ vxyz, const f64 *__restrict__ axyz,
+    f64 *__restrict__ uint_, const f64 *__restrict__ duint) {
+    u64 i = u64(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < u64(n) * 3) {
+        f64 a  = axyz[i];
+        f64 v  = vxyz[i];
+        v      = v + dt_half * a;
+        xyz[i] = xyz[i] + dt * v;
+        v      = v + dt_half * a;
+        vxyz[i] = v;
+    }
+    if (i < n) {
+        f64 du = duint[i];
+        f64 u  = uint_[i];
+        u      = u + dt_half * du;
+        u      = u + dt_half * du;
+        uint_[i] = u;
+    }
+}
+void leapfrog_predictor(cudaStream_t s, u32 n, f64 dt, f64 *xyz, f64 *vxyz, const f64 *axyz, f64 *uint_, const f64 *duint) {
+    if (!n)
+        return;
+    predictor_kernel<<<grid_for(u64(n) * 3, 256), 256, 0, s>>>(n, dt, dt / 2, xyz, vxyz, axyz, uint_, duint);
+    SB_COUNT_LAUNCH();
+    SB_LAUNCH_CHECK();
+}
+
+// ---- leapfrog corrector + eps_v² max + Σ v·v ----------------------------------------------------
+__global__ void __launch_bounds__(256) corrector_kernel(
+    u32 n, f64 hdt, f64 *__restrict__ vxyz, const f64 *__restrict__ axyz, const f64 *__restrict__ axyz_old,
+    f64 *__restrict__ uint_, const f64 *__restrict__ duint, const f64 *__restrict__ duint_old, u64 *red_max,
+    f64 *red_sum) {
+    u32 i     = blockIdx.x * blockDim.x + threadIdx.x;
+    f64 epsv2 = -INFINITY, vsq = 0;
+    if (i < n) {
+        f64 ix = hdt * (axyz[3 * u64(i)] - axyz_old[3 * u64(i)]);
+        f64 iy = hdt * (axyz[3 * u64(i) + 1] - axyz_old[3 * u64(i) + 1]);
+        f64 iz = hdt * (axyz[3 * u64(i) + 2] - axyz_old[3 * u64(i) + 2]);
+        f64 vx = vxyz[3 * u64(i)] + ix, vy = vxyz[3 * u64(i) + 1] + iy, vz = vxyz[3 * u64(i) + 2] + iz;
+        vxyz[3 * u64(i)]     = vx;
+        vxyz[3 * u64(i) + 1] = vy;
+        vxyz[3 * u64(i) + 2] = vz;
+        epsv2    = ix * ix + iy * iy + iz * iz;
+        vsq      = vx * vx + vy * vy + vz * vz;
+        f64 incu = hdt * (duint[i] - duint_old[i]);
+        uint_[i] = uint_[i] + incu;
+    }
+    __shared__ f64 smax[8], ssum[8];
+    f64 m = warp_max(epsv2), q = warp_sum(vsq);
+    if ((threadIdx.x & 31) == 0) {
+        smax[threadIdx.x >> 5] = m;
+        ssum[threadIdx.x >> 5] = q;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        f64 a = smax[0], b = ssum[0];
+        for (int k = 1; k < 8; k++) {
+            a = fmax(a, smax[k]);
+            b += ssum[k];
+        }
+        atomicMax((unsigned long long *) red_max, (unsigned long long) f64_to_ordered(a));
+        atomicAdd(red_sum, b);
+    }
+}
+void leapfrog_corrector(
+    cudaStream_t s, u32 n, f64 hdt, f64 *vxyz, const f64 *axyz, const f64 *axyz_old, f64 *uint_, const f64 *duint,
+    const f64 *duint_old, u64 *red_max, f64 *red_sum) {
+    if (!n)
+        return;
+    corrector_kernel<<<grid_for(n, 256), 256, 0, s>>>(n, hdt, vxyz, axyz, axyz_old, uint_, duint, duint_old, red_max, red_sum);
+    SB_COUNT_LAUNCH();
+    SB_LAUNCH_CHECK();
+}
+
+// ---- periodic wrap ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) wrap_kernel(u32 n, f64 *__restrict__ xyz, f64 b0x, f64 b0y, f64 b0z, f64 b1x, f64 b1y, f64 b1z) {
+    u64 i = u64(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= u64(n) * 3)
+        return;
+    int c    = int(i % 3);
+    f64 lo   = c == 0 ? b0x : (c == 1 ? b0y : b0z);
+    f64 hi   = c == 0 ? b1x : (c == 1 ? b1y : b1z);
+    f64 delt = hi - lo;
+    f64 r    = xyz[i] - lo;
+    r        = fmod(r, delt);
+    r += delt;
+    r = fmod(r, delt);
+    r += lo;
+    xyz[i] = r;
+}
+void periodic_wrap(cudaStream_t s, u32 n, f64 *xyz, const f64 bmin[3], const f64 bmax[3]) {
+    if (!n)
+        return;
+    wrap_kernel<<<grid_for(u64(n) * 3, 256), 256, 0, s>>>(n, xyz, bmin[0], bmin[1], bmin[2], bmax[0], bmax[1], bmax[2]);
+    SB_COUNT_LAUNCH();
+    SB_LAUNCH_CHECK();
+}
+
+// ---- external force: central point mass -----------------------------------------------------------
+__global__ void __launch_bounds__(256) point_mass_kernel(u32 n, const f64 *__restrict__ xyz, f64 *__restrict__ axyz_ext, f64 mGM) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    f64 x = xyz[3 * u64(i)] - 0., y = xyz[3 * u64(i) + 1] - 0., z = xyz[3 * u64(i) + 2] - 0.;
+    f64 abs_ra   = sqrt(x * x + y * y + z * z);
+    f64 abs_ra_3 = abs_ra * abs_ra * abs_ra;
+    axyz_ext[3 * u64(i)] += (mGM * x) / abs_ra_3;
+    axyz_ext[3 * u64(i) + 1] += (mGM * y) / abs_ra_3;
+    axyz_ext[3 * u64(i) + 2] += (mGM * z) / abs_ra_3;
+}
+void ext_force_point_mass(cudaStream_t s, u32 n, const f64 *xyz, f64 *axyz_ext, f64 central_mass, f64 G) {
+    if (!n)
+        return;
+    point_mass_kernel<<<grid_for(n, 256), 256, 0, s>>>(n, xyz, axyz_ext, -central_mass * G);
+    SB_COUNT_LAUNCH();
+    SB_LAUNCH_CHECK();
+}
+
+// ---- selection flags --------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) flag_in_box_kernel(
+    u32 n, const f64 *__restrict__ xyz, f64 l0, f64 l1, f64 l2, f64 h0, f64 h1, f64 h2, u8 *__restrict__ flag) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    f64 x = xyz[3 * u64(i)], y = xyz[3 * u64(i) + 1], z = xyz[3 * u64(i) + 2];
+    flag[i] = ((l0 <= x) && (x < h0) && (l1 <= y) && (y < h1) && (l2 <= z) && (z < h2)) ? 1 : 0;
+}
+void flag_in_box(cudaStream_t s, u32 n, const f64 *xyz, const f64 lo[3], const f64 hi[3], u8 *flag) {
+    if (!n)
+        return;
+    flag_in_box_kernel<<<grid_for(n, 256), 256, 0, s>>>(n, xyz, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], flag);
+    SB_COUNT_LAUNCH();
+    SB_LAUNCH_CHECK();
+}
+
+/// mode 0: keep if |r - c|² > rad² (accretion: ExternalForces.cpp:651-655, rad = Racc)
+/// mode 1: keep if !(|r - c| > rad)  (kill sphere: GetParticlesOutsideSphere.cpp:34-36)
+__global__ void __launch_bounds__(256) flag_sphere_kernel(
+    u32 n, const f64 *__restrict__ xyz, f64 cx, f64 cy, f64 cz, f64 rad, int mode, u8 *__restrict__ flag) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    f64 x = xyz[3 * u64(i)] - cx, y = xyz[3 * u64(i) + 1] - cy, z = xyz[3 * u64(i) + 2] - cz;
+    f64 d2 = x * x + y * y + z * z;
+    if (mode == 0)
+        flag[i] = (d2 > rad * rad) ? 1 : 0;
+    else
+        flag[i] = (sqrt(d2) > rad) ? 0 : 1;
+}
+void flag_sphere(cudaStream_t s, u32 n, const f64 *xyz, const f64 c[3], f64 rad, int mode, u8 *flag) {
+    if (!n)
+        return;
+    flag_sphere_kernel<<<grid_for(n, 256), 256, 0, s>>>(n, xyz, c[0], c[1], c[2], rad, mode, flag);
+    SB_COUNT_LAUNCH();
+    SB_LAUNCH_CHECK();
+}
+
+/// owner patch of each particle: index of the patch whose [lo,hi) box contains it, 0xFFFFFFFF if none
+__global__ void __launch_bounds__(256) patch_owner_kernel(
+    u32 n, const f64 *__restrict__ xyz, u32 npatch, const f64 *__restrict__ boxes /*npatch*6*/, u32 self,
+    u8 *__restrict__ stay_flag, u32 *__restrict__ owner) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    f64 x = xyz[3 * u64(i)], y = xyz[3 * u64(i) + 1], z = xyz[3 * u64(i) + 2];
+    u32 own = 0xFFFFFFFFu;
+    for (u32 k = 0; k < npatch; k++) {
+        const f64 *b = boxes + 6 * k;
+        if (b[0] <= x && x < b[3] && b[1] <= y && y < b[4] && b[2] <= z && z < b[5]) {
+            own = k;
+            break;
+        }
+    }
+    owner[i]     = own;
+    stay_flag[i] = (own == self) ? 1 : 0;
+}
+void patch_owner(cudaStream_t s, u32 n, const f64 *xyz, u32 npatch, const f64 *d_boxes, u32 self, u8 *stay_flag, u32 *owner) {
+    if (!n)
+        return;
+    patch_owner_kernel<<<grid_for(n, 256), 256, 0, s>>>(n, xyz, npatch, d_boxes, self, stay_flag, owner);
+    SB_COUNT_LAUNCH();
+    SB_LAUNCH_CHECK();
+}
+__global__ void __launch_bounds__(256) flag_eq_kernel(u32 n, const u32 *__restrict__ v, u32 val, u8 *__restrict__ flag) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        flag[i] = (v[i] == val) ? 1 : 0;
+}
+void flag_equal(cudaStream_t s, u32 n, const u32 *v, u32 val, u8 *flag) {
+    if (!n)
+        return;
+    flag_eq_kernel<<<grid_for(n, 256), 256, 0, s>>>(n, v, val, flag);
+    SB_COUNT_LAUNCH();
+    SB_LAUNCH_CHECK();
+}
+
+/// ids[pos[i]] = i where flag[i]  (stream compaction, ascending ids)
+__global__ void __launch_bounds__(256) scatter_ids_kernel(u32 n, const u8 *__restrict__ flag, const u32 *__restrict__ pos, u32 *__restrict__ ids) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flag[i])
+        ids[pos[i]] = i;
+}
+void scatter_ids(cudaStream_t s, u32 n, const u8 *flag, const u32 *pos, u32 *ids) {
+    if (!n)
+        return;
+    scatter_ids_kernel<<<grid_for(n, 256), 256, 0, s>>>(n, flag, pos, ids);
+    SB_COUNT_LAUNCH();
+    SB_LAUNCH_CHECK();
+}
+
+// ---- gathers ------------------------------------------------------------------------------------------
+/// dst[k*nvar + c] = src[ids[k]*nvar + c]   (append_subset_to / keep_ids)
+__global__ void __launch_bounds__(256) gather_field_kernel(u32 cnt, int nvar, const u32 *__restrict__ ids, const f64 *__restrict__ src, f64 *__restrict__ dst) {
+    u64 t = u64(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= u64(cnt) * nvar)
+        return;
+    u32 k = u32(t / nvar);
+    int c = int(t % nvar);
+    dst[t] = src[u64(ids[k]) * nvar + c];
+}
+void gather_field(cudaStream_t s, u32 cnt, int nvar, const u32 *ids, const f64 *src, f64 *dst) {
+    if (!cnt)
+        return;
+    gather_field_kernel<<<grid_for(u64(cnt) * nvar, 256), 256, 0, s>>>(cnt, nvar, ids, src, dst);
+    SB_COUNT_LAUNCH();
+    SB_LAUNCH_CHECK();
+}
+
+// ---- packs ---------------------------------------------------------------------------------------------
+/// A[i] = (xyz_i, h_i) for the real particles
+__global__ void __launch_bounds__(256) pack_xyzh_kernel(u32 n, const f64 *__restrict__ xyz, const f64 *__restrict__ h, Pack4 *__restrict__ A) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    A[i] = Pack4{xyz[3 * u64(i)], xyz[3 * u64(i) + 1], xyz[3 * u64(i) + 2], h[i]};
+}
+void pack_xyzh(cudaStream_t s, u32 n, const f64 *xyz, const f64 *h, Pack4 *A) {
+    if (!n)
+        return;
+    pack_xyzh_kernel<<<grid_for(n, 256), 256, 0, s>>>(n, xyz, h, A);
+    SB_COUNT_LAUNCH();
+    SB_LAUNCH_CHECK();
+}
+/// ghost positions: A_dst[k] = (xyz[ids[k]] + offset, h[ids[k]])
+__global__ void __launch_bounds__(256) ghost_xyzh_kernel(
+    u32 cnt, const u32 *__restrict__ ids, const f64 *__restrict__ xyz, const f64 *__restrict__ h, f64 ox, f64 oy,
+    f64 oz, Pack4 *__restrict__ A_dst) {
+    u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= cnt)
+        return;
+    u32 id   = ids[k];
+    A_dst[k] = Pack4{xyz[3 * u64(id)] + ox, xyz[3 * u64(id) + 1] + oy, xyz[3 * u64(id) + 2] + oz, h[id]};
+}
+void ghost_xyzh(cudaStream_t s, u32 cnt, const u32 *ids, const f64 *xyz, const f64 *h, const f64 off[3], Pack4 *A_dst) {
+    if (!cnt)
+        return;
+    ghost_xyzh_kernel<<<grid_for(cnt, 256), 256, 0, s>>>(cnt, ids, xyz, h, off[0], off[1], off[2], A_dst);
+    SB_COUNT_LAUNCH();
+    SB_LAUNCH_CHECK();
+}
+
+/// field packs.  ids == nullptr: identity (real particles of the patch itself)
+/// A.d = h ; B = (v, u) ; C.b = omega ; D = (a, 0) when `axyz` is given
+__global__ void __launch_bounds__(256) pack_fields_kernel(
+    u32 cnt, const u32 *__restrict__ ids, const f64 *__restrict__ h, const f64 *__restrict__ vxyz,
+    const f64 *__restrict__ uint_, const f64 *__restrict__ omega, const f64 *__restrict__ axyz,
+    Pack4 *__restrict__ A, Pack4 *__restrict__ B, Pack4 *__restrict__ C, Pack4 *__restrict__ D) {
+    u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= cnt)
+        return;
+    u32 id = ids ? ids[k] : k;
+    A[k].d = h[id];
+    B[k]   = Pack4{vxyz[3 * u64(id)], vxyz[3 * u64(id) + 1], vxyz[3 * u64(id) + 2], uint_[id]};
+    C[k].b = omega[id];
+    if (axyz)
+        D[k] = Pack4{axyz[3 * u64(id)], axyz[3 * u64(id) + 1], axyz[3 * u64(id) + 2], 0.};
+}
+void pack_fields(
+    cudaStream_t s, u32 cnt, const u32 *ids, const f64 *h, const f64 *vxyz, const f64 *uint_, const f64 *omega,
+    const f64 *axyz, Pack4 *A, Pack4 *B, Pack4 *C, Pack4 *D) {
+    if (!cnt)
+        return;
+    pack_fields_kernel<<<grid_for(cnt, 256), 256, 0, s>>>(cnt, ids, h, vxyz, uint_, omega, axyz, A, B, C, D);
+    SB_COUNT_LAUNCH();
+    SB_LAUNCH_CHECK();
+}
+/// C[k].d = alpha[ids ? ids[k] : k]
+__global__ void __launch_bounds__(256) pack_alpha_kernel(u32 cnt, const u32 *__restrict__ ids, const f64 *__restrict__ alpha, Pack4 *__restrict__ C) {
+    u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= cnt)
+        return;
+    C[k].d = alpha[ids ? ids[k] : k];
+}
+void pack_alpha(cudaStream_t s, u32 cnt, const u32 *ids, const f64 *alpha, Pack4 *C) {
+    if (!cnt)
+        return;
+    pack_alpha_kernel<<<grid_for(cnt, 256), 256, 0, s>>>(cnt, ids, alpha, C);
+    SB_COUNT_LAUNCH();
+    SB_LAUNCH_CHECK();
+}
+/// out[i] = C[i].c (sound speed of the real particles → main field, Solver.cpp:3129-3161)
+__global__ void __launch_bounds__(256) unpack_cs_kernel(u32 n, const Pack4 *__restrict__ C, f64 *__restrict__ cs) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        cs[i] = C[i].c;
+}
+void unpack_cs(cudaStream_t s, u32 n, const Pack4 *C, f64 *cs) {
+    if (!n)
+        return;
+    unpack_cs_kernel<<<grid_for(n, 256), 256, 0, s>>>(n, C, cs);
+    SB_COUNT_LAUNCH();
+    SB_LAUNCH_CHECK();
+}
+/// generic component extraction for inspection (tests): out[i*nc + c] = P[i].comp(first + c)
+__global__ void __launch_bounds__(256) unpack_comp_kernel(u32 n, const Pack4 *__restrict__ P, int first, int nc, f64 *__restrict__ out) {
+    u64 t = u64(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= u64(n) * nc)
+        return;
+    u32 i = u32(t / nc);
+    int c = first + int(t % nc);
+    const f64 *q = reinterpret_cast<const f64 *>(P + i);
+    out[t]       = q[c];
+}
+void unpack_comp(cudaStream_t s, u32 n, const Pack4 *P, int first, int nc, f64 *out) {
+    if (!n)
+        return;
+    unpack_comp_kernel<<<grid_for(u64(n) * nc, 256), 256, 0, s>>>(n, P, first, nc, out);
+    SB_COUNT_LAUNCH();
+    SB_LAUNCH_CHECK();
+}
+
+// ---- max reduction of a field (interactR_patch = max(h)·htol·Rkern) ---------------------------------------
+__global__ void __launch_bounds__(256) max_reduce_kernel(u32 n, const f64 *__restrict__ v, u64 *red) {
+    f64 m = -INFINITY;
+    for (u64 i = u64(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += u64(gridDim.x) * blockDim.x)
+        m = fmax(m, v[i]);
+    __shared__ f64 sm[8];
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0)
+        sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        f64 a = sm[0];
+        for (int k = 1; k < 8; k++)
+            a = fmax(a, sm[k]);
+        atomicMax((unsigned long long *) red, (unsigned long long) f64_to_ordered(a));
+    }
+}
+void max_reduce(cudaStream_t s, u32 n, const f64 *v, u64 *red) {
+    if (!n)
+        return;
+    unsigned nb = (unsigned) std::min<u64>(u64(kNumSM) * 8, (u64(n) + 255) / 256);
+    max_reduce_kernel<<<nb, 256, 0, s>>>(n, v, red);
+    SB_COUNT_LAUNCH();
+    SB_LAUNCH_CHECK();
+}
+
+} // namespace sb

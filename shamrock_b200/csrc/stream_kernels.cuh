@@ -1,0 +1,25 @@
+// stream_kernels.cuh — launchers of the streaming kernels (stream_kernels.cu)
+#pragma once
+#include "sph.cuh"
+
+namespace sb {
+void leapfrog_predictor(cudaStream_t s, u32 n, f64 dt, f64 *xyz, f64 *vxyz, const f64 *axyz, f64 *uint_, const f64 *duint);
+void leapfrog_corrector(cudaStream_t s, u32 n, f64 hdt, f64 *vxyz, const f64 *axyz, const f64 *axyz_old, f64 *uint_,
+                        const f64 *duint, const f64 *duint_old, u64 *red_max, f64 *red_sum);
+void periodic_wrap(cudaStream_t s, u32 n, f64 *xyz, const f64 bmin[3], const f64 bmax[3]);
+void ext_force_point_mass(cudaStream_t s, u32 n, const f64 *xyz, f64 *axyz_ext, f64 central_mass, f64 G);
+void flag_in_box(cudaStream_t s, u32 n, const f64 *xyz, const f64 lo[3], const f64 hi[3], u8 *flag);
+void flag_sphere(cudaStream_t s, u32 n, const f64 *xyz, const f64 c[3], f64 rad, int mode, u8 *flag);
+void patch_owner(cudaStream_t s, u32 n, const f64 *xyz, u32 npatch, const f64 *d_boxes, u32 self, u8 *stay_flag, u32 *owner);
+void flag_equal(cudaStream_t s, u32 n, const u32 *v, u32 val, u8 *flag);
+void scatter_ids(cudaStream_t s, u32 n, const u8 *flag, const u32 *pos, u32 *ids);
+void gather_field(cudaStream_t s, u32 cnt, int nvar, const u32 *ids, const f64 *src, f64 *dst);
+void pack_xyzh(cudaStream_t s, u32 n, const f64 *xyz, const f64 *h, Pack4 *A);
+void ghost_xyzh(cudaStream_t s, u32 cnt, const u32 *ids, const f64 *xyz, const f64 *h, const f64 off[3], Pack4 *A_dst);
+void pack_fields(cudaStream_t s, u32 cnt, const u32 *ids, const f64 *h, const f64 *vxyz, const f64 *uint_,
+                 const f64 *omega, const f64 *axyz, Pack4 *A, Pack4 *B, Pack4 *C, Pack4 *D);
+void pack_alpha(cudaStream_t s, u32 cnt, const u32 *ids, const f64 *alpha, Pack4 *C);
+void unpack_cs(cudaStream_t s, u32 n, const Pack4 *C, f64 *cs);
+void unpack_comp(cudaStream_t s, u32 n, const Pack4 *P, int first, int nc, f64 *out);
+void max_reduce(cudaStream_t s, u32 n, const f64 *v, u64 *red);
+} // namespace sb

@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py — full SPH step throughput (particle-updates/s) of the B200 path, reference protocol.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--npart-per-gpu P] [--impl reference]
+
+Workload (BASELINE.json config C4, the one the metric is quoted on at 1/2/4/8 GPUs; protocol of the
+reference's examples/benchmarks/sph_homogeneous_benchmark.py): HCP lattice in a periodic box, M4 kernel,
+CD10 artificial viscosity, adiabatic gamma = 5/3, Sedov-like `uint` injection, C_cour = C_force = 0.1,
+16 Mi particles per GPU (weak scaling: the box is stretched along x, one slab of patches per GPU);
+W warm-up timestep()s, then K x { set_next_dt(0); timestep() }.  rate = sum_ranks N / max_ranks t.
+
+One JSON line on stdout (rank 0).  `value`: patch data resident in HBM.  `e2e`: the same step driven
+through the C ABI with HOST patch data: every step uploads all main-layout fields from pinned host
+memory (shamb200_model_set_field), runs shamb200_model_evolve_once and reads all fields back.
+`--impl reference`: the CPU oracle (a port of the reference's algorithms; the reference itself needs
+SYCL + MPI and cannot be built in this image) on all host cores, on a bounded sample of the workload.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H100_PUBLISHED = 25.50e6  # reference full-step rate, 1x H100, same protocol (N = 33.8 M)
+MAIN_FIELDS = [("xyz", 3), ("vxyz", 3), ("axyz", 3), ("axyz_ext", 3), ("hpart", 1), ("uint", 1), ("duint", 1),
+               ("alpha_AV", 1), ("divv", 1), ("dtdivv", 1), ("curlv", 3), ("soundspeed", 1)]
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)"""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i",
+                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def workload(npart_per_gpu, n_gpus, kernel="M4"):
+    from tests import scenarios as S
+
+    # weak scaling: box stretched along x, patch grid = n_gpus slabs (power of two)
+    sc = S.periodic_box(npart_per_gpu * n_gpus, kernel, "cd10", jitter=0.0, grid=(n_gpus, 1, 1),
+                        stretch=(n_gpus, 1, 1), sort_mode="radix")
+    return sc
+
+
+# algorithmic bytes per launch of the heavy kernels (M merged, N real, K neighbours)
+def alg_bytes(stage, N, M, K, L):
+    return {
+        "neigh_cache": 64 * M + 4 * K + 12 * N,
+        "h_iteration": 4 * K + 32 * M + 40 * N,
+        "omega": 4 * K + 32 * M + 8 * N,
+        "divv_curlv_dtdivv": 12 * K + 200 * M + 40 * N,
+        "forces": 4 * K + 104 * M + 32 * N,
+        "vsig_cfl": 4 * K + 64 * M + 64 * N,
+        "build_trees": 176 * M + 90 * L,
+    }.get(stage)
+
+
+def run_reference(args):
+    """CPU arm: the oracle port on all host cores, bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import pyoracle as po
+    from tests import scenarios as S
+
+    n_sample = args.cpu_sample
+    sc = workload(n_sample, 1)
+    o = S.make_oracle(sc)
+    n = len(sc["xyz"])
+    for _ in range(max(args.warmup, 1)):
+        o.evolve_once()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.set_next_dt(0.0)
+        o.evolve_once()
+    dt = time.perf_counter() - t0
+    v = n * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "SPH particle-updates/sec (full step)", "value": v, "unit": "particles/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C4 periodic HCP box, M4, CD10 AV, adiabatic, dt=0 replay (sph_homogeneous_benchmark "
+                   "protocol)", "npart_sample": n},
+        "cpu_baseline": {"value": v, "unit": "particles/s", "cores": po.num_threads(), "kind": "port",
+                         "sample": f"{n} particles of the same box (oracle port of the reference algorithms, "
+                                   f"OpenMP), {args.steps} dt=0 replays"},
+        "e2e": {"value": v, "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(args):
+    from oracle import pyoracle as po
+    from tests import scenarios as S
+
+    sc = workload(args.cpu_sample, 1)
+    o = S.make_oracle(sc)
+    n = len(sc["xyz"])
+    o.evolve_once()
+    t0 = time.perf_counter()
+    k = 2
+    for _ in range(k):
+        o.set_next_dt(0.0)
+        o.evolve_once()
+    dt = time.perf_counter() - t0
+    return {"value": n * k / dt, "unit": "particles/s", "cores": po.num_threads(), "kind": "port",
+            "sample": f"{n} particles of the same periodic box, 1 warm-up + {k} dt=0 replays, oracle (C++/OpenMP port "
+                      "of the reference algorithms; the SYCL reference cannot be built here)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--npart-per-gpu", type=int, default=16 * 2**20)
+    ap.add_argument("--cpu-sample", type=int, default=400000)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from shamrock_b200 import _capi
+    from tests import scenarios as S
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local)
+    nccl_id = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        ids = [_capi.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        nccl_id = ids[0]
+
+    sc = workload(args.npart_per_gpu, world)
+    ctx = _capi.Context(local)
+    m = S.make_cuda(sc, ctx=ctx, keep_step_data=False, rank=rank, world=world, nccl_id=nccl_id)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(k):
+            fn()
+        e1.record(stream)
+        e1.synchronize()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def step():
+        m.set_next_dt(0.0)
+        m.evolve_once()
+
+    # warm-up: first real timestep (converges h), then dt = 0 replays
+    m.evolve_once()
+    for _ in range(args.warmup - 1):
+        step()
+    st = m.state()
+    n_local = int(st["n_local"])
+    n_total = int(st["npart"])
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    _capi.reset_launch_count()
+    stage_acc = {}
+
+    def step_acc():
+        step()
+        for k, v in m.stage_times().items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v
+
+    ms = timed(step_acc, args.steps)
+    launches = _capi.launch_count()
+    clk = clocks.stop() if rank == 0 else None
+    st = m.state()
+    value = n_total * args.steps / (ms * 1e-3)
+
+    # ---- e2e: host patch data in, host patch data out, every step ---------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host = {}
+        ips = [ip for ip in range(m.patch_count) if m.patch_is_local(ip) and m.patch_size(ip)]
+        h2d = 0
+        for ip in ips:
+            for nm, nv in MAIN_FIELDS:
+                a = m.get(ip, nm)
+                t = torch.empty(a.size, dtype=torch.float64).pin_memory()
+                t.numpy()[:] = a.reshape(-1)
+                host[(ip, nm)] = t
+                h2d += a.nbytes
+        lib = _capi.lib()
+        import ctypes as C
+
+        def e2e_step():
+            for (ip, nm), t in host.items():
+                _capi.check(lib.shamb200_model_set_field(m.h, C.c_uint32(ip), nm.encode(), C.c_void_p(t.data_ptr()),
+                                                         C.c_uint64(t.numel())))
+            m.set_next_dt(0.0)
+            m.evolve_once()
+            for (ip, nm), t in host.items():
+                r = lib.shamb200_model_get(m.h, C.c_uint32(ip), nm.encode(), C.c_void_p(t.data_ptr()),
+                                           C.c_int64(t.numel() * 8))
+                assert r == t.numel() * 8
+
+        e2e_step()
+        k2 = max(2, min(args.steps, 3))
+        ms2 = timed(e2e_step, k2)
+        e2e_val = n_total * k2 / (ms2 * 1e-3)
+        tot = torch.tensor([float(h2d)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tot)
+        e2e = {"value": e2e_val, "unit": "particles/s", "h2d_bytes_per_step": int(tot.item()),
+               "d2h_bytes_per_step": int(tot.item()), "ms_per_step": ms2 / k2}
+
+    if rank == 0:
+        hbm_peak, peak_src = peaks()
+        # dominant stage (device time between CUDA-event marks on the step's stream) and its roofline
+        N, K = n_local, int(st["K_local"])
+        M, L = int(st.get("m_local", N) or N), int(st.get("leaves_local", N // 6) or N // 6)
+        per_stage = {k: v / args.steps for k, v in stage_acc.items()}
+        cand = {k: v for k, v in per_stage.items() if alg_bytes(k, N, M, K, L)}
+        top = max(cand, key=cand.get)
+        nb = alg_bytes(top, N, M, K, L)
+        achieved = nb / (cand[top] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "alg_bytes_per_launch": nb, "ms_per_launch": cand[top],
+                    "stage_ms": {k: round(v, 3) for k, v in per_stage.items()}}
+        line = {
+            "metric": "SPH particle-updates/sec (full step)", "value": value, "unit": "particles/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": value / H100_PUBLISHED, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "C4: periodic HCP box, M4 kernel, CD10 AV, adiabatic gamma=5/3, Sedov-like uint "
+                       "injection, dt=0 replay (reference protocol sph_homogeneous_benchmark.py)",
+                       "npart_total": n_total, "npart_per_gpu": n_total // world, "neighbours_per_particle": K / max(N, 1),
+                       "patches": list(sc["grid"]), "sort": sc["sort_mode"], "fp": _capi.lib().shamb200_build_info().decode(),
+                       "l2": "inputs larger than L2 (no flush needed)",
+                       "vs_baseline_ref": "reference on 1x H100, 25.5 M part/s (BASELINE.md §1)"},
+            "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "h_subcycles": st["h_subcycles"], "corrector_iter": st["corrector_iter"],
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(args)
+        print(json.dumps(line), flush=True)
+    m.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -135,6 +135,28 @@ int shamb200_h_iterate_loop(shamb200_ctx *ctx, int kernel, const shamb200_csr *c
 int shamb200_compute_omega(shamb200_ctx *ctx, int kernel, const shamb200_csr *csr, const double *d_xyz,
                            size_t stride_dbl, const double *d_hpart, double *d_omega, double gpart_mass);
 
+/* ---- patch decomposition / ghost-zone planning (host only, no CUDA call) ---------------------------
+ * Pure functions of replicated metadata: every rank computes the same plan, so the NCCL send/recv
+ * pairs of the ghost exchange match without negotiation.
+ * replaces: the static part of PatchScheduler (shamrock/src/scheduler/PatchScheduler.cpp; patches on
+ * the 2^21 integer grid, Patch.hpp:63-72) and BasicSPHGhostHandler::find_interfaces
+ * (shammodels/sph/src/BasicSPHGhosts.cpp:261-509) with the exchange order of
+ * shambase::DistributedDataShared (multimap on (sender, receiver), DistributedDataShared.hpp:54). */
+typedef struct shamb200_iface {
+    uint32_t sender, receiver; /* patch indices                                         */
+    int32_t ioff[3];           /* periodic image (-1, 0, 1 per axis)                    */
+    double offset[3];          /* added to the sender's positions                       */
+    double cut_lo[3], cut_hi[3]; /* sender-frame box [lo, hi) whose particles are ghosts  */
+} shamb200_iface;
+/* boxes: [np*6] (lo[3], hi[3]) per patch, x fastest; owner: [np] rank of each patch */
+int shamb200_plan_patch_grid(const double bmin[3], const double bmax[3], uint32_t nx, uint32_t ny, uint32_t nz,
+                             int world_size, double *boxes, int32_t *owner);
+/* interact_r[np] = max(h)*htol*Rkern per patch, pcount[np] particle counts.  Writes up to cap
+ * interfaces (exchange order) and the total number found into *n_found. */
+int shamb200_plan_interfaces(uint32_t npatch, const double *boxes, const double bmin[3], const double bmax[3],
+                             int periodic, const double *interact_r, const uint32_t *pcount, uint32_t cap,
+                             shamb200_iface *out, uint32_t *n_found);
+
 /* ---- model (shammodels::sph::Model<f64_3, Kernel> / Solver::evolve_once) -------------------------
  * Host-side drop-in: owns the patch data on the device and runs the whole step on the GPU.
  * Mirrors shammodels/sph/include/shammodels/sph/Model.hpp:55-1076 and Solver.cpp:1942-3272 for

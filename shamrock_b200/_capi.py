@@ -57,6 +57,11 @@ class SolverConfig(C.Structure):
     ]
 
 
+class Iface(C.Structure):
+    _fields_ = [("sender", C.c_uint32), ("receiver", C.c_uint32), ("ioff", C.c_int32 * 3),
+                ("offset", C.c_double * 3), ("cut_lo", C.c_double * 3), ("cut_hi", C.c_double * 3)]
+
+
 # every symbol include/shamb200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
     "shamb200_last_error", "shamb200_build_info", "shamb200_launch_count", "shamb200_reset_launch_count",
@@ -69,7 +74,7 @@ SYMBOLS = [
     "shamb200_model_patch_is_local", "shamb200_model_patch_size", "shamb200_model_get",
     "shamb200_model_set_field", "shamb200_model_evolve_once", "shamb200_model_state",
     "shamb200_model_set_next_dt", "shamb200_model_set_time", "shamb200_model_set_cfl_multiplier",
-    "shamb200_model_stage_times",
+    "shamb200_model_stage_times", "shamb200_plan_patch_grid", "shamb200_plan_interfaces",
 ]
 
 _lib = None
@@ -308,6 +313,31 @@ class Model:
         check(lib().shamb200_model_stage_times(self.h, C.byref(names), C.byref(ms), C.byref(cnt)))
         ns = names.value.decode().split(";") if names.value else []
         return {n: ms[i] for i, n in enumerate(ns[: cnt.value])}
+
+
+def plan_patch_grid(bmin, bmax, grid, world=1):
+    """host-only: boxes [np,2,3] and owner rank [np] of the static patch grid"""
+    n = grid[0] * grid[1] * grid[2]
+    boxes = np.zeros((n, 2, 3))
+    owner = np.zeros(n, dtype=np.int32)
+    check(lib().shamb200_plan_patch_grid((C.c_double * 3)(*bmin), (C.c_double * 3)(*bmax), *[C.c_uint32(g) for g in grid],
+                                         int(world), boxes.ctypes.data_as(C.c_void_p), owner.ctypes.data_as(C.c_void_p)))
+    return boxes, owner
+
+
+def plan_interfaces(boxes, bmin, bmax, periodic, interact_r, pcount):
+    """host-only: the ghost interfaces in exchange order (list of Iface)"""
+    boxes = np.ascontiguousarray(boxes, dtype=np.float64)
+    n = len(boxes)
+    ir = np.ascontiguousarray(interact_r, dtype=np.float64)
+    pc = np.ascontiguousarray(pcount, dtype=np.uint32)
+    cap = 27 * n * n
+    out = (Iface * cap)()
+    nf = C.c_uint32()
+    check(lib().shamb200_plan_interfaces(C.c_uint32(n), boxes.ctypes.data_as(C.c_void_p), (C.c_double * 3)(*bmin),
+                                         (C.c_double * 3)(*bmax), int(periodic), ir.ctypes.data_as(C.c_void_p),
+                                         pc.ctypes.data_as(C.c_void_p), C.c_uint32(cap), out, C.byref(nf)))
+    return [out[i] for i in range(nf.value)]
 
 
 def nccl_unique_id():

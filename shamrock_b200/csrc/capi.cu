@@ -197,6 +197,50 @@ int shamb200_compute_omega(
     });
 }
 
+// ---- planning (host only) -------------------------------------------------------------------------
+int shamb200_plan_patch_grid(
+    const double bmin[3], const double bmax[3], uint32_t nx, uint32_t ny, uint32_t nz, int world_size,
+    double *boxes, int32_t *owner) {
+    return guard([&] {
+        auto g = plan_patch_grid(bmin, bmax, nx, ny, nz, world_size);
+        for (size_t k = 0; k < g.size(); k++) {
+            for (int d = 0; d < 3; d++) {
+                boxes[6 * k + d]     = g[k].lo[d];
+                boxes[6 * k + 3 + d] = g[k].hi[d];
+            }
+            owner[k] = g[k].owner;
+        }
+    });
+}
+int shamb200_plan_interfaces(
+    uint32_t npatch, const double *boxes, const double bmin[3], const double bmax[3], int periodic,
+    const double *interact_r, const uint32_t *pcount, uint32_t cap, shamb200_iface *out, uint32_t *n_found) {
+    return guard([&] {
+        std::vector<PatchBox> pb(npatch);
+        for (uint32_t k = 0; k < npatch; k++) {
+            pb[k].id = k;
+            for (int d = 0; d < 3; d++) {
+                pb[k].lo[d] = boxes[6 * k + d];
+                pb[k].hi[d] = boxes[6 * k + 3 + d];
+            }
+        }
+        auto c = plan_interfaces(
+            pb, bmin, bmax, periodic != 0, std::vector<double>(interact_r, interact_r + npatch),
+            std::vector<uint32_t>(pcount, pcount + npatch));
+        *n_found = uint32_t(c.size());
+        for (size_t q = 0; q < c.size() && q < cap; q++) {
+            out[q].sender   = c[q].sender;
+            out[q].receiver = c[q].receiver;
+            for (int d = 0; d < 3; d++) {
+                out[q].ioff[d]   = c[q].ioff[d];
+                out[q].offset[d] = c[q].offset[d];
+                out[q].cut_lo[d] = c[q].cut_lo[d];
+                out[q].cut_hi[d] = c[q].cut_hi[d];
+            }
+        }
+    });
+}
+
 // ---- model --------------------------------------------------------------------------------------
 void shamb200_solver_config_default(shamb200_solver_config *cfg) {
     std::memset(cfg, 0, sizeof(*cfg));

@@ -14,7 +14,6 @@
 
 namespace sb {
 
-static constexpr u64 PATCH_GRID = 1ull << 21; // PatchScheduler::max_axis_patch_coord_length
 
 // ---------------------------------------------------------------------------------------------
 // PatchFields
@@ -126,36 +125,16 @@ __global__ void __launch_bounds__(256) count_in_boxes_kernel(
 // setup
 // ---------------------------------------------------------------------------------------------
 void Model::set_box(const f64 bmin[3], const f64 bmax[3], u32 nx, u32 ny, u32 nz) {
-    auto pow2 = [](u32 v) { return v && !(v & (v - 1)); };
-    if (!pow2(nx) || !pow2(ny) || !pow2(nz))
-        throw std::invalid_argument("the patch grid must be made of powers of two");
     for (int d = 0; d < 3; d++) {
         box_min[d] = bmin[d];
         box_max[d] = bmax[d];
     }
+    std::vector<PatchBox> grid = plan_patch_grid(bmin, bmax, nx, ny, nz, world);
     patches.clear();
-    u32 nn[3]  = {nx, ny, nz};
-    u32 np     = nx * ny * nz;
-    patches.resize(np);
-    for (u32 z = 0; z < nz; z++)
-        for (u32 y = 0; y < ny; y++)
-            for (u32 x = 0; x < nx; x++) {
-                u32 k     = x + nx * (y + ny * z);
-                PatchD &p = patches[k];
-                p.id      = k;
-                u32 c[3]  = {x, y, z};
-                for (int d = 0; d < 3; d++) {
-                    u64 sz    = PATCH_GRID / nn[d];
-                    p.cmin[d] = sz * c[d];
-                    p.cmax[d] = sz * (c[d] + 1) - 1;
-                    // CoordRangeTransform<u64_3,f64_3> "multiply": obj = f64(pc) * fact + bmin
-                    f64 fact = (box_max[d] - box_min[d]) / f64(PATCH_GRID);
-                    p.lo[d]  = f64(p.cmin[d]) * fact + box_min[d];
-                    p.hi[d]  = f64(p.cmax[d] + 1) * fact + box_min[d];
-                }
-                // contiguous blocks of patches per rank (ids ascending)
-                p.owner = int((u64(k) * u64(world)) / np);
-            }
+    patches.resize(grid.size());
+    for (size_t k = 0; k < grid.size(); k++)
+        static_cast<PatchBox &>(patches[k]) = grid[k];
+    u32 np = u32(grid.size());
     std::vector<f64> hb(size_t(np) * 6);
     for (u32 k = 0; k < np; k++)
         for (int d = 0; d < 3; d++) {
@@ -376,105 +355,140 @@ void Model::apply_position_boundary() {
     reattribute_patch_objects();
 }
 
-/// ReattributeDataUtility::reatribute_patch_objects (ReattributeDataUtility.hpp:40-230)
+/// histogram of the owner patch ids of one patch's particles (slot np = "no owner")
+__global__ void __launch_bounds__(256) owner_hist_kernel(u32 n, const u32 *__restrict__ owner, u32 np, u32 *__restrict__ counts) {
+    extern __shared__ u32 sc[];
+    for (u32 j = threadIdx.x; j <= np; j += blockDim.x)
+        sc[j] = 0;
+    __syncthreads();
+    for (u64 i = u64(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += u64(gridDim.x) * blockDim.x) {
+        u32 o = owner[i];
+        atomicAdd(&sc[o < np ? o : np], 1u);
+    }
+    __syncthreads();
+    for (u32 j = threadIdx.x; j <= np; j += blockDim.x)
+        if (sc[j])
+            atomicAdd(&counts[j], sc[j]);
+}
+
+/// ReattributeDataUtility::reatribute_patch_objects (ReattributeDataUtility.hpp:40-230): particles that
+/// left their patch are extracted (order preserving) and appended to their new owner, senders in
+/// ascending patch id (the multimap order of the reference's part_exchange).  Across ranks the rows
+/// travel as one NCCL send/recv per field.
 void Model::reattribute_patch_objects() {
-    size_t np = patches.size();
+    const size_t np = patches.size();
     if (np == 1)
         return; // single patch: periodic → everything is inside after the wrap; free → no constraint
-    if (world > 1)
-        throw std::runtime_error("particle migration between ranks: see solver_comm.cu");
-    // owners and stay flags per patch
-    struct Mig {
-        u32 src, dst, count;
-        DevBuf<u32> ids;
-    };
-    std::vector<Mig> migs;
+    // 1. owners + per-destination counts of every local patch (one read-back per patch)
     std::vector<DevBuf<u32>> owners(np);
-    std::vector<u32> kept(np, 0);
-    bool any = false;
+    std::vector<u64> cm(np * np, 0); // cm[src*np + dst]
+    box_counts.ensure(np + 1);
     for (size_t k = 0; k < np; k++) {
         PatchD &p = patches[k];
-        if (!p.f.n)
+        if (!is_local(p) || !p.f.n)
             continue;
         flag.ensure(p.f.n);
         owners[k].ensure(p.f.n);
         patch_owner(s(), p.f.n, p.f.xyz.p, u32(np), d_boxes.p, u32(k), flag.p, owners[k].p);
-        pos.ensure(p.f.n);
-        exclusive_scan<u8>(s(), flag.p, pos.p, p.f.n, scan_tmp, red.p + 5);
-        SB_CUDA_CHECK(cudaMemcpyAsync(h_red.p + 5, red.p + 5, sizeof(u64), cudaMemcpyDeviceToHost, s()));
+        SB_CUDA_CHECK(cudaMemsetAsync(box_counts.p, 0, (np + 1) * sizeof(u32), s()));
+        unsigned nb = (unsigned) std::min<u64>(u64(kNumSM) * 8, (u64(p.f.n) + 255) / 256);
+        owner_hist_kernel<<<nb, 256, (np + 1) * sizeof(u32), s()>>>(p.f.n, owners[k].p, u32(np), box_counts.p);
+        SB_COUNT_LAUNCH();
+        std::vector<u32> hc(np + 1);
+        SB_CUDA_CHECK(cudaMemcpyAsync(hc.data(), box_counts.p, (np + 1) * sizeof(u32), cudaMemcpyDeviceToHost, s()));
         SB_CUDA_CHECK(cudaStreamSynchronize(s()));
-        kept[k] = u32(h_red.p[5]);
-        if (kept[k] == p.f.n)
-            continue;
-        any = true;
-        for (size_t d = 0; d < np; d++) {
-            if (d == k)
-                continue;
-            flag_equal(s(), p.f.n, owners[k].p, u32(d), flag.p);
-            exclusive_scan<u8>(s(), flag.p, pos.p, p.f.n, scan_tmp, red.p + 5);
-            SB_CUDA_CHECK(cudaMemcpyAsync(h_red.p + 5, red.p + 5, sizeof(u64), cudaMemcpyDeviceToHost, s()));
-            SB_CUDA_CHECK(cudaStreamSynchronize(s()));
-            u32 cnt = u32(h_red.p[5]);
-            if (!cnt)
-                continue;
-            Mig m;
-            m.src   = u32(k);
-            m.dst   = u32(d);
-            m.count = cnt;
-            m.ids.ensure(cnt);
-            scatter_ids(s(), p.f.n, flag.p, pos.p, m.ids.p);
-            migs.push_back(std::move(m));
-        }
-        // particles owned by nobody (outside the box with free boundaries) cannot be attributed
-        u32 moved = 0;
-        for (auto &m : migs)
-            if (m.src == k)
-                moved += m.count;
-        if (kept[k] + moved != p.f.n)
+        if (hc[np])
             throw std::runtime_error("a new id could not be computed");
+        for (size_t d = 0; d < np; d++)
+            if (d != k)
+                cm[k * np + d] = hc[d];
     }
+    comm_allreduce_host_u64(*this, cm.data(), cm.size(), 1);
+    bool any = false;
+    for (u64 v : cm)
+        any = any || v;
     if (!any)
         return;
-    // stage the migrants (all fields) before compacting the sources
-    struct Staged {
-        std::vector<DevBuf<f64>> f;
+    // 2. stage the migrants of the local senders (all fields) before compacting the sources
+    struct Mig {
+        u32 src, dst, count;
+        std::vector<DevBuf<f64>> f; // staged rows (local sender only)
     };
-    std::vector<Staged> staged(migs.size());
-    for (size_t q = 0; q < migs.size(); q++) {
-        PatchD &src = patches[migs[q].src];
-        auto refs   = src.f.all();
-        staged[q].f.resize(refs.size());
+    std::vector<Mig> migs;
+    for (size_t k = 0; k < np; k++)
+        for (size_t d = 0; d < np; d++)
+            if (cm[k * np + d]) {
+                Mig m;
+                m.src   = u32(k);
+                m.dst   = u32(d);
+                m.count = u32(cm[k * np + d]);
+                migs.push_back(std::move(m));
+            }
+    for (auto &m : migs) {
+        PatchD &src = patches[m.src];
+        if (!is_local(src))
+            continue;
+        flag_equal(s(), src.f.n, owners[m.src].p, m.dst, flag.p);
+        pos.ensure(src.f.n);
+        exclusive_scan<u8>(s(), flag.p, pos.p, src.f.n, scan_tmp, red.p + 5);
+        owner_tmp.ensure(m.count);
+        scatter_ids(s(), src.f.n, flag.p, pos.p, owner_tmp.p);
+        auto refs = src.f.all();
+        m.f.resize(refs.size());
         for (size_t r = 0; r < refs.size(); r++) {
-            staged[q].f[r].ensure(size_t(migs[q].count) * refs[r].nvar);
-            gather_field(s(), migs[q].count, refs[r].nvar, migs[q].ids.p, refs[r].buf->p, staged[q].f[r].p);
+            m.f[r].ensure(size_t(m.count) * refs[r].nvar);
+            gather_field(s(), m.count, refs[r].nvar, owner_tmp.p, refs[r].buf->p, m.f[r].p);
         }
     }
+    // 3. compact the sources
     for (size_t k = 0; k < np; k++) {
         PatchD &p = patches[k];
-        if (!p.f.n || kept[k] == p.f.n)
+        if (!is_local(p) || !p.f.n)
+            continue;
+        u64 out = 0;
+        for (size_t d = 0; d < np; d++)
+            out += cm[k * np + d];
+        if (!out)
             continue;
         flag_equal(s(), p.f.n, owners[k].p, u32(k), flag.p);
         keep_flagged(p);
     }
-    // append: sender ascending, then receiver (multimap order of part_exchange)
-    for (size_t q = 0; q < migs.size(); q++) {
-        PatchD &dst = patches[migs[q].dst];
-        u32 newn    = dst.f.n + migs[q].count;
-        dst.f.reserve(newn, s());
-        auto refs = dst.f.all();
-        for (size_t r = 0; r < refs.size(); r++)
-            SB_CUDA_CHECK(cudaMemcpyAsync(
-                refs[r].buf->p + size_t(dst.f.n) * refs[r].nvar, staged[q].f[r].p,
-                size_t(migs[q].count) * refs[r].nvar * sizeof(f64), cudaMemcpyDeviceToDevice, s()));
-        dst.f.n = newn;
+    // 4. append at the destinations: (sender, receiver) ascending
+    for (auto &m : migs) {
+        PatchD &dst = patches[m.dst];
+        if (is_local(dst))
+            dst.f.reserve(dst.f.n + m.count, s());
     }
+    comm_group_start(*this);
+    for (auto &m : migs) {
+        PatchD &src = patches[m.src];
+        PatchD &dst = patches[m.dst];
+        auto refs   = dst.f.all();
+        if (is_local(dst)) {
+            for (size_t r = 0; r < refs.size(); r++) {
+                f64 *tail    = refs[r].buf->p + size_t(dst.f.n) * refs[r].nvar;
+                size_t bytes = size_t(m.count) * refs[r].nvar * sizeof(f64);
+                if (is_local(src))
+                    SB_CUDA_CHECK(cudaMemcpyAsync(tail, m.f[r].p, bytes, cudaMemcpyDeviceToDevice, s()));
+                else
+                    comm_recv(*this, tail, bytes, src.owner);
+            }
+            dst.f.n += m.count;
+        } else if (is_local(src)) {
+            for (size_t r = 0; r < refs.size(); r++)
+                comm_send(*this, m.f[r].p, size_t(m.count) * refs[r].nvar * sizeof(f64), dst.owner);
+        }
+    }
+    comm_group_end(*this);
     SB_CUDA_CHECK(cudaStreamSynchronize(s()));
 }
 
 // ---------------------------------------------------------------------------------------------
 // ghost zones
 // ---------------------------------------------------------------------------------------------
-/// SPHUtilities::build_interf_cache + BasicSPHGhostHandler::find_interfaces / gen_id_table_interfaces
+/// SPHUtilities::build_interf_cache + BasicSPHGhostHandler::find_interfaces / gen_id_table_interfaces.
+/// The interface plan is a pure function of replicated metadata (ghost_plan.hpp); the metadata
+/// (per-patch max h and particle count, per-interface ghost count) is all-reduced over NCCL.
 void Model::build_ghost_cache() {
     const size_t np = patches.size();
     const f64 Rkern = cfg.kernel == SHAMB200_KERNEL_M4 ? 2.0 : 3.0;
@@ -486,65 +500,25 @@ void Model::build_ghost_cache() {
         if (is_local(patches[k]) && patches[k].f.n)
             max_reduce(s(), patches[k].f.n, patches[k].f.hpart.p, red.p + 8 + k);
     read_red(8 + int(np));
+    std::vector<u64> meta(2 * np, 0); // [ordered max h | count]; remote patches contribute 0
+    for (size_t k = 0; k < np; k++)
+        if (is_local(patches[k]) && patches[k].f.n) {
+            meta[k]      = h_red.p[8 + k];
+            meta[np + k] = patches[k].f.n;
+        }
+    comm_allreduce_host_u64(*this, meta.data(), meta.size(), 1);
     std::vector<f64> interactR(np, std::numeric_limits<f64>::lowest());
     std::vector<u32> pcount(np, 0);
     for (size_t k = 0; k < np; k++)
-        if (is_local(patches[k]) && patches[k].f.n) {
-            interactR[k] = ordered_to_f64(h_red.p[8 + k]) * cfg.htol_up_coarse_cycle * Rkern;
-            pcount[k]    = patches[k].f.n;
+        if (meta[np + k]) {
+            interactR[k] = ordered_to_f64(meta[k]) * cfg.htol_up_coarse_cycle * Rkern;
+            pcount[k]    = u32(meta[np + k]);
         }
-    // (multi-rank: interactR / pcount are all-gathered in solver_comm.cu)
-
-    f64 bsize[3] = {box_max[0] - box_min[0], box_max[1] - box_min[1], box_max[2] - box_min[2]};
-    int rep      = (cfg.bc == SHAMB200_BC_PERIODIC) ? 1 : 0;
-    std::vector<Iface> cand;
-    for (i32 xoff = -rep; xoff <= rep; xoff++)
-        for (i32 yoff = -rep; yoff <= rep; yoff++)
-            for (i32 zoff = -rep; zoff <= rep; zoff++) {
-                f64 off[3] = {xoff * bsize[0], yoff * bsize[1], zoff * bsize[2]};
-                for (size_t sd = 0; sd < np; sd++) {
-                    if (!pcount[sd])
-                        continue;
-                    const PatchD &S = patches[sd];
-                    for (size_t rc = 0; rc < np; rc++) {
-                        if (!pcount[rc])
-                            continue;
-                        if (rc == sd && xoff == 0 && yoff == 0 && zoff == 0)
-                            continue;
-                        const PatchD &R = patches[rc];
-                        f64 Rr          = interactR[rc];
-                        bool ok         = true;
-                        Iface itf;
-                        for (int d = 0; d < 3; d++) {
-                            f64 elo = R.lo[d] - Rr, ehi = R.hi[d] + Rr;
-                            f64 so_lo = S.lo[d] + off[d], so_hi = S.hi[d] + off[d];
-                            f64 ilo = std::fmax(elo, so_lo), ihi = std::fmin(ehi, so_hi);
-                            if (!(ihi >= ilo))
-                                ok = false;
-                            f64 moff      = -off[d];
-                            itf.cut_lo[d] = std::fmax(S.lo[d], elo + moff);
-                            itf.cut_hi[d] = std::fmin(S.hi[d], ehi + moff);
-                            itf.offset[d] = off[d];
-                        }
-                        if (!ok)
-                            continue;
-                        itf.sender   = u32(sd);
-                        itf.receiver = u32(rc);
-                        itf.ioff[0]  = xoff;
-                        itf.ioff[1]  = yoff;
-                        itf.ioff[2]  = zoff;
-                        cand.push_back(std::move(itf));
-                    }
-                }
-            }
-    // multimap<(sender,receiver)> order, equal keys in insertion (offset loop) order
-    std::stable_sort(cand.begin(), cand.end(), [&](const Iface &a, const Iface &b) {
-        if (patches[a.sender].id != patches[b.sender].id)
-            return patches[a.sender].id < patches[b.sender].id;
-        return patches[a.receiver].id < patches[b.receiver].id;
-    });
+    std::vector<IfaceCand> cand
+        = plan_interfaces(std::vector<PatchBox>(patches.begin(), patches.end()), box_min, box_max,
+                          cfg.bc == SHAMB200_BC_PERIODIC, interactR, pcount);
     // counts of every candidate with a local sender: one kernel per sender patch
-    std::vector<u32> counts(cand.size(), 0);
+    std::vector<u64> counts(cand.size(), 0);
     for (size_t sd = 0; sd < np; sd++) {
         if (!is_local(patches[sd]) || !patches[sd].f.n)
             continue;
@@ -575,14 +549,23 @@ void Model::build_ghost_cache() {
         for (size_t j = 0; j < mine.size(); j++)
             counts[mine[j]] = hc[j];
     }
+    comm_allreduce_host_u64(*this, counts.data(), counts.size(), 1);
     // keep the non-empty interfaces ("prevent sending empty patches"), build their id lists
     ifaces.clear();
     std::vector<u32> ghost_run(np, 0);
     for (size_t q = 0; q < cand.size(); q++) {
         if (!counts[q])
             continue;
-        Iface itf   = std::move(cand[q]);
-        itf.count   = counts[q];
+        Iface itf;
+        itf.sender   = cand[q].sender;
+        itf.receiver = cand[q].receiver;
+        for (int d = 0; d < 3; d++) {
+            itf.offset[d] = cand[q].offset[d];
+            itf.ioff[d]   = cand[q].ioff[d];
+            itf.cut_lo[d] = cand[q].cut_lo[d];
+            itf.cut_hi[d] = cand[q].cut_hi[d];
+        }
+        itf.count   = u32(counts[q]);
         itf.dst_off = ghost_run[itf.receiver];
         ghost_run[itf.receiver] += itf.count;
         PatchD &S = patches[itf.sender];
@@ -595,6 +578,13 @@ void Model::build_ghost_cache() {
             scatter_ids(s(), S.f.n, flag.p, pos.p, itf.ids.p);
         }
         ifaces.push_back(std::move(itf));
+    }
+    // staging offsets of the interfaces this rank sends to another rank
+    send_total = 0;
+    for (auto &itf : ifaces) {
+        itf.stage_off = send_total;
+        if (is_local(patches[itf.sender]) && !is_local(patches[itf.receiver]))
+            send_total += itf.count;
     }
     for (size_t k = 0; k < np; k++) {
         patches[k].st.n = patches[k].f.n;
@@ -611,12 +601,22 @@ void Model::merge_position_ghost() {
         st.A.ensure(st.m, 1.1);
         pack_xyzh(s(), st.n, p.f.xyz.p, p.f.hpart.p, st.A.p);
     }
+    send_stage.ensure(send_total, 1.1);
+    comm_group_start(*this);
     for (auto &itf : ifaces) {
         PatchD &R = patches[itf.receiver];
         PatchD &S = patches[itf.sender];
-        if (is_local(R) && is_local(S))
+        if (is_local(R) && is_local(S)) {
             ghost_xyzh(s(), itf.count, itf.ids.p, S.f.xyz.p, S.f.hpart.p, itf.offset, R.st.A.p + R.st.n + itf.dst_off);
+        } else if (is_local(S)) { // C1: positions + h of the ghosts, 32 B each, straight from the gather
+            Pack4 *stg = send_stage.p + itf.stage_off;
+            ghost_xyzh(s(), itf.count, itf.ids.p, S.f.xyz.p, S.f.hpart.p, itf.offset, stg);
+            comm_send(*this, stg, size_t(itf.count) * sizeof(Pack4), R.owner);
+        } else if (is_local(R)) {
+            comm_recv(*this, R.st.A.p + R.st.n + itf.dst_off, size_t(itf.count) * sizeof(Pack4), S.owner);
+        }
     }
+    comm_group_end(*this);
     if (cfg.keep_step_data)
         for (auto &p : patches)
             if (is_local(p) && p.f.n) {
@@ -709,7 +709,9 @@ void Model::sph_prestep() {
         bool should_rerun_gz = local_min_eps < 0;
         bool below_tol       = local_max_eps < cfg.epsilon_h;
         bool converged       = below_tol && !should_rerun_gz;
-        // (multi-rank: are_all_rank_true in solver_comm.cu)
+        u64 all_conv         = converged ? 1 : 0; // are_all_rank_true (LoopSmoothingLengthIter.cpp:63-64)
+        comm_allreduce_host_u64(*this, &all_conv, 1, 2);
+        converged = all_conv != 0;
         if (!converged)
             continue;
         break;
@@ -729,6 +731,8 @@ void Model::sph_prestep() {
 /// Solver::communicate_merge_ghosts_fields (Solver.cpp:1394-1633)
 void Model::communicate_merge_ghosts_fields() {
     const bool has_a = cfg.av == SHAMB200_AV_CD10;
+    std::vector<std::pair<const Iface *, size_t>> recv_plan;
+    size_t recv_total = 0;
     for (auto &p : patches) {
         if (!is_local(p) || !p.f.n)
             continue;
@@ -741,15 +745,47 @@ void Model::communicate_merge_ghosts_fields() {
             s(), st.n, nullptr, p.f.hpart.p, p.f.vxyz.p, p.f.uint_.p, st.omega.p, has_a ? p.f.axyz.p : nullptr,
             st.A.p, st.B.p, st.C.p, st.D.p);
     }
+    // C2: the ghost fields.  Remote interfaces are staged as [A | B | C | (D)] blocks of Pack4; the
+    // receiver gets them straight into its merged arrays (A keeps its position, h is refreshed by a
+    // small kernel from the staged copy on the sender: A block carries (x,y,z,h) again).
+    const size_t nblk = has_a ? 4 : 3;
+    send_stage.ensure(send_total * nblk, 1.1);
+    comm_group_start(*this);
     for (auto &itf : ifaces) {
         PatchD &R = patches[itf.receiver];
         PatchD &S = patches[itf.sender];
+        const size_t bytes = size_t(itf.count) * sizeof(Pack4);
         if (is_local(R) && is_local(S)) {
             u32 o = R.st.n + itf.dst_off;
             pack_fields(
                 s(), itf.count, itf.ids.p, S.f.hpart.p, S.f.vxyz.p, S.f.uint_.p, S.st.omega.p,
                 has_a ? S.f.axyz.p : nullptr, R.st.A.p + o, R.st.B.p + o, R.st.C.p + o, has_a ? R.st.D.p + o : nullptr);
+        } else if (is_local(S)) {
+            Pack4 *sA = send_stage.p + itf.stage_off * nblk;
+            Pack4 *sB = sA + itf.count, *sC = sB + itf.count, *sD = has_a ? sC + itf.count : nullptr;
+            ghost_xyzh(s(), itf.count, itf.ids.p, S.f.xyz.p, S.f.hpart.p, itf.offset, sA);
+            pack_fields(
+                s(), itf.count, itf.ids.p, S.f.hpart.p, S.f.vxyz.p, S.f.uint_.p, S.st.omega.p,
+                has_a ? S.f.axyz.p : nullptr, sA, sB, sC, sD);
+            comm_send(*this, sA, bytes * nblk, R.owner);
+        } else if (is_local(R)) {
+            // one message per interface: land it in the receive staging, then scatter to A.d/B/C.b/D
+            recv_plan.push_back({&itf, recv_total});
+            recv_total += size_t(itf.count) * nblk;
         }
+    }
+    recv_stage.ensure(recv_total, 1.1);
+    for (auto &rp : recv_plan)
+        comm_recv(*this, recv_stage.p + rp.second, size_t(rp.first->count) * nblk * sizeof(Pack4),
+                  patches[rp.first->sender].owner);
+    comm_group_end(*this);
+    for (auto &rp : recv_plan) {
+        const Iface &itf = *rp.first;
+        PatchD &R        = patches[itf.receiver];
+        u32 o            = R.st.n + itf.dst_off;
+        const Pack4 *sA  = recv_stage.p + rp.second;
+        const Pack4 *sB = sA + itf.count, *sC = sB + itf.count, *sD = has_a ? sC + itf.count : nullptr;
+        unpack_ghost_fields(s(), itf.count, sA, sB, sC, sD, R.st.A.p + o, R.st.B.p + o, R.st.C.p + o, has_a ? R.st.D.p + o : nullptr);
     }
 }
 
@@ -758,11 +794,36 @@ void Model::exchange_alpha_ghosts() {
     for (auto &p : patches)
         if (is_local(p) && p.f.n)
             pack_alpha(s(), p.st.n, nullptr, p.st.alpha_updated.p, p.st.C.p);
+    // C3: 8 B per ghost; remote interfaces go through compact f64 staging on both sides
+    size_t recv_total = 0;
+    for (auto &itf : ifaces)
+        if (is_local(patches[itf.receiver]) && !is_local(patches[itf.sender]))
+            recv_total += itf.count;
+    send_stage_f.ensure(send_total, 1.1);
+    recv_stage_f.ensure(recv_total, 1.1);
+    size_t roff = 0;
+    comm_group_start(*this);
     for (auto &itf : ifaces) {
         PatchD &R = patches[itf.receiver];
         PatchD &S = patches[itf.sender];
-        if (is_local(R) && is_local(S))
+        if (is_local(R) && is_local(S)) {
             pack_alpha(s(), itf.count, itf.ids.p, S.st.alpha_updated.p, R.st.C.p + R.st.n + itf.dst_off);
+        } else if (is_local(S)) {
+            gather_field(s(), itf.count, 1, itf.ids.p, S.st.alpha_updated.p, send_stage_f.p + itf.stage_off);
+            comm_send(*this, send_stage_f.p + itf.stage_off, size_t(itf.count) * sizeof(f64), R.owner);
+        } else if (is_local(R)) {
+            comm_recv(*this, recv_stage_f.p + roff, size_t(itf.count) * sizeof(f64), S.owner);
+            roff += itf.count;
+        }
+    }
+    comm_group_end(*this);
+    roff = 0;
+    for (auto &itf : ifaces) {
+        PatchD &R = patches[itf.receiver];
+        if (is_local(R) && !is_local(patches[itf.sender])) {
+            pack_alpha(s(), itf.count, nullptr, recv_stage_f.p + roff, R.st.C.p + R.st.n + itf.dst_off);
+            roff += itf.count;
+        }
     }
 }
 
@@ -795,7 +856,7 @@ void Model::evolve_once() {
     for (auto &p : patches)
         if (is_local(p))
             npart_all += p.f.n;
-    // (multi-rank: allreduce sum in solver_comm.cu)
+    comm_allreduce_host_u64(*this, &npart_all, 1, 0);
 
     sph_prestep();
 
@@ -877,7 +938,8 @@ void Model::evolve_once() {
         read_red(5);
         f64 rank_veps_v = std::sqrt(ordered_to_f64(h_red.p[2]));
         f64 sum_vsq     = bits_to_f64(h_red.p[3]);
-        // (multi-rank: allreduce sum / max in solver_comm.cu)
+        comm_allreduce_host_f64(*this, &sum_vsq, 1, 0);     // C7 (Solver.cpp:2587)
+        comm_allreduce_host_f64(*this, &rank_veps_v, 1, 1); // C7 (Solver.cpp:2597)
         f64 vmean_sq   = sum_vsq / f64(npart_all);
         f64 vmean      = std::sqrt(vmean_sq);
         f64 rank_eps_v = rank_veps_v / vmean;
@@ -912,7 +974,7 @@ void Model::evolve_once() {
             }
             read_red(5);
             next_cfl = ordered_to_f64(h_red.p[4]);
-            // (multi-rank: allreduce min in solver_comm.cu)
+            comm_allreduce_host_f64(*this, &next_cfl, 1, 2); // C8: global dt (Solver.cpp:3119)
         }
         corrector_iter_cnt++;
     } while (need_rerun_corrector);

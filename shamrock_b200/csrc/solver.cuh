@@ -3,6 +3,7 @@
 // for the configuration subset of SURVEY.md §8.
 #pragma once
 #include "../../include/shamb200.h"
+#include "ghost_plan.hpp"
 #include "neigh.cuh"
 #include "sph.cuh"
 #include "stream_kernels.cuh"
@@ -46,6 +47,7 @@ struct Iface {
     f64 cut_lo[3], cut_hi[3];
     u32 count   = 0;
     u32 dst_off = 0; ///< offset inside the receiver's ghost range
+    size_t stage_off = 0; ///< offset (objects) in the send staging when the receiver is on another rank
     DevBuf<u32> ids;
 };
 
@@ -59,11 +61,7 @@ struct PatchStep {
     DevBuf<f64> mh_snapshot; ///< pre-iteration merged h (keep_step_data only)
 };
 
-struct PatchD {
-    u64 id = 0;
-    u64 cmin[3], cmax[3];
-    f64 lo[3], hi[3];
-    int owner = 0;
+struct PatchD : PatchBox {
     PatchFields f;
     PatchStep st;
 };
@@ -103,6 +101,12 @@ struct Model {
     DevBuf<f64> field_tmp, d_boxes;
     DevBuf<u32> box_counts;
     std::vector<f64> host_tmp;
+    // multi-GPU staging (ghost / migration sends) and host<->device scratch of the scalar allreduces
+    DevBuf<Pack4> send_stage, recv_stage;
+    size_t send_total = 0; ///< ghosts this rank sends to other ranks (objects)
+    DevBuf<f64> send_stage_f, recv_stage_f;
+    DevBuf<u64> comm_dev;
+    PinnedBuf<u64> comm_host;
 
     explicit Model(Ctx *c, const shamb200_solver_config &cf) : ctx(c), cfg(cf) {}
     cudaStream_t s() const { return ctx->stream; }
@@ -138,6 +142,9 @@ void comm_unique_id(void *out128);
 void comm_init(Model &m, int rank, int world, const void *id128);
 void comm_allreduce_f64(Model &m, f64 *d_buf, size_t n, int op); ///< op: 0 sum, 1 max, 2 min
 void comm_allreduce_u64(Model &m, u64 *d_buf, size_t n, int op);
+/// blocking allreduce of a few HOST scalars, in place (no-op when world == 1)
+void comm_allreduce_host_f64(Model &m, f64 *vals, size_t n, int op);
+void comm_allreduce_host_u64(Model &m, u64 *vals, size_t n, int op);
 void comm_group_start(Model &m);
 void comm_group_end(Model &m);
 void comm_send(Model &m, const void *d, size_t bytes, int peer);

@@ -111,6 +111,30 @@ void comm_allreduce_u64(Model &m, u64 *d_buf, size_t n, int op) {
     int nop = op == 0 ? ncclSum_ : (op == 1 ? ncclMax_ : ncclMin_);
     SB_NCCL_CHECK(nccl().AllReduce(d_buf, d_buf, n, ncclUint64_, nop, (ncclComm_t) m.nccl_comm, m.s()));
 }
+void comm_allreduce_host_u64(Model &m, u64 *vals, size_t n, int op) {
+    if (m.world == 1 || n == 0)
+        return;
+    m.comm_dev.ensure(n);
+    m.comm_host.ensure(n);
+    std::memcpy(m.comm_host.p, vals, n * sizeof(u64));
+    SB_CUDA_CHECK(cudaMemcpyAsync(m.comm_dev.p, m.comm_host.p, n * sizeof(u64), cudaMemcpyHostToDevice, m.s()));
+    comm_allreduce_u64(m, m.comm_dev.p, n, op);
+    SB_CUDA_CHECK(cudaMemcpyAsync(m.comm_host.p, m.comm_dev.p, n * sizeof(u64), cudaMemcpyDeviceToHost, m.s()));
+    SB_CUDA_CHECK(cudaStreamSynchronize(m.s()));
+    std::memcpy(vals, m.comm_host.p, n * sizeof(u64));
+}
+void comm_allreduce_host_f64(Model &m, f64 *vals, size_t n, int op) {
+    if (m.world == 1 || n == 0)
+        return;
+    m.comm_dev.ensure(n);
+    m.comm_host.ensure(n);
+    std::memcpy(m.comm_host.p, vals, n * sizeof(f64));
+    SB_CUDA_CHECK(cudaMemcpyAsync(m.comm_dev.p, m.comm_host.p, n * sizeof(f64), cudaMemcpyHostToDevice, m.s()));
+    comm_allreduce_f64(m, reinterpret_cast<f64 *>(m.comm_dev.p), n, op);
+    SB_CUDA_CHECK(cudaMemcpyAsync(m.comm_host.p, m.comm_dev.p, n * sizeof(f64), cudaMemcpyDeviceToHost, m.s()));
+    SB_CUDA_CHECK(cudaStreamSynchronize(m.s()));
+    std::memcpy(vals, m.comm_host.p, n * sizeof(f64));
+}
 void comm_group_start(Model &m) {
     if (m.world > 1)
         SB_NCCL_CHECK(nccl().GroupStart());
@@ -120,9 +144,13 @@ void comm_group_end(Model &m) {
         SB_NCCL_CHECK(nccl().GroupEnd());
 }
 void comm_send(Model &m, const void *d, size_t bytes, int peer) {
+    if (!bytes)
+        return;
     SB_NCCL_CHECK(nccl().Send(d, bytes, ncclUint8_, peer, (ncclComm_t) m.nccl_comm, m.s()));
 }
 void comm_recv(Model &m, void *d, size_t bytes, int peer) {
+    if (!bytes)
+        return;
     SB_NCCL_CHECK(nccl().Recv(d, bytes, ncclUint8_, peer, (ncclComm_t) m.nccl_comm, m.s()));
 }
 void comm_destroy(Model &m) {

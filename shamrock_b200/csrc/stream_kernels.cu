@@ -302,6 +302,29 @@ void pack_fields(
     SB_COUNT_LAUNCH();
     SB_LAUNCH_CHECK();
 }
+/// received ghost-field blocks → merged arrays: A.d = h, B = (v,u), C.b = omega, D = (a,0)
+__global__ void __launch_bounds__(256) unpack_ghost_fields_kernel(
+    u32 cnt, const Pack4 *__restrict__ sA, const Pack4 *__restrict__ sB, const Pack4 *__restrict__ sC,
+    const Pack4 *__restrict__ sD, Pack4 *__restrict__ A, Pack4 *__restrict__ B, Pack4 *__restrict__ C,
+    Pack4 *__restrict__ D) {
+    u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= cnt)
+        return;
+    A[k].d = sA[k].d;
+    B[k]   = sB[k];
+    C[k].b = sC[k].b;
+    if (sD)
+        D[k] = sD[k];
+}
+void unpack_ghost_fields(
+    cudaStream_t s, u32 cnt, const Pack4 *sA, const Pack4 *sB, const Pack4 *sC, const Pack4 *sD, Pack4 *A, Pack4 *B,
+    Pack4 *C, Pack4 *D) {
+    if (!cnt)
+        return;
+    unpack_ghost_fields_kernel<<<grid_for(cnt, 256), 256, 0, s>>>(cnt, sA, sB, sC, sD, A, B, C, D);
+    SB_COUNT_LAUNCH();
+    SB_LAUNCH_CHECK();
+}
 /// C[k].d = alpha[ids ? ids[k] : k]
 __global__ void __launch_bounds__(256) pack_alpha_kernel(u32 cnt, const u32 *__restrict__ ids, const f64 *__restrict__ alpha, Pack4 *__restrict__ C) {
     u32 k = blockIdx.x * blockDim.x + threadIdx.x;

@@ -18,6 +18,8 @@ void pack_xyzh(cudaStream_t s, u32 n, const f64 *xyz, const f64 *h, Pack4 *A);
 void ghost_xyzh(cudaStream_t s, u32 cnt, const u32 *ids, const f64 *xyz, const f64 *h, const f64 off[3], Pack4 *A_dst);
 void pack_fields(cudaStream_t s, u32 cnt, const u32 *ids, const f64 *h, const f64 *vxyz, const f64 *uint_,
                  const f64 *omega, const f64 *axyz, Pack4 *A, Pack4 *B, Pack4 *C, Pack4 *D);
+void unpack_ghost_fields(cudaStream_t s, u32 cnt, const Pack4 *sA, const Pack4 *sB, const Pack4 *sC, const Pack4 *sD,
+                         Pack4 *A, Pack4 *B, Pack4 *C, Pack4 *D);
 void pack_alpha(cudaStream_t s, u32 cnt, const u32 *ids, const f64 *alpha, Pack4 *C);
 void unpack_cs(cudaStream_t s, u32 n, const Pack4 *C, f64 *cs);
 void unpack_comp(cudaStream_t s, u32 n, const Pack4 *P, int first, int nc, f64 *out);

@@ -1,0 +1,71 @@
+"""torchrun worker of tests/test_gpu_multirank.py: one process per GPU, NCCL ghost exchange; every rank
+checks its local patches against the single-process oracle (bit-exact in the strict build)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from shamrock_b200 import _capi  # noqa: E402
+from tests import scenarios as S  # noqa: E402
+from tests.test_gpu_step import INT_NAMES, close  # noqa: E402
+
+
+def main():
+    which = sys.argv[1]
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ids = [_capi.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    if which == "periodic":
+        sc = S.periodic_box(16000, "M4", "cd10", jitter=0.2, grid=(2, 2, 1))
+        steps, rtol = 4, 0.0
+    elif which == "sod":
+        sc = S.sod_tube(16, "M6", grid=(4, 1, 1))
+        steps, rtol = 2, 0.0
+    else:
+        sc = S.disc(8000, "M4", grid=(2, 2, 2))
+        steps, rtol = 2, 1e-12
+    strict = b"strict" in _capi.lib().shamb200_build_info()
+    if not strict:
+        rtol = 1e-10
+    o = S.make_oracle(sc)
+    m = S.make_cuda(sc, ctx=_capi.Context(local), rank=rank, world=world, nccl_id=ids[0])
+    names = ["xyz", "vxyz", "axyz", "hpart", "uint", "duint", "step.mxyz", "step.omega", "step.pressure", "step.g_v",
+             "step.vsig"]
+    if sc["cfg"]["av"] == 3:
+        names += ["alpha_AV", "divv", "curlv", "dtdivv", "step.g_a", "step.g_alpha"]
+    nloc = 0
+    for k in range(steps):
+        so, sm = o.evolve_once(), m.evolve_once()
+        for key in ("h_subcycles", "corrector_iter", "npart"):
+            assert so[key] == sm[key], (k, key, so[key], sm[key])
+        ok, msg = close([sm["dt"]], [so["dt"]], rtol)
+        assert ok, ("dt", k, so["dt"], sm["dt"])
+        for ip in range(m.patch_count):
+            if not m.patch_is_local(ip):
+                continue
+            assert m.patch_size(ip) == o.patch_size(ip), (k, ip, m.patch_size(ip), o.patch_size(ip))
+            if not m.patch_size(ip):
+                continue
+            nloc += 1
+            for nm in INT_NAMES:
+                assert np.array_equal(m.get(ip, nm), o.get(ip, nm)), (k, ip, nm)
+            for nm in names:
+                ok, msg = close(m.get(ip, nm), o.get(ip, nm), rtol)
+                assert ok, (k, ip, nm, msg)
+    assert nloc > 0
+    moved = sum(o.patch_size(ip) for ip in range(o.patch_count))
+    dist.barrier()
+    print(f"rank {rank}: {which} ok ({nloc} patch-steps checked, N={moved})", flush=True)
+    m.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

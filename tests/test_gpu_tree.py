@@ -312,13 +312,12 @@ def test_tree_large_properties(ctx, n, mode):
     assert (np.diff(a["reduced_morton"].astype(np.int64)) > 0).all()  # unique leaf codes
     assert np.array_equal(a["reduced_morton"], sm[rim[:L]])
     # every node except the root has exactly one parent; leaves and internal cells all covered
-    tgt = np.concatenate([a["lchild_id"].astype(np.int64) + I * a["lchild_flag"],
-                          a["rchild_id"].astype(np.int64) + I * a["rchild_flag"]])
+    lc = a["lchild_id"].astype(np.int64) + I * a["lchild_flag"].astype(np.int64)
+    rc = a["rchild_id"].astype(np.int64) + I * a["rchild_flag"].astype(np.int64)
+    tgt = np.concatenate([lc, rc])
     assert np.array_equal(np.sort(tgt), np.arange(1, I + L))
     # root box = box of all points; every child box inside its parent's
     pos = xyz.cpu().numpy()
     assert np.array_equal(a["aabb_min"][0], pos.min(0)) and np.array_equal(a["aabb_max"][0], pos.max(0))
-    lc = a["lchild_id"].astype(np.int64) + I * a["lchild_flag"]
-    rc = a["rchild_id"].astype(np.int64) + I * a["rchild_flag"]
     assert np.array_equal(a["aabb_min"][:I], np.minimum(a["aabb_min"][lc], a["aabb_min"][rc]))
     assert np.array_equal(a["aabb_max"][:I], np.maximum(a["aabb_max"][lc], a["aabb_max"][rc]))

@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--npart-per-gpu", type=int, default=16 * 2**20)
     ap.add_argument("--cpu-sample", type=int, default=400000)
     ap.add_argument("--impl", default="b200")
+    ap.add_argument("--fp", default="fast", choices=["fast", "strict"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -207,7 +208,7 @@ def main():
 
     sc = workload(args.npart_per_gpu, world)
     ctx = _capi.Context(local)
-    m = S.make_cuda(sc, ctx=ctx, keep_step_data=False, rank=rank, world=world, nccl_id=nccl_id)
+    m = S.make_cuda(sc, ctx=ctx, keep_step_data=False, rank=rank, world=world, nccl_id=nccl_id, fp_mode=args.fp)
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
 
     def barrier():
@@ -320,7 +321,9 @@ def main():
             "config": {"workload": "C4: periodic HCP box, M4 kernel, CD10 AV, adiabatic gamma=5/3, Sedov-like uint "
                        "injection, dt=0 replay (reference protocol sph_homogeneous_benchmark.py)",
                        "npart_total": n_total, "npart_per_gpu": n_total // world, "neighbours_per_particle": K / max(N, 1),
-                       "patches": list(sc["grid"]), "sort": sc["sort_mode"], "fp": _capi.lib().shamb200_build_info().decode(),
+                       "patches": list(sc["grid"]), "sort": sc["sort_mode"],
+                       "fp": {"fast": "fast (FMA, per-particle reciprocals; parity 1e-10 relative vs the oracle)",
+                              "strict": "strict (no FMA, bit-identical to the oracle)"}[args.fp],
                        "l2": "inputs larger than L2 (no flush needed)",
                        "vs_baseline_ref": "reference on 1x H100, 25.5 M part/s (BASELINE.md §1)"},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,

@@ -48,6 +48,12 @@ enum { SHAMB200_SORT_BITONIC = 0, SHAMB200_SORT_RADIX = 1 };
 enum { SHAMB200_EOS_ADIABATIC = 0, SHAMB200_EOS_ISOTHERMAL = 1, SHAMB200_EOS_LOCALLY_ISOTHERMAL_LP07 = 2 };
 enum { SHAMB200_AV_NONE = 0, SHAMB200_AV_CONSTANT = 1, SHAMB200_AV_MM97 = 2, SHAMB200_AV_CD10 = 3, SHAMB200_AV_CONSTANT_DISC = 4 };
 enum { SHAMB200_BC_FREE = 0, SHAMB200_BC_PERIODIC = 1 };
+/* floating-point contract of the SPH loops of the model path.  STRICT: the reference's expressions in
+ * the reference's order, no FMA contraction: every float64 output is bit-identical to a CPU run of the
+ * reference algorithms (the oracle).  FAST: same algorithm, pair math restructured (per-particle
+ * reciprocals, rsqrt, FMA, several lanes per particle): within 1e-10 relative per particle.  Integer
+ * outputs (Morton codes, sort permutation, tree, neighbour lists) are exact in both modes. */
+enum { SHAMB200_FP_STRICT = 0, SHAMB200_FP_FAST = 1 };
 
 const char *shamb200_last_error(void);
 /* library / build information ("sm_100a", strict-fp flag, ...) */
@@ -179,6 +185,8 @@ typedef struct shamb200_solver_config {
     double pm_mass, pm_racc, constant_G;
     int32_t n_kill_spheres;
     int32_t keep_step_data; /* keep per-step intermediates for shamb200_model_get (tests) */
+    int32_t fp_mode;        /* SHAMB200_FP_*                                   */
+    int32_t reserved0;
     double kill_center[4][3];
     double kill_radius[4];
 } shamb200_solver_config;

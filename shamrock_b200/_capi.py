@@ -13,6 +13,7 @@ SORT_MODES = {"bitonic": 0, "radix": 1}
 EOS = {"adiabatic": 0, "isothermal": 1, "locally_isothermal_lp07": 2}
 AV = {"none": 0, "constant": 1, "varying_mm97": 2, "varying_cd10": 3, "constant_disc": 4}
 BC = {"free": 0, "periodic": 1}
+FP_MODES = {"strict": 0, "fast": 1}
 
 
 class ShamB200Error(RuntimeError):
@@ -53,6 +54,7 @@ class SolverConfig(C.Structure):
         ("sort_mode", C.c_int32), ("has_point_mass", C.c_int32),
         ("pm_mass", C.c_double), ("pm_racc", C.c_double), ("constant_G", C.c_double),
         ("n_kill_spheres", C.c_int32), ("keep_step_data", C.c_int32),
+        ("fp_mode", C.c_int32), ("reserved0", C.c_int32),
         ("kill_center", (C.c_double * 3) * 4), ("kill_radius", C.c_double * 4),
     ]
 

@@ -2,9 +2,9 @@
 
     python -m shamrock_b200.build [--force]
 
-The tree / neighbour / streaming kernels are always compiled with -fmad=false (bit-exact integer
-and comparison results).  The SPH loops are compiled strict by default (bit-identical to the CPU
-oracle); SHAMB200_FAST_MATH=1 allows FMA contraction in sph.cu only (1e-10 relative contract).
+Everything is compiled with -fmad=false (bit-exact integer and comparison results, float64 outputs
+bit-identical to the CPU oracle) except sph2_fast.cu, the fast-fp variant of the SPH loops selected at
+run time by shamb200_solver_config.fp_mode (FMA contraction on, 1e-10 relative contract).
 """
 import os
 import subprocess
@@ -19,10 +19,15 @@ LIB = os.path.join(HERE, "libshamb200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off"]
 SOURCES = {
+    "runtime.cu": ["-fmad=false"],
     "tree.cu": ["-fmad=false"],
     "neigh.cu": ["-fmad=false"],
     "stream_kernels.cu": ["-fmad=false"],
-    "sph.cu": None,  # strict / fast decided below
+    "sph.cu": ["-fmad=false"],
+    "neigh2.cu": ["-fmad=false"],
+    "sph2.cu": ["-fmad=false"],
+    "sph2_strict.cu": ["-fmad=false"],
+    "sph2_fast.cu": ["-fmad=true"],
     "solver.cu": ["-fmad=false"],
     "solver_comm.cu": ["-fmad=false"],
     "capi.cu": ["-fmad=false"],
@@ -54,13 +59,10 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     os.makedirs(OBJ, exist_ok=True)
-    fast = os.environ.get("SHAMB200_FAST_MATH", "0") == "1"
     nvcc = _nvcc()
 
     def compile_one(item):
         src, flags = item
-        if flags is None:
-            flags = ["-fmad=true", "-DSB_FAST_MATH"] if fast else ["-fmad=false"]
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))
         cmd = [nvcc, "-ccbin", _host_cxx()] + ARCH + COMMON + flags + ["-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:

@@ -55,11 +55,7 @@ extern "C" {
 
 const char *shamb200_last_error(void) { return g_err.c_str(); }
 const char *shamb200_build_info(void) {
-#ifdef SB_FAST_MATH
-    return "shamb200 sm_100a fp=fast(fma) tree=strict";
-#else
-    return "shamb200 sm_100a fp=strict(no-fma, bit-exact with the oracle)";
-#endif
+    return "shamb200 sm_100a fp=strict(no-fma, bit-exact with the oracle)+fast(fma), selected by fp_mode";
 }
 uint64_t shamb200_launch_count(void) { return g_launch_count; }
 void shamb200_reset_launch_count(void) { g_launch_count = 0; }
@@ -136,9 +132,21 @@ int shamb200_neigh_cache_build(
     return guard([&] {
         if (tree->d_sort_index_map != ctx->c.api_tree.index_map.p)
             throw std::invalid_argument("the tree view is stale (not the last tree built by this context)");
+        if (two_stage) { // the B200 search (neigh2.cu), exported in the reference's ObjectCache layout
+            SearchBuffers &sb = ctx->c.api_srch;
+            search_prepare_sorted_strided(ctx->c.stream, ctx->c.api_tree, sb, d_xyz, stride_dbl, d_hpart, 1, obj_cnt);
+            search_build(ctx->c.stream, ctx->c.api_tree, sb, d_rint, Rkern, h_tolerance);
+            export_object_cache(ctx->c.stream, ctx->c.api_tree, sb);
+            out->obj_cnt           = sb.N;
+            out->sum_neigh_cnt     = u32(sb.K);
+            out->d_cnt_neigh       = sb.x_cnt.p;
+            out->d_scanned_cnt     = sb.x_scanned.p;
+            out->d_index_neigh_map = sb.x_list.p;
+            return;
+        }
         neigh_cache_build(
             ctx->c.stream, ctx->c.api_tree, ctx->c.api_nb, d_xyz, stride_dbl, d_hpart, d_rint, obj_cnt, Rkern,
-            h_tolerance, two_stage != 0, 1);
+            h_tolerance, false, 1);
         out->obj_cnt           = ctx->c.api_nb.N;
         out->sum_neigh_cnt     = ctx->c.api_nb.K;
         out->d_cnt_neigh       = ctx->c.api_nb.cnt.p;

@@ -41,6 +41,16 @@ constexpr int kNumSM = 148; // B200
 
 inline unsigned grid_for(u64 n, unsigned block) { return (unsigned) ((n + block - 1) / block); }
 
+/// Caching device allocator (runtime.cu): freed blocks are kept in size buckets and handed out again,
+/// so the per-step scratch of the solver never reaches cudaMalloc/cudaFree (which synchronise the
+/// device) after the first steps.  Safe without events because each context enqueues all of its
+/// work on ONE in-order stream.  Replaces sham::DeviceBuffer's USM allocations for this path
+/// (shambackends/include/shambackends/DeviceBuffer.hpp).
+void *pool_alloc(size_t bytes);
+void pool_free(void *p);
+void pool_release_all();            ///< give every cached block back to the driver
+size_t pool_bytes_reserved();
+
 /// grow-only device buffer (no preservation unless asked)
 template<class T>
 struct DevBuf {
@@ -66,7 +76,7 @@ struct DevBuf {
     ~DevBuf() { release(); }
     void release() {
         if (p)
-            cudaFree(p);
+            pool_free(p);
         p   = nullptr;
         cap = 0;
     }
@@ -75,8 +85,8 @@ struct DevBuf {
         if (n > cap) {
             release();
             size_t want = size_t(double(n) * slack) + 16;
-            SB_CUDA_CHECK(cudaMalloc(&p, want * sizeof(T)));
-            cap = want;
+            p           = static_cast<T *>(pool_alloc(want * sizeof(T)));
+            cap         = want;
         }
         return p;
     }
@@ -84,14 +94,11 @@ struct DevBuf {
     T *ensure_keep(size_t n, size_t keep, cudaStream_t s, double slack = 1.0) {
         if (n > cap) {
             size_t want = size_t(double(n) * slack) + 16;
-            T *np       = nullptr;
-            SB_CUDA_CHECK(cudaMalloc(&np, want * sizeof(T)));
+            T *np       = static_cast<T *>(pool_alloc(want * sizeof(T)));
             if (p && keep)
                 SB_CUDA_CHECK(cudaMemcpyAsync(np, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, s));
-            if (p) {
-                SB_CUDA_CHECK(cudaStreamSynchronize(s));
-                cudaFree(p);
-            }
+            if (p)
+                pool_free(p); // stream-ordered reuse: later users are enqueued after the copy
             p   = np;
             cap = want;
         }

@@ -1,0 +1,67 @@
+// neigh2.cuh — the B200 neighbour search: Morton-sorted particle storage, packed tree nodes, one capped
+// tree walk per leaf (candidate rank ranges), a warp-cooperative accept pass whose lanes are the
+// candidates (ballot masks), and an ordered fill.  Output: a CSR over the REAL particles in sorted
+// (Morton rank) order whose entries are RANKS; `export_object_cache` converts it to the reference's
+// ObjectCache layout (by particle id, ids) — bit-identical to NeighbourCache.cpp:223-604.
+#pragma once
+#include "sph.cuh"
+#include "tree.cuh"
+
+namespace sb {
+
+/// one tree node in 64 bytes (two 32-byte sectors): box, interaction radius, children / leaf range
+struct alignas(64) NodePack {
+    f64 lo[3], hi[3];
+    f64 rint;       ///< max(h) * htol of the node's objects
+    u32 left, right; ///< internal: child node ids (leaves are offset by I); leaf: rank range [left, right)
+};
+
+constexpr int RANGE_CAP_DEFAULT = 64;
+
+struct SearchBuffers {
+    u32 N = 0, M = 0, L = 0, I = 0;
+    u64 K        = 0; ///< total neighbour count
+    u32 range_cap = RANGE_CAP_DEFAULT;
+    DevBuf<NodePack> nodes;  // [I+L]
+    DevBuf<Pack4> SA;        // [M] (x,y,z,h) in sorted order
+    DevBuf<u32> inv_map;     // [M] rank of merged index i
+    DevBuf<u8> real_flag;    // [M+1]
+    DevBuf<u32> real_prefix; // [M+1] exclusive scan of real_flag over ranks (slot of a real rank)
+    DevBuf<u32> slot_rank;   // [N] rank of slot k
+    DevBuf<u32> ranges;      // [L * cap * 2]
+    DevBuf<u32> nrange, ncand, mask_words, mask_off; // [L]
+    DevBuf<u32> masks;
+    DevBuf<u32> cnt_s, off_s; // [N]
+    DevBuf<u32> list_s;       // [K] ranks, ascending inside each list
+    DevBuf<u32> scan_tmp;
+    DevBuf<u64> scalars;
+    PinnedBuf<u64> h_scalars;
+    // exported ObjectCache (by id), built on demand
+    bool exported = false;
+    DevBuf<u32> x_cnt, x_scanned, x_list;
+};
+
+/// rank-CSR view handed to the SPH loops
+struct RankCsr {
+    const u32 *cnt, *off, *list; ///< by slot; entries are ranks
+    const u32 *slot_rank;        ///< [N]
+    const u32 *index_map;        ///< rank -> merged id
+    u32 N;
+};
+inline RankCsr rank_csr_of(const SearchBuffers &sb, const TreeBuffers &tb) {
+    return RankCsr{sb.cnt_s.p, sb.off_s.p, sb.list_s.p, sb.slot_rank.p, tb.index_map.p, sb.N};
+}
+
+/// SA[r] = A[index_map[r]], inv_map, real flags / slots.  A: merged (x,y,z,h) by id, N real objects first.
+void search_prepare_sorted(cudaStream_t s, const TreeBuffers &tb, SearchBuffers &sb, const Pack4 *A, u32 N);
+/// same from separate position / h arrays (stage-level C ABI)
+void search_prepare_sorted_strided(
+    cudaStream_t s, const TreeBuffers &tb, SearchBuffers &sb, const f64 *xyz, size_t stride, const f64 *h,
+    size_t hstride, u32 N);
+/// the search proper (two-stage criterion of the reference).  Synchronises once (list sizing).
+void search_build(
+    cudaStream_t s, const TreeBuffers &tb, SearchBuffers &sb, const f64 *d_rint, f64 Rkern, f64 h_tolerance);
+/// ObjectCache layout of the reference (cnt / scanned by id, ids).  Synchronises.
+void export_object_cache(cudaStream_t s, const TreeBuffers &tb, SearchBuffers &sb);
+
+} // namespace sb

@@ -243,25 +243,26 @@ int64_t Model::get(u32 ip, const std::string &name, void *out, int64_t cap) {
         if (name == r.name)
             return copy_dev(s(), r.buf->p, size_t(p.f.n) * r.nvar, out, cap);
     PatchStep &st = p.st;
-    auto packc    = [&](const Pack4 *P, u32 cnt, int first, int nc) -> int64_t {
+    auto packc    = [&](const Pack4 *P, u32 cnt, int first, int nc, const u32 *map) -> int64_t {
         int64_t nb = int64_t(size_t(cnt) * nc * sizeof(f64));
         if (out && cap >= nb && nb > 0) {
             field_tmp.ensure(size_t(cnt) * nc);
-            unpack_comp(s(), cnt, P, first, nc, field_tmp.p);
+            unpack_comp(s(), cnt, P, first, nc, field_tmp.p, map);
             return copy_dev(s(), field_tmp.p, size_t(cnt) * nc, out, cap);
         }
         return nb;
     };
-    if (name == "step.mxyz") return packc(st.A.p, st.m, 0, 3);
+    const u32 *inv = st.srch.inv_map.p;
+    if (name == "step.mxyz") return packc(st.A.p, st.m, 0, 3, nullptr);
     if (name == "step.mh") return cfg.keep_step_data ? copy_dev(s(), st.mh_snapshot.p, st.m, out, cap) : -1;
-    if (name == "step.g_h") return packc(st.A.p, st.m, 3, 1);
-    if (name == "step.g_v") return packc(st.B.p, st.m, 0, 3);
-    if (name == "step.g_u") return packc(st.B.p, st.m, 3, 1);
-    if (name == "step.pressure") return packc(st.C.p, st.m, 0, 1);
-    if (name == "step.g_omega") return packc(st.C.p, st.m, 1, 1);
-    if (name == "step.soundspeed") return packc(st.C.p, st.m, 2, 1);
-    if (name == "step.g_alpha") return packc(st.C.p, st.m, 3, 1);
-    if (name == "step.g_a") return packc(st.D.p, st.m, 0, 3);
+    if (name == "step.g_h") return packc(st.srch.SA.p, st.m, 3, 1, inv);
+    if (name == "step.g_v") return packc(st.SB.p, st.m, 0, 3, inv);
+    if (name == "step.g_u") return packc(st.SB.p, st.m, 3, 1, inv);
+    if (name == "step.pressure") return packc(st.SC.p, st.m, 0, 1, inv);
+    if (name == "step.g_omega") return packc(st.SC.p, st.m, 1, 1, inv);
+    if (name == "step.soundspeed") return packc(st.SC.p, st.m, 2, 1, inv);
+    if (name == "step.g_alpha") return packc(st.SC.p, st.m, 3, 1, inv);
+    if (name == "step.g_a") return packc(st.SD.p, st.m, 0, 3, inv);
     if (name == "step.rint") return copy_dev(s(), st.rint.p, size_t(st.tree.I) + st.tree.L, out, cap);
     if (name == "step.omega") return copy_dev(s(), st.omega.p, st.n, out, cap);
     if (name == "step.alpha_updated") return copy_dev(s(), st.alpha_updated.p, st.n, out, cap);
@@ -279,9 +280,12 @@ int64_t Model::get(u32 ip, const std::string &name, void *out, int64_t cap) {
     if (name == "tree.endrange") return copy_dev(s(), t.endrange.p, t.I, out, cap);
     if (name == "tree.aabb_min") return copy_dev(s(), t.aabb_min.p, (size_t(t.I) + t.L) * 3, out, cap);
     if (name == "tree.aabb_max") return copy_dev(s(), t.aabb_max.p, (size_t(t.I) + t.L) * 3, out, cap);
-    if (name == "cache.cnt_neigh") return copy_dev(s(), st.nb.cnt.p, st.nb.N, out, cap);
-    if (name == "cache.scanned_cnt") return copy_dev(s(), st.nb.scanned.p, st.nb.N, out, cap);
-    if (name == "cache.index_neigh_map") return copy_dev(s(), st.nb.list.p, st.nb.K, out, cap);
+    if (name.rfind("cache.", 0) == 0) { // the reference's ObjectCache layout, converted on demand
+        export_object_cache(s(), st.tree, st.srch);
+        if (name == "cache.cnt_neigh") return copy_dev(s(), st.srch.x_cnt.p, st.srch.N, out, cap);
+        if (name == "cache.scanned_cnt") return copy_dev(s(), st.srch.x_scanned.p, st.srch.N, out, cap);
+        if (name == "cache.index_neigh_map") return copy_dev(s(), st.srch.x_list.p, st.srch.K, out, cap);
+    }
     return -1;
 }
 
@@ -643,21 +647,17 @@ void Model::compute_presteps_rint() {
                 p.st.rint.p, 4);
         }
 }
-/// Solver::start_neighbors_cache (Solver.cpp:1364-1386)
+/// Solver::start_neighbors_cache (Solver.cpp:1364-1386): Morton-sorted storage + the B200 search
 void Model::start_neighbors_cache() {
     const f64 Rkern = cfg.kernel == SHAMB200_KERNEL_M4 ? 2.0 : 3.0;
     K_local         = 0;
     for (auto &p : patches)
         if (is_local(p) && p.f.n) {
-            const f64 *A = reinterpret_cast<const f64 *>(p.st.A.p);
-            neigh_cache_build(
-                s(), p.st.tree, p.st.nb, A, 4, A + 3, p.st.rint.p, p.st.n, Rkern, cfg.htol_up_coarse_cycle,
-                cfg.use_two_stage_search != 0, 4);
-            K_local += p.st.nb.K;
+            search_prepare_sorted(s(), p.st.tree, p.st.srch, p.st.A.p, p.st.n);
+            search_build(s(), p.st.tree, p.st.srch, p.st.rint.p, Rkern, cfg.htol_up_coarse_cycle);
+            K_local += p.st.srch.K;
         }
 }
-
-static CsrView csr_of(const PatchStep &st) { return CsrView{st.nb.cnt.p, st.nb.scanned.p, st.nb.list.p, st.nb.N}; }
 
 /// Solver::sph_prestep (Solver.cpp:1060-1304)
 void Model::sph_prestep() {
@@ -689,21 +689,45 @@ void Model::sph_prestep() {
         f64 local_max_eps = std::numeric_limits<f64>::max();
         f64 local_min_eps = -1;
         u32 iter_h        = 0;
-        for (; iter_h < cfg.h_iter_per_subcycles; iter_h++) {
+        // A Newton sweep of particle a reads only positions and its own h (IterateSmoothingLengthDensity.cpp:
+        // 52-119), and a particle stops sweeping once its eps <= 1e-6 (hard-coded gate, :75): all sweeps of
+        // LoopSmoothingLengthIter run inside ONE launch, each particle iterating on its own, with the same
+        // result as the reference's synchronous sweeps.  (epsilon_h != 1e-6 keeps the host loop.)  Ω is
+        // evaluated in the same launch with the converged h (ComputeOmega.cpp:36-73).
+        const bool fused = cfg.epsilon_h == 1e-6;
+        if (fused) {
             reset_red();
             for (auto &p : patches)
                 if (is_local(p) && p.f.n) {
                     PatchStep &st = p.st;
-                    h_iterate(
-                        s(), cfg.kernel, csr_of(st), reinterpret_cast<const f64 *>(st.A.p), 4, st.tree.index_map.p,
-                        st.m, st.h_old.p, p.f.hpart.p, st.eps.p, cfg.gpart_mass, cfg.htol_up_coarse_cycle,
-                        cfg.htol_up_fine_cycle, red.p);
+                    st.omega.ensure(st.n);
+                    h_solve(
+                        s(), cfg.fp_mode, cfg.kernel, rank_csr_of(st.srch, st.tree), st.srch.SA.p, st.h_old.p,
+                        p.f.hpart.p, st.eps.p, st.omega.p, cfg.gpart_mass, cfg.htol_up_coarse_cycle,
+                        cfg.htol_up_fine_cycle, cfg.h_iter_per_subcycles, true, true, red.p);
                 }
-            read_red(2);
+            read_red(3);
             local_max_eps = ordered_to_f64(h_red.p[0]);
             local_min_eps = ordered_to_f64(h_red.p[1]);
-            if (local_max_eps < cfg.epsilon_h)
-                break;
+            u32 sweeps    = u32(h_red.p[2]); // slot 2 doubles as the sweep counter during the h iteration
+            iter_h        = local_max_eps < cfg.epsilon_h ? (sweeps ? sweeps - 1 : 0) : cfg.h_iter_per_subcycles;
+        } else {
+            for (; iter_h < cfg.h_iter_per_subcycles; iter_h++) {
+                reset_red();
+                for (auto &p : patches)
+                    if (is_local(p) && p.f.n) {
+                        PatchStep &st = p.st;
+                        h_solve(
+                            s(), cfg.fp_mode, cfg.kernel, rank_csr_of(st.srch, st.tree), st.srch.SA.p, st.h_old.p,
+                            p.f.hpart.p, st.eps.p, nullptr, cfg.gpart_mass, cfg.htol_up_coarse_cycle,
+                            cfg.htol_up_fine_cycle, 1, true, false, red.p);
+                    }
+                read_red(2);
+                local_max_eps = ordered_to_f64(h_red.p[0]);
+                local_min_eps = ordered_to_f64(h_red.p[1]);
+                if (local_max_eps < cfg.epsilon_h)
+                    break;
+            }
         }
         h_iters_last         = iter_h;
         bool should_rerun_gz = local_min_eps < 0;
@@ -717,18 +741,22 @@ void Model::sph_prestep() {
         break;
     }
     h_subcycles = hstep_cnt + 1;
-    timer.mark(s(), "omega");
-    for (auto &p : patches)
-        if (is_local(p) && p.f.n) {
-            PatchStep &st = p.st;
-            st.omega.ensure(st.n);
-            compute_omega(
-                s(), cfg.kernel, csr_of(st), reinterpret_cast<const f64 *>(st.A.p), 4, st.tree.index_map.p, st.m,
-                p.f.hpart.p, st.omega.p, cfg.gpart_mass);
-        }
+    if (cfg.epsilon_h != 1e-6) {
+        timer.mark(s(), "omega");
+        for (auto &p : patches)
+            if (is_local(p) && p.f.n) {
+                PatchStep &st = p.st;
+                st.omega.ensure(st.n);
+                h_solve(
+                    s(), cfg.fp_mode, cfg.kernel, rank_csr_of(st.srch, st.tree), st.srch.SA.p, st.h_old.p, p.f.hpart.p,
+                    st.eps.p, st.omega.p, cfg.gpart_mass, cfg.htol_up_coarse_cycle, cfg.htol_up_fine_cycle, 0, false,
+                    true, red.p);
+            }
+    }
 }
 
-/// Solver::communicate_merge_ghosts_fields (Solver.cpp:1394-1633)
+/// Solver::communicate_merge_ghosts_fields (Solver.cpp:1394-1633).  The merged fields are written
+/// straight into the Morton-sorted records (slot = inv_map[merged index]).
 void Model::communicate_merge_ghosts_fields() {
     const bool has_a = cfg.av == SHAMB200_AV_CD10;
     std::vector<std::pair<const Iface *, size_t>> recv_plan;
@@ -737,17 +765,16 @@ void Model::communicate_merge_ghosts_fields() {
         if (!is_local(p) || !p.f.n)
             continue;
         PatchStep &st = p.st;
-        st.B.ensure(st.m, 1.1);
-        st.C.ensure(st.m, 1.1);
+        st.SB.ensure(st.m, 1.1);
+        st.SC.ensure(st.m, 1.1);
         if (has_a)
-            st.D.ensure(st.m, 1.1);
+            st.SD.ensure(st.m, 1.1);
         pack_fields(
             s(), st.n, nullptr, p.f.hpart.p, p.f.vxyz.p, p.f.uint_.p, st.omega.p, has_a ? p.f.axyz.p : nullptr,
-            st.A.p, st.B.p, st.C.p, st.D.p);
+            st.srch.SA.p, st.SB.p, st.SC.p, st.SD.p, st.srch.inv_map.p);
     }
-    // C2: the ghost fields.  Remote interfaces are staged as [A | B | C | (D)] blocks of Pack4; the
-    // receiver gets them straight into its merged arrays (A keeps its position, h is refreshed by a
-    // small kernel from the staged copy on the sender: A block carries (x,y,z,h) again).
+    // C2: the ghost fields.  Remote interfaces are staged as [A | B | C | (D)] blocks of Pack4 (one NCCL
+    // message per interface) and scattered into the receiver's sorted records on arrival.
     const size_t nblk = has_a ? 4 : 3;
     send_stage.ensure(send_total * nblk, 1.1);
     comm_group_start(*this);
@@ -759,7 +786,8 @@ void Model::communicate_merge_ghosts_fields() {
             u32 o = R.st.n + itf.dst_off;
             pack_fields(
                 s(), itf.count, itf.ids.p, S.f.hpart.p, S.f.vxyz.p, S.f.uint_.p, S.st.omega.p,
-                has_a ? S.f.axyz.p : nullptr, R.st.A.p + o, R.st.B.p + o, R.st.C.p + o, has_a ? R.st.D.p + o : nullptr);
+                has_a ? S.f.axyz.p : nullptr, R.st.srch.SA.p, R.st.SB.p, R.st.SC.p, has_a ? R.st.SD.p : nullptr,
+                R.st.srch.inv_map.p + o);
         } else if (is_local(S)) {
             Pack4 *sA = send_stage.p + itf.stage_off * nblk;
             Pack4 *sB = sA + itf.count, *sC = sB + itf.count, *sD = has_a ? sC + itf.count : nullptr;
@@ -769,7 +797,6 @@ void Model::communicate_merge_ghosts_fields() {
                 has_a ? S.f.axyz.p : nullptr, sA, sB, sC, sD);
             comm_send(*this, sA, bytes * nblk, R.owner);
         } else if (is_local(R)) {
-            // one message per interface: land it in the receive staging, then scatter to A.d/B/C.b/D
             recv_plan.push_back({&itf, recv_total});
             recv_total += size_t(itf.count) * nblk;
         }
@@ -785,7 +812,9 @@ void Model::communicate_merge_ghosts_fields() {
         u32 o            = R.st.n + itf.dst_off;
         const Pack4 *sA  = recv_stage.p + rp.second;
         const Pack4 *sB = sA + itf.count, *sC = sB + itf.count, *sD = has_a ? sC + itf.count : nullptr;
-        unpack_ghost_fields(s(), itf.count, sA, sB, sC, sD, R.st.A.p + o, R.st.B.p + o, R.st.C.p + o, has_a ? R.st.D.p + o : nullptr);
+        unpack_ghost_fields(
+            s(), itf.count, sA, sB, sC, sD, R.st.srch.SA.p, R.st.SB.p, R.st.SC.p, has_a ? R.st.SD.p : nullptr,
+            R.st.srch.inv_map.p + o);
     }
 }
 
@@ -793,7 +822,7 @@ void Model::communicate_merge_ghosts_fields() {
 void Model::exchange_alpha_ghosts() {
     for (auto &p : patches)
         if (is_local(p) && p.f.n)
-            pack_alpha(s(), p.st.n, nullptr, p.st.alpha_updated.p, p.st.C.p);
+            pack_alpha(s(), p.st.n, nullptr, p.st.alpha_updated.p, p.st.SC.p, p.st.srch.inv_map.p);
     // C3: 8 B per ghost; remote interfaces go through compact f64 staging on both sides
     size_t recv_total = 0;
     for (auto &itf : ifaces)
@@ -807,7 +836,7 @@ void Model::exchange_alpha_ghosts() {
         PatchD &R = patches[itf.receiver];
         PatchD &S = patches[itf.sender];
         if (is_local(R) && is_local(S)) {
-            pack_alpha(s(), itf.count, itf.ids.p, S.st.alpha_updated.p, R.st.C.p + R.st.n + itf.dst_off);
+            pack_alpha(s(), itf.count, itf.ids.p, S.st.alpha_updated.p, R.st.SC.p, R.st.srch.inv_map.p + R.st.n + itf.dst_off);
         } else if (is_local(S)) {
             gather_field(s(), itf.count, 1, itf.ids.p, S.st.alpha_updated.p, send_stage_f.p + itf.stage_off);
             comm_send(*this, send_stage_f.p + itf.stage_off, size_t(itf.count) * sizeof(f64), R.owner);
@@ -821,7 +850,7 @@ void Model::exchange_alpha_ghosts() {
     for (auto &itf : ifaces) {
         PatchD &R = patches[itf.receiver];
         if (is_local(R) && !is_local(patches[itf.sender])) {
-            pack_alpha(s(), itf.count, nullptr, recv_stage_f.p + roff, R.st.C.p + R.st.n + itf.dst_off);
+            pack_alpha(s(), itf.count, nullptr, recv_stage_f.p + roff, R.st.SC.p, R.st.srch.inv_map.p + R.st.n + itf.dst_off);
             roff += itf.count;
         }
     }
@@ -878,29 +907,16 @@ void Model::evolve_once() {
                     p.st.alpha_updated.p, p.f.alpha_AV.p, size_t(p.st.n) * sizeof(f64), cudaMemcpyDeviceToDevice, s()));
             }
         timer.mark(s(), "divv_curlv_dtdivv");
-        for (auto &p : patches) {
-            if (!is_local(p) || !p.f.n)
-                continue;
-            PatchStep &st = p.st;
-            if (has_dtdivv) {
-                if (cfg.combined_dtdiv_divcurlv_compute) {
-                    compute_dtdivv(
-                        s(), cfg.kernel, csr_of(st), st.A.p, st.B.p, st.D.p, st.tree.index_map.p, st.m, cfg.gpart_mass,
-                        true, p.f.divv.p, p.f.curlv.p, p.f.dtdivv.p);
-                } else {
-                    compute_divv_curlv(
-                        s(), cfg.kernel, csr_of(st), st.A.p, st.B.p, st.C.p, st.tree.index_map.p, st.m, cfg.gpart_mass,
-                        p.f.divv.p, has_curl ? p.f.curlv.p : nullptr);
-                    compute_dtdivv(
-                        s(), cfg.kernel, csr_of(st), st.A.p, st.B.p, st.D.p, st.tree.index_map.p, st.m, cfg.gpart_mass,
-                        false, p.f.divv.p, p.f.curlv.p, p.f.dtdivv.p);
-                }
-            } else if (has_alpha) {
-                compute_divv_curlv(
-                    s(), cfg.kernel, csr_of(st), st.A.p, st.B.p, st.C.p, st.tree.index_map.p, st.m, cfg.gpart_mass,
-                    p.f.divv.p, has_curl ? p.f.curlv.p : nullptr);
+        if (has_alpha)
+            for (auto &p : patches) {
+                if (!is_local(p) || !p.f.n)
+                    continue;
+                PatchStep &st = p.st;
+                av_operators(
+                    s(), cfg.fp_mode, cfg.kernel, rank_csr_of(st.srch, st.tree), st.srch.SA.p, st.SB.p, st.SC.p, st.SD.p,
+                    cfg.gpart_mass, has_curl, has_dtdivv, cfg.combined_dtdiv_divcurlv_compute != 0, p.f.divv.p,
+                    p.f.curlv.p, p.f.dtdivv.p);
             }
-        }
         timer.mark(s(), "av_eos");
         if (has_alpha) {
             for (auto &p : patches)
@@ -913,9 +929,22 @@ void Model::evolve_once() {
         for (auto &p : patches)
             if (is_local(p) && p.f.n)
                 compute_eos(
-                    s(), cfg.kernel, cfg.eos, p.st.A.p, p.st.B.p, p.st.C.p, p.st.m, cfg.gpart_mass, cfg.gamma, cfg.cs0,
-                    cfg.eos_q, cfg.eos_r0);
+                    s(), cfg.kernel, cfg.eos, p.st.srch.SA.p, p.st.SB.p, p.st.SC.p, p.st.m, cfg.gpart_mass, cfg.gamma,
+                    cfg.cs0, cfg.eos_q, cfg.eos_r0);
+        if (cfg.fp_mode == SHAMB200_FP_FAST)
+            for (auto &p : patches)
+                if (is_local(p) && p.f.n) {
+                    p.st.SE.ensure(p.st.m, 1.1);
+                    p.st.SF.ensure(p.st.m, 1.1);
+                    derive_fast(
+                        s(), cfg.kernel, cfg.av, p.st.m, p.st.srch.SA.p, p.st.SB.p, p.st.SC.p, cfg.gpart_mass,
+                        cfg.alpha_AV, p.st.SE.p, p.st.SF.p);
+                }
         timer.mark(s(), "forces");
+        // forces, v_sig and the CFL dt come out of one pass over the neighbour lists.  The CFL uses the cfl
+        // multiplier in force at launch: if the corrector test below halves it, the whole pass is redone.
+        const f64 C_cour  = cfg.cfl_cour * cfl_multiplier;
+        const f64 C_force = cfg.cfl_force * cfl_multiplier;
         reset_red();
         for (auto &p : patches) {
             if (!is_local(p) || !p.f.n)
@@ -923,11 +952,14 @@ void Model::evolve_once() {
             PatchStep &st = p.st;
             st.a_old.ensure(size_t(st.n) * 3);
             st.du_old.ensure(st.n);
+            st.vsig.ensure(st.n);
+            st.cfl_dt.ensure(st.n);
             SB_CUDA_CHECK(cudaMemcpyAsync(st.a_old.p, p.f.axyz.p, size_t(st.n) * 3 * sizeof(f64), cudaMemcpyDeviceToDevice, s()));
             SB_CUDA_CHECK(cudaMemcpyAsync(st.du_old.p, p.f.duint.p, size_t(st.n) * sizeof(f64), cudaMemcpyDeviceToDevice, s()));
-            compute_forces(
-                s(), cfg.kernel, cfg.av, csr_of(st), st.A.p, st.B.p, st.C.p, st.tree.index_map.p, st.m, sp,
-                p.f.axyz_ext.p, p.f.axyz.p, p.f.duint.p);
+            force_cfl(
+                s(), cfg.fp_mode, cfg.kernel, cfg.av, rank_csr_of(st.srch, st.tree), st.srch.SA.p, st.SB.p, st.SC.p,
+                st.SE.p, st.SF.p, sp, p.f.axyz_ext.p, p.f.axyz.p, p.f.duint.p, C_cour, C_force, st.vsig.p, st.cfl_dt.p,
+                red.p + 4);
         }
         timer.mark(s(), "corrector");
         for (auto &p : patches)
@@ -953,10 +985,6 @@ void Model::evolve_once() {
             need_rerun_corrector = false;
         }
         if (!need_rerun_corrector) {
-            timer.mark(s(), "vsig_cfl");
-            f64 C_cour  = cfg.cfl_cour * cfl_multiplier;
-            f64 C_force = cfg.cfl_force * cfl_multiplier;
-            reset_red();
             for (auto &p : patches) {
                 if (!is_local(p) || !p.f.n)
                     continue;
@@ -964,15 +992,9 @@ void Model::evolve_once() {
                 if (has_alpha)
                     SB_CUDA_CHECK(cudaMemcpyAsync(
                         p.f.alpha_AV.p, st.alpha_updated.p, size_t(st.n) * sizeof(f64), cudaMemcpyDeviceToDevice, s()));
-                st.vsig.ensure(st.n);
-                st.cfl_dt.ensure(st.n);
-                compute_vsig_cfl(
-                    s(), cfg.kernel, csr_of(st), st.A.p, st.B.p, st.C.p, st.tree.index_map.p, st.m, p.f.axyz.p, C_cour,
-                    C_force, st.vsig.p, st.cfl_dt.p, red.p + 4);
                 if (has_cs_field)
-                    unpack_cs(s(), st.n, st.C.p, p.f.soundspeed.p);
+                    unpack_cs(s(), st.n, st.SC.p, p.f.soundspeed.p, st.srch.inv_map.p);
             }
-            read_red(5);
             next_cfl = ordered_to_f64(h_red.p[4]);
             comm_allreduce_host_f64(*this, &next_cfl, 1, 2); // C8: global dt (Solver.cpp:3119)
         }

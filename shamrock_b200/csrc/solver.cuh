@@ -5,7 +5,9 @@
 #include "../../include/shamb200.h"
 #include "ghost_plan.hpp"
 #include "neigh.cuh"
+#include "neigh2.cuh"
 #include "sph.cuh"
+#include "sph2.cuh"
 #include "stream_kernels.cuh"
 #include "tree.cuh"
 #include <map>
@@ -22,6 +24,7 @@ struct Ctx {
     // arenas of the stage-level C ABI (shamb200_tree_build / shamb200_neigh_cache_build)
     TreeBuffers api_tree;
     NeighBuffers api_nb;
+    SearchBuffers api_srch;
     DevBuf<u64> red;
     PinnedBuf<u64> h_red;
 };
@@ -53,10 +56,12 @@ struct Iface {
 
 struct PatchStep {
     u32 n = 0, m = 0;
-    DevBuf<Pack4> A, B, C, D;
+    DevBuf<Pack4> A;          ///< merged (x,y,z,h) by merged id (real first, then ghosts): tree-build input
+    DevBuf<Pack4> SB, SC, SD; ///< Morton-sorted records: (v,u), (P,omega,cs,alpha), (a,0); (x,y,z,h) is srch.SA
+    DevBuf<Pack4> SE, SF;     ///< fast fp mode: per-particle derived factors (sph2_fast.cu)
     TreeBuffers tree;
     DevBuf<f64> rint;
-    NeighBuffers nb;
+    SearchBuffers srch;
     DevBuf<f64> omega, alpha_updated, vsig, cfl_dt, eps, h_old, a_old, du_old;
     DevBuf<f64> mh_snapshot; ///< pre-iteration merged h (keep_step_data only)
 };

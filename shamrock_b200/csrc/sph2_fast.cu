@@ -1,0 +1,526 @@
+// sph2_fast.cu — fast-fp SPH loops of the model path (compiled with -fmad=true).
+//
+// Same algorithm and the same neighbour lists as sph2_strict.cu; what changes is how the FP64 pipe — the
+// binding roof of these loops on B200 — is used:
+//  * G lanes per particle stride over its neighbour list (G = 8 for M4, 16 for M6), so a warp's loads
+//    are runs of consecutive ranks (Morton-sorted records) and no lane waits on a longer list;
+//    partial sums are combined with warp shuffles;
+//  * everything that depends on ONE particle only (1/h, norm/h^4, rho, 1/(rho^2 Ω), 1/(rho Ω), α c_s,
+//    P/(rho^2 Ω)) is computed once per particle (derive_fast) instead of once per pair: the pair math
+//    has one rsqrt, one reciprocal and one sqrt left (the reference's has ~12 divisions / 2 sqrt);
+//  * kernel normalisations and the particle mass are factored out of the sums; FMA contraction is on.
+// Results agree with the strict path to rounding (~1e-15 relative per pair); the parity tests hold this
+// mode to 1e-10 relative per particle (north-star tolerance).  Reference loops: see sph2_strict.cu.
+#include "sph2.cuh"
+#include "sphkern.cuh"
+
+namespace sb {
+
+namespace {
+
+constexpr int BLK = 128;
+
+__device__ __forceinline__ Pack4 ld4(const Pack4 *p) {
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+    double2 lo = __ldg(q), hi = __ldg(q + 1);
+    return Pack4{lo.x, lo.y, hi.x, hi.y};
+}
+
+/// sum over the G lanes of a group, result broadcast from the group's first lane (identical in all lanes)
+/// lanes of this thread's group (groups of one warp may sit in different loop trips: the shuffles name
+/// only the group's own lanes)
+template<int G>
+__device__ __forceinline__ u32 group_mask() {
+    if (G >= 32)
+        return 0xffffffffu;
+    u32 lane = threadIdx.x & 31u;
+    return ((1u << G) - 1u) << (lane & ~u32(G - 1));
+}
+template<int G>
+__device__ __forceinline__ f64 group_sum(f64 v) {
+    const u32 m = group_mask<G>();
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1)
+        v += __shfl_down_sync(m, v, o, G);
+    return __shfl_sync(m, v, 0, G);
+}
+template<int G>
+__device__ __forceinline__ f64 group_max(f64 v) {
+    const u32 m = group_mask<G>();
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1)
+        v = fmax(v, __shfl_down_sync(m, v, o, G));
+    return __shfl_sync(m, v, 0, G);
+}
+
+// ---- h Newton iteration (all sweeps) + Ω ------------------------------------------------------------
+/// Σ_b f(q_ab) and Σ_b (3 f + q f') over the list of one particle, by the G lanes of its group
+template<class K, int G>
+__device__ __forceinline__ void density_sums(
+    const RankCsr &c, const Pack4 *__restrict__ SA, u32 s0, u32 s1, int sub, const Pack4 &a, f64 h_a, f64 &sf,
+    f64 &sg) {
+    const f64 hinv = 1. / h_a;
+    const f64 lim  = h_a * h_a * (K::Rkern * K::Rkern);
+    f64 f_acc = 0, g_acc = 0;
+    for (u32 j = s0 + sub; j < s1; j += G) {
+        Pack4 b = ld4(SA + c.list[j]);
+        f64 dx = a.a - b.a, dy = a.b - b.b, dz = a.c - b.c;
+        f64 r2 = dx * dx + dy * dy + dz * dz;
+        if (r2 > lim)
+            continue;
+        f64 q  = sqrt(r2) * hinv;
+        f64 f  = K::f(q);
+        f64 df = K::df(q);
+        f_acc += f;
+        g_acc += 3 * f + q * df;
+    }
+    sf = group_sum<G>(f_acc);
+    sg = group_sum<G>(g_acc);
+}
+
+template<class K, int G>
+__global__ void __launch_bounds__(BLK) h_solve_fast_kernel(
+    RankCsr c, const Pack4 *__restrict__ SA, const f64 *__restrict__ h_old, f64 *__restrict__ hpart,
+    f64 *__restrict__ eps, f64 *__restrict__ omega, f64 part_mass, f64 h_max_tot_max_evol, f64 h_max_evol_p,
+    u32 max_sweeps, bool do_iter, bool do_omega, u64 *red) {
+    const u32 t   = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 k   = t / G;
+    const int sub = int(t % G);
+    // groups past the end clamp to the last particle (their lanes must stay in the shuffles) and write nothing
+    const bool valid = k < c.N;
+    const u32 kk     = valid ? k : c.N - 1;
+    const u32 r      = c.slot_rank[kk];
+    const u32 id     = c.index_map[r];
+    const Pack4 a    = ld4(SA + r);
+    f64 h_a          = hpart[id];
+    const u32 s0 = c.off[kk], s1 = s0 + c.cnt[kk];
+    constexpr f64 hf3 = K::hfactd * K::hfactd * K::hfactd;
+    f64 e_out  = 0;
+    u32 sweeps = 0;
+    if (do_iter) {
+        f64 e            = eps[id];
+        const f64 ha_0   = h_old[id];
+        const f64 h_max_evol_m = 1 / h_max_evol_p;
+        while (sweeps < max_sweeps && e > 1e-6) {
+            f64 sf, sg;
+            density_sums<K, G>(c, SA, s0, s1, sub, a, h_a, sf, sg);
+            f64 hinv    = 1. / h_a;
+            f64 hinv3   = hinv * hinv * hinv;
+            f64 rho_sum = part_mass * K::norm_3d * hinv3 * sf;
+            f64 sumdWdh = -part_mass * K::norm_3d * hinv3 * hinv * sg;
+            f64 rho_ha  = part_mass * hf3 * hinv3;
+            f64 f_iter  = rho_sum - rho_ha;
+            f64 df_iter = sumdWdh + 3 * rho_ha * hinv;
+            f64 new_h   = h_a - f_iter / df_iter;
+            if (new_h < h_a * h_max_evol_m)
+                new_h = h_max_evol_m * h_a;
+            if (new_h > h_a * h_max_evol_p)
+                new_h = h_max_evol_p * h_a;
+            if (new_h < ha_0 * h_max_tot_max_evol) {
+                e   = fabs(new_h - h_a) / ha_0;
+                h_a = new_h;
+            } else {
+                h_a = ha_0 * h_max_tot_max_evol;
+                e   = -1;
+            }
+            sweeps++;
+        }
+        e_out = e;
+        if (valid && sub == 0) {
+            eps[id]   = e;
+            hpart[id] = h_a;
+        }
+    }
+    if (do_omega) {
+        f64 sf, sg;
+        density_sums<K, G>(c, SA, s0, s1, sub, a, h_a, sf, sg);
+        // Ω = 1 + h/(3 ρ_h) Σ m ∂W/∂h = 1 - (norm / (3 hfact³)) Σ (3 f + q f')
+        if (valid && sub == 0)
+            omega[id] = 1 - (K::norm_3d / (3 * hf3)) * sg;
+    }
+    if (do_iter) {
+        __shared__ f64 smax[BLK / 32], smin[BLK / 32];
+        __shared__ u32 ssw[BLK / 32];
+        const bool mine = valid && sub == 0;
+        f64 vmax = warp_max(mine ? e_out : -f64(INFINITY));
+        f64 vmin = warp_min(mine ? e_out : f64(INFINITY));
+        u32 sw   = mine ? sweeps : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            sw = max(sw, __shfl_xor_sync(0xffffffffu, sw, o));
+        if ((threadIdx.x & 31) == 0) {
+            smax[threadIdx.x >> 5] = vmax;
+            smin[threadIdx.x >> 5] = vmin;
+            ssw[threadIdx.x >> 5]  = sw;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            f64 x = smax[0], y = smin[0];
+            u32 z = ssw[0];
+#pragma unroll
+            for (int q = 1; q < BLK / 32; q++) {
+                x = fmax(x, smax[q]);
+                y = fmin(y, smin[q]);
+                z = max(z, ssw[q]);
+            }
+            atomicMax((unsigned long long *) &red[0], (unsigned long long) f64_to_ordered(x));
+            atomicMin((unsigned long long *) &red[1], (unsigned long long) f64_to_ordered(y));
+            atomicMax((unsigned long long *) &red[2], (unsigned long long) z);
+        }
+    }
+}
+
+// ---- ∇·v, ∇×v, d(∇·v)/dt ------------------------------------------------------------------------------
+template<class K, int G, bool SPHDIV, bool CURL, bool MAT, bool COMBINED>
+__global__ void __launch_bounds__(BLK) av_operators_fast_kernel(
+    RankCsr c, const Pack4 *__restrict__ SA, const Pack4 *__restrict__ SB, const Pack4 *__restrict__ SC,
+    const Pack4 *__restrict__ SD, f64 pmass, f64 *__restrict__ divv, f64 *__restrict__ curlv,
+    f64 *__restrict__ dtdivv) {
+    const u32 t      = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 k      = t / G;
+    const int sub    = int(t % G);
+    const bool valid = k < c.N;
+    const u32 kk     = valid ? k : c.N - 1;
+    const u32 r      = c.slot_rank[kk];
+    const u32 id     = c.index_map[r];
+    constexpr f64 Rker2 = K::Rkern * K::Rkern;
+    const Pack4 pa = ld4(SA + r), va = ld4(SB + r);
+    const Pack4 aa = MAT ? ld4(SD + r) : Pack4{0, 0, 0, 0};
+    const f64 h_a   = pa.d;
+    const f64 hinv  = 1. / h_a;
+    const f64 dWn_a = K::norm_3d * (hinv * hinv) * (hinv * hinv);
+    const f64 lim_a = h_a * h_a * Rker2;
+    f64 snv = 0, cx = 0, cy = 0, cz = 0;
+    f64 Rij[9], Rv[9], Ra[9];
+    if (MAT) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            Rij[i] = 0;
+            Rv[i]  = 0;
+            Ra[i]  = 0;
+        }
+    }
+    const u32 s0 = c.off[kk], s1 = s0 + c.cnt[kk];
+    for (u32 j = s0 + sub; j < s1; j += G) {
+        u32 rb   = c.list[j];
+        Pack4 pb = ld4(SA + rb);
+        f64 dx = pa.a - pb.a, dy = pa.b - pb.b, dz = pa.c - pb.c;
+        f64 r2  = dx * dx + dy * dy + dz * dz;
+        f64 h_b = pb.d;
+        if ((r2 > lim_a && r2 > h_b * h_b * Rker2) || r2 < 1e-18) // r < 1e-9: zero unit vector in the reference
+            continue;
+        f64 rinv = rsqrt(r2);
+        f64 q    = (r2 * rinv) * hinv;
+        f64 gs   = dWn_a * K::df(q) * rinv; // ∇W_ab(h_a) = gs · r_ab  (mass factored out)
+        f64 gx = gs * dx, gy = gs * dy, gz = gs * dz;
+        Pack4 vb = ld4(SB + rb);
+        f64 vx = va.a - vb.a, vy = va.b - vb.b, vz = va.c - vb.c;
+        if (SPHDIV) {
+            snv += vx * gx + vy * gy + vz * gz;
+            if (CURL) {
+                cx += vy * gz - vz * gy;
+                cy += vz * gx - vx * gz;
+                cz += vx * gy - vy * gx;
+            }
+        }
+        if (MAT) {
+            Pack4 ab  = ld4(SD + rb);
+            f64 v[3]  = {vx, vy, vz};
+            f64 a[3]  = {aa.a - ab.a, aa.b - ab.b, aa.c - ab.c};
+            f64 rr[3] = {dx, dy, dz};
+            f64 g[3]  = {gx, gy, gz};
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int m = 0; m < 3; m++) {
+                    Rij[3 * i + m] -= rr[i] * g[m];
+                    Rv[3 * i + m] -= v[m] * g[i];
+                    Ra[3 * i + m] -= a[m] * g[i];
+                }
+        }
+    }
+    if (SPHDIV) {
+        snv = group_sum<G>(snv);
+        if (CURL) {
+            cx = group_sum<G>(cx);
+            cy = group_sum<G>(cy);
+            cz = group_sum<G>(cz);
+        }
+    }
+    if (MAT) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            Rij[i] = group_sum<G>(Rij[i]);
+            Rv[i]  = group_sum<G>(Rv[i]);
+            Ra[i]  = group_sum<G>(Ra[i]);
+        }
+    }
+    if (!valid || sub != 0)
+        return;
+    if (SPHDIV) {
+        f64 omega_a = SC[r].b;
+        f64 hfh     = K::hfactd * hinv;
+        f64 rho_a   = pmass * hfh * hfh * hfh;
+        f64 fac     = -pmass / (omega_a * rho_a);
+        divv[id]    = fac * snv;
+        if (CURL) {
+            curlv[3 * u64(id)]     = fac * cx;
+            curlv[3 * u64(id) + 1] = fac * cy;
+            curlv[3 * u64(id) + 2] = fac * cz;
+        }
+    }
+    if (MAT) { // dv = Rij^-1 Rv, da = Rij^-1 Ra  (matrix_legacy.hpp:25,53); the mass cancels
+        f64 a00 = Rij[0], a01 = Rij[1], a02 = Rij[2], a10 = Rij[3], a11 = Rij[4], a12 = Rij[5], a20 = Rij[6],
+            a21 = Rij[7], a22 = Rij[8];
+        f64 det = (-a02 * a11 * a20 + a01 * a12 * a20 + a02 * a10 * a21 - a00 * a12 * a21 - a01 * a10 * a22
+                   + a00 * a11 * a22);
+        f64 idet = 1. / det;
+        f64 inv[9];
+        inv[0] = (-a12 * a21 + a11 * a22) * idet;
+        inv[1] = (a02 * a21 - a01 * a22) * idet;
+        inv[2] = (-a02 * a11 + a01 * a12) * idet;
+        inv[3] = (a12 * a20 - a10 * a22) * idet;
+        inv[4] = (-a02 * a20 + a00 * a22) * idet;
+        inv[5] = (a02 * a10 - a00 * a12) * idet;
+        inv[6] = (-a11 * a20 + a10 * a21) * idet;
+        inv[7] = (a01 * a20 - a00 * a21) * idet;
+        inv[8] = (-a01 * a10 + a00 * a11) * idet;
+        f64 dv[9], da_tr = 0;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+#pragma unroll
+            for (int m = 0; m < 3; m++)
+                dv[3 * i + m] = inv[3 * i] * Rv[m] + inv[3 * i + 1] * Rv[3 + m] + inv[3 * i + 2] * Rv[6 + m];
+            da_tr += inv[3 * i] * Ra[i] + inv[3 * i + 1] * Ra[3 + i] + inv[3 * i + 2] * Ra[6 + i];
+        }
+        f64 tens = 0;
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int m = 0; m < 3; m++)
+                tens += dv[3 * m + i] * dv[3 * i + m];
+        if (COMBINED) {
+            divv[id]               = dv[0] + dv[4] + dv[8];
+            curlv[3 * u64(id)]     = dv[5] - dv[7];
+            curlv[3 * u64(id) + 1] = dv[6] - dv[2];
+            curlv[3 * u64(id) + 2] = dv[1] - dv[3];
+        }
+        dtdivv[id] = da_tr - tens;
+    }
+}
+
+// ---- per-particle derived factors ----------------------------------------------------------------------
+template<class K>
+__global__ void __launch_bounds__(256) derive_fast_kernel(
+    u32 M, bool vary, f64 alpha_const, const Pack4 *__restrict__ SA, const Pack4 *__restrict__ SC, f64 pmass,
+    Pack4 *__restrict__ SE, Pack4 *__restrict__ SF) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M)
+        return;
+    f64 h    = SA[i].d;
+    Pack4 cc = SC[i]; // (P, omega, cs, alpha)
+    f64 hinv = 1. / h;
+    f64 hfh  = K::hfactd * hinv;
+    f64 rho  = pmass * hfh * hfh * hfh;
+    f64 sub  = rho * rho * cc.b;
+    f64 iro2 = (sub != 0. && sub == sub) ? 1. / sub : 0.; // inv_sat_zero
+    f64 iro  = 1. / (rho * cc.b);
+    f64 alpha = vary ? cc.d : alpha_const;
+    SE[i] = Pack4{hinv, K::norm_3d * (hinv * hinv) * (hinv * hinv), rho, iro2};
+    SF[i] = Pack4{iro, alpha * cc.c, cc.a * iro2, cc.a};
+}
+
+// ---- forces + v_sig + CFL --------------------------------------------------------------------------------
+template<class K, int AV, int G>
+__global__ void __launch_bounds__(BLK) force_cfl_fast_kernel(
+    RankCsr c, const Pack4 *__restrict__ SA, const Pack4 *__restrict__ SB, const Pack4 *__restrict__ SE,
+    const Pack4 *__restrict__ SF, const Pack4 *__restrict__ SC, SphParams p, const f64 *__restrict__ axyz_ext,
+    f64 *__restrict__ axyz, f64 *__restrict__ duint, f64 C_cour, f64 C_force, f64 *__restrict__ vsig_out,
+    f64 *__restrict__ cfl_out, u64 *red_min) {
+    const u32 t      = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 k      = t / G;
+    const int sub    = int(t % G);
+    const bool valid = k < c.N;
+    const u32 kk     = valid ? k : c.N - 1;
+    const u32 r      = c.slot_rank[kk];
+    const u32 id     = c.index_map[r];
+    constexpr f64 Rker2 = K::Rkern * K::Rkern;
+    constexpr bool DISC = (AV == AVK_DISC);
+    const Pack4 pa = ld4(SA + r), va = ld4(SB + r), ea = ld4(SE + r), fa = ld4(SF + r);
+    const f64 h_a = pa.d, u_a = va.d;
+    const f64 hinv_a = ea.a, dWn_a = ea.b, rho_a = ea.c, iro2_a = ea.d;
+    const f64 iro_a = fa.a, acs_a = fa.b, Pfac_a = fa.c, P_a = fa.d;
+    const f64 cs_a  = SC[r].c;
+    const f64 lim_a = h_a * h_a * Rker2;
+    f64 fx = 0, fy = 0, fz = 0, dU1 = 0, dU2 = 0, vsig_max = 0;
+    const u32 s0 = c.off[kk], s1 = s0 + c.cnt[kk];
+    for (u32 j = s0 + sub; j < s1; j += G) {
+        u32 rb   = c.list[j];
+        Pack4 pb = ld4(SA + rb);
+        f64 dx = pa.a - pb.a, dy = pa.b - pb.b, dz = pa.c - pb.c;
+        f64 r2  = dx * dx + dy * dy + dz * dz;
+        f64 h_b = pb.d;
+        if (r2 > lim_a && r2 > h_b * h_b * Rker2)
+            continue;
+        if (r2 < 1e-18) { // r < 1e-9 (the particle itself): zero unit vector, only v_sig sees the pair
+            vsig_max = fmax(vsig_max, cs_a);
+            continue;
+        }
+        f64 rinv = rsqrt(r2);
+        f64 rab  = r2 * rinv;
+        Pack4 eb = ld4(SE + rb), vb = ld4(SB + rb), fb = ld4(SF + rb);
+        f64 vx = va.a - vb.a, vy = va.b - vb.b, vz = va.c - vb.c;
+        f64 vr  = (vx * dx + vy * dy + vz * dz) * rinv;
+        f64 avr = fabs(vr);
+        f64 Fa  = dWn_a * K::df(rab * hinv_a);
+        f64 Fb  = eb.b * K::df(rab * eb.a);
+        f64 vsig_a = acs_a + p.beta_AV * avr;
+        f64 vsig_b = fb.b + p.beta_AV * avr;
+        f64 qa_ab, qb_ab;
+        if (DISC) { // q_av_disc (q_ab.hpp:42-60)
+            f64 vd_a = (vr < 0.) ? vsig_a : acs_a;
+            f64 vd_b = (vr < 0.) ? vsig_b : fb.b;
+            qa_ab    = (-0.5 * rho_a * rinv * h_a) * vd_a * vr;
+            qb_ab    = (-0.5 * eb.c * rinv * h_b) * vd_b * vr;
+        } else { // q_av (q_ab.hpp:37-40)
+            qa_ab = fmax(-0.5 * rho_a * vsig_a * vr, 0.);
+            qb_ab = fmax(-0.5 * eb.c * vsig_b * vr, 0.);
+        }
+        f64 ka = Pfac_a + qa_ab * iro2_a; // (P_a + q_a) / (rho_a² Ω_a)
+        f64 kb = fb.c + qb_ab * eb.d;
+        f64 cf = (ka * Fa + kb * Fb) * rinv;
+        fx += cf * dx;
+        fy += cf * dy;
+        fz += cf * dz;
+        dU1 += ka * vr * Fa;
+        f64 vsig_u = sqrt(fabs(P_a - fb.d) * 2. * __drcp_rn(rho_a + eb.c));
+        dU2 += vsig_u * (u_a - vb.d) * (Fa * iro_a + Fb * fb.a);
+        vsig_max = fmax(vsig_max, cs_a + 2.0 * avr);
+    }
+    fx       = group_sum<G>(fx);
+    fy       = group_sum<G>(fy);
+    fz       = group_sum<G>(fz);
+    dU1      = group_sum<G>(dU1);
+    dU2      = group_sum<G>(dU2);
+    vsig_max = group_max<G>(vsig_max);
+    f64 dt_out = f64(INFINITY);
+    if (valid && sub == 0) {
+        f64 ax = -p.pmass * fx + axyz_ext[3 * u64(id)];
+        f64 ay = -p.pmass * fy + axyz_ext[3 * u64(id) + 1];
+        f64 az = -p.pmass * fz + axyz_ext[3 * u64(id) + 2];
+        axyz[3 * u64(id)]     = ax;
+        axyz[3 * u64(id) + 1] = ay;
+        axyz[3 * u64(id) + 2] = az;
+        duint[id]             = p.pmass * (dU1 + 0.5 * p.alpha_u * dU2);
+        vsig_out[id]          = vsig_max;
+        f64 dt_c = C_cour * h_a / vsig_max;
+        f64 dt_f = C_force * sqrt(h_a / sqrt(ax * ax + ay * ay + az * az));
+        dt_out   = fmin(dt_c, dt_f);
+        cfl_out[id] = dt_out;
+    }
+    __shared__ f64 smin[BLK / 32];
+    f64 m = warp_min(dt_out);
+    if ((threadIdx.x & 31) == 0)
+        smin[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        f64 b = smin[0];
+#pragma unroll
+        for (int q = 1; q < BLK / 32; q++)
+            b = fmin(b, smin[q]);
+        atomicMin((unsigned long long *) red_min, (unsigned long long) f64_to_ordered(b));
+    }
+}
+
+template<int G>
+unsigned grid_groups(u32 N) {
+    return grid_for(u64(N) * G, BLK);
+}
+
+} // namespace
+
+// lanes per particle: ~60 accepted pairs (M4) / ~150 (M6) per list
+#define SB_KDG(kernel, CALL)                                                                     \
+    do {                                                                                         \
+        if ((kernel) == KERN_M4) {                                                               \
+            using KT        = KM4;                                                               \
+            constexpr int G = 8;                                                                 \
+            CALL;                                                                                \
+        } else {                                                                                 \
+            using KT        = KM6;                                                               \
+            constexpr int G = 16;                                                                \
+            CALL;                                                                                \
+        }                                                                                        \
+        SB_COUNT_LAUNCH();                                                                       \
+        SB_LAUNCH_CHECK();                                                                       \
+    } while (0)
+
+void h_solve_fast(
+    cudaStream_t s, int kernel, RankCsr c, const Pack4 *SA, const f64 *h_old, f64 *hpart, f64 *eps, f64 *omega,
+    f64 pmass, f64 h_evol_max, f64 h_evol_iter_max, u32 max_sweeps, bool do_iter, bool do_omega, u64 *red) {
+    if (!c.N)
+        return;
+    SB_KDG(kernel, (h_solve_fast_kernel<KT, G><<<grid_groups<G>(c.N), BLK, 0, s>>>(
+                       c, SA, h_old, hpart, eps, omega, pmass, h_evol_max, h_evol_iter_max, max_sweeps, do_iter,
+                       do_omega, red)));
+}
+
+void av_operators_fast(
+    cudaStream_t s, int kernel, RankCsr c, const Pack4 *SA, const Pack4 *SB, const Pack4 *SC, const Pack4 *SD,
+    f64 pmass, bool want_curl, bool want_dtdivv, bool combined, f64 *divv, f64 *curlv, f64 *dtdivv) {
+    if (!c.N)
+        return;
+#define AVOP(S_, C_, M_, CB_)                                                                    \
+    SB_KDG(kernel, (av_operators_fast_kernel<KT, G, S_, C_, M_, CB_><<<grid_groups<G>(c.N), BLK, 0, s>>>(   \
+                       c, SA, SB, SC, SD, pmass, divv, curlv, dtdivv)))
+    if (want_dtdivv) {
+        if (combined)
+            AVOP(false, false, true, true);
+        else if (want_curl)
+            AVOP(true, true, true, false);
+        else
+            AVOP(true, false, true, false);
+    } else {
+        if (want_curl)
+            AVOP(true, true, false, false);
+        else
+            AVOP(true, false, false, false);
+    }
+#undef AVOP
+}
+
+void derive_fast(
+    cudaStream_t s, int kernel, int av, u32 M, const Pack4 *SA, const Pack4 *SB, const Pack4 *SC, f64 pmass,
+    f64 alpha_AV, Pack4 *SE, Pack4 *SF) {
+    (void) SB;
+    if (!M)
+        return;
+    bool vary = (av == AVK_MM97 || av == AVK_CD10);
+    if (kernel == KERN_M4)
+        derive_fast_kernel<KM4><<<grid_for(M, 256), 256, 0, s>>>(M, vary, alpha_AV, SA, SC, pmass, SE, SF);
+    else
+        derive_fast_kernel<KM6><<<grid_for(M, 256), 256, 0, s>>>(M, vary, alpha_AV, SA, SC, pmass, SE, SF);
+    SB_COUNT_LAUNCH();
+    SB_LAUNCH_CHECK();
+}
+
+void force_cfl_fast(
+    cudaStream_t s, int kernel, int av, RankCsr c, const Pack4 *SA, const Pack4 *SB, const Pack4 *SE, const Pack4 *SF,
+    const Pack4 *SC, SphParams p, const f64 *axyz_ext, f64 *axyz, f64 *duint, f64 C_cour, f64 C_force, f64 *vsig,
+    f64 *cfl_dt, u64 *red_min) {
+    if (!c.N)
+        return;
+#define FRC(AV_)                                                                                 \
+    SB_KDG(kernel, (force_cfl_fast_kernel<KT, AV_, G><<<grid_groups<G>(c.N), BLK, 0, s>>>(       \
+                       c, SA, SB, SE, SF, SC, p, axyz_ext, axyz, duint, C_cour, C_force, vsig, cfl_dt, red_min)))
+    switch (av) {
+    case AVK_CONSTANT:
+    case AVK_MM97:
+    case AVK_CD10: FRC(AVK_CD10); break; // α·c_s comes from the derived record in every non-disc mode
+    case AVK_DISC: FRC(AVK_DISC); break;
+    default: throw std::invalid_argument("unsupported artificial viscosity configuration");
+    }
+#undef FRC
+}
+
+} // namespace sb

@@ -279,93 +279,101 @@ void ghost_xyzh(cudaStream_t s, u32 cnt, const u32 *ids, const f64 *xyz, const f
 
 /// field packs.  ids == nullptr: identity (real particles of the patch itself)
 /// A.d = h ; B = (v, u) ; C.b = omega ; D = (a, 0) when `axyz` is given
+/// dst_map (optional): record k goes to slot dst_map[k] (the Morton rank of merged index base + k)
 __global__ void __launch_bounds__(256) pack_fields_kernel(
-    u32 cnt, const u32 *__restrict__ ids, const f64 *__restrict__ h, const f64 *__restrict__ vxyz,
-    const f64 *__restrict__ uint_, const f64 *__restrict__ omega, const f64 *__restrict__ axyz,
-    Pack4 *__restrict__ A, Pack4 *__restrict__ B, Pack4 *__restrict__ C, Pack4 *__restrict__ D) {
+    u32 cnt, const u32 *__restrict__ ids, const u32 *__restrict__ dst_map, const f64 *__restrict__ h,
+    const f64 *__restrict__ vxyz, const f64 *__restrict__ uint_, const f64 *__restrict__ omega,
+    const f64 *__restrict__ axyz, Pack4 *__restrict__ A, Pack4 *__restrict__ B, Pack4 *__restrict__ C,
+    Pack4 *__restrict__ D) {
     u32 k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= cnt)
         return;
     u32 id = ids ? ids[k] : k;
-    A[k].d = h[id];
-    B[k]   = Pack4{vxyz[3 * u64(id)], vxyz[3 * u64(id) + 1], vxyz[3 * u64(id) + 2], uint_[id]};
-    C[k].b = omega[id];
+    u32 o  = dst_map ? dst_map[k] : k;
+    A[o].d = h[id];
+    B[o]   = Pack4{vxyz[3 * u64(id)], vxyz[3 * u64(id) + 1], vxyz[3 * u64(id) + 2], uint_[id]};
+    C[o].b = omega[id];
     if (axyz)
-        D[k] = Pack4{axyz[3 * u64(id)], axyz[3 * u64(id) + 1], axyz[3 * u64(id) + 2], 0.};
+        D[o] = Pack4{axyz[3 * u64(id)], axyz[3 * u64(id) + 1], axyz[3 * u64(id) + 2], 0.};
 }
 void pack_fields(
     cudaStream_t s, u32 cnt, const u32 *ids, const f64 *h, const f64 *vxyz, const f64 *uint_, const f64 *omega,
-    const f64 *axyz, Pack4 *A, Pack4 *B, Pack4 *C, Pack4 *D) {
+    const f64 *axyz, Pack4 *A, Pack4 *B, Pack4 *C, Pack4 *D, const u32 *dst_map) {
     if (!cnt)
         return;
-    pack_fields_kernel<<<grid_for(cnt, 256), 256, 0, s>>>(cnt, ids, h, vxyz, uint_, omega, axyz, A, B, C, D);
+    pack_fields_kernel<<<grid_for(cnt, 256), 256, 0, s>>>(cnt, ids, dst_map, h, vxyz, uint_, omega, axyz, A, B, C, D);
     SB_COUNT_LAUNCH();
     SB_LAUNCH_CHECK();
 }
 /// received ghost-field blocks → merged arrays: A.d = h, B = (v,u), C.b = omega, D = (a,0)
 __global__ void __launch_bounds__(256) unpack_ghost_fields_kernel(
     u32 cnt, const Pack4 *__restrict__ sA, const Pack4 *__restrict__ sB, const Pack4 *__restrict__ sC,
-    const Pack4 *__restrict__ sD, Pack4 *__restrict__ A, Pack4 *__restrict__ B, Pack4 *__restrict__ C,
-    Pack4 *__restrict__ D) {
+    const Pack4 *__restrict__ sD, const u32 *__restrict__ dst_map, Pack4 *__restrict__ A, Pack4 *__restrict__ B,
+    Pack4 *__restrict__ C, Pack4 *__restrict__ D) {
     u32 k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= cnt)
         return;
-    A[k].d = sA[k].d;
-    B[k]   = sB[k];
-    C[k].b = sC[k].b;
+    u32 o  = dst_map ? dst_map[k] : k;
+    A[o].d = sA[k].d;
+    B[o]   = sB[k];
+    C[o].b = sC[k].b;
     if (sD)
-        D[k] = sD[k];
+        D[o] = sD[k];
 }
 void unpack_ghost_fields(
     cudaStream_t s, u32 cnt, const Pack4 *sA, const Pack4 *sB, const Pack4 *sC, const Pack4 *sD, Pack4 *A, Pack4 *B,
-    Pack4 *C, Pack4 *D) {
+    Pack4 *C, Pack4 *D, const u32 *dst_map) {
     if (!cnt)
         return;
-    unpack_ghost_fields_kernel<<<grid_for(cnt, 256), 256, 0, s>>>(cnt, sA, sB, sC, sD, A, B, C, D);
+    unpack_ghost_fields_kernel<<<grid_for(cnt, 256), 256, 0, s>>>(cnt, sA, sB, sC, sD, dst_map, A, B, C, D);
     SB_COUNT_LAUNCH();
     SB_LAUNCH_CHECK();
 }
 /// C[k].d = alpha[ids ? ids[k] : k]
-__global__ void __launch_bounds__(256) pack_alpha_kernel(u32 cnt, const u32 *__restrict__ ids, const f64 *__restrict__ alpha, Pack4 *__restrict__ C) {
+__global__ void __launch_bounds__(256) pack_alpha_kernel(
+    u32 cnt, const u32 *__restrict__ ids, const u32 *__restrict__ dst_map, const f64 *__restrict__ alpha,
+    Pack4 *__restrict__ C) {
     u32 k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= cnt)
         return;
-    C[k].d = alpha[ids ? ids[k] : k];
+    C[dst_map ? dst_map[k] : k].d = alpha[ids ? ids[k] : k];
 }
-void pack_alpha(cudaStream_t s, u32 cnt, const u32 *ids, const f64 *alpha, Pack4 *C) {
+void pack_alpha(cudaStream_t s, u32 cnt, const u32 *ids, const f64 *alpha, Pack4 *C, const u32 *dst_map) {
     if (!cnt)
         return;
-    pack_alpha_kernel<<<grid_for(cnt, 256), 256, 0, s>>>(cnt, ids, alpha, C);
+    pack_alpha_kernel<<<grid_for(cnt, 256), 256, 0, s>>>(cnt, ids, dst_map, alpha, C);
     SB_COUNT_LAUNCH();
     SB_LAUNCH_CHECK();
 }
 /// out[i] = C[i].c (sound speed of the real particles → main field, Solver.cpp:3129-3161)
-__global__ void __launch_bounds__(256) unpack_cs_kernel(u32 n, const Pack4 *__restrict__ C, f64 *__restrict__ cs) {
+__global__ void __launch_bounds__(256) unpack_cs_kernel(
+    u32 n, const Pack4 *__restrict__ C, const u32 *__restrict__ src_map, f64 *__restrict__ cs) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n)
-        cs[i] = C[i].c;
+        cs[i] = C[src_map ? src_map[i] : i].c;
 }
-void unpack_cs(cudaStream_t s, u32 n, const Pack4 *C, f64 *cs) {
+void unpack_cs(cudaStream_t s, u32 n, const Pack4 *C, f64 *cs, const u32 *src_map) {
     if (!n)
         return;
-    unpack_cs_kernel<<<grid_for(n, 256), 256, 0, s>>>(n, C, cs);
+    unpack_cs_kernel<<<grid_for(n, 256), 256, 0, s>>>(n, C, src_map, cs);
     SB_COUNT_LAUNCH();
     SB_LAUNCH_CHECK();
 }
 /// generic component extraction for inspection (tests): out[i*nc + c] = P[i].comp(first + c)
-__global__ void __launch_bounds__(256) unpack_comp_kernel(u32 n, const Pack4 *__restrict__ P, int first, int nc, f64 *__restrict__ out) {
+__global__ void __launch_bounds__(256) unpack_comp_kernel(
+    u32 n, const Pack4 *__restrict__ P, const u32 *__restrict__ src_map, int first, int nc, f64 *__restrict__ out) {
     u64 t = u64(blockIdx.x) * blockDim.x + threadIdx.x;
     if (t >= u64(n) * nc)
         return;
     u32 i = u32(t / nc);
     int c = first + int(t % nc);
-    const f64 *q = reinterpret_cast<const f64 *>(P + i);
+    const f64 *q = reinterpret_cast<const f64 *>(P + (src_map ? src_map[i] : i));
     out[t]       = q[c];
 }
-void unpack_comp(cudaStream_t s, u32 n, const Pack4 *P, int first, int nc, f64 *out) {
+void unpack_comp(cudaStream_t s, u32 n, const Pack4 *P, int first, int nc, f64 *out, const u32 *src_map) {
     if (!n)
         return;
-    unpack_comp_kernel<<<grid_for(u64(n) * nc, 256), 256, 0, s>>>(n, P, first, nc, out);
+    unpack_comp_kernel<<<grid_for(u64(n) * nc, 256), 256, 0, s>>>(n, P, src_map, first, nc, out);
     SB_COUNT_LAUNCH();
     SB_LAUNCH_CHECK();
 }

@@ -16,12 +16,13 @@ void scatter_ids(cudaStream_t s, u32 n, const u8 *flag, const u32 *pos, u32 *ids
 void gather_field(cudaStream_t s, u32 cnt, int nvar, const u32 *ids, const f64 *src, f64 *dst);
 void pack_xyzh(cudaStream_t s, u32 n, const f64 *xyz, const f64 *h, Pack4 *A);
 void ghost_xyzh(cudaStream_t s, u32 cnt, const u32 *ids, const f64 *xyz, const f64 *h, const f64 off[3], Pack4 *A_dst);
+/// dst_map / src_map (optional) redirect record k to slot map[k] (Morton-sorted storage)
 void pack_fields(cudaStream_t s, u32 cnt, const u32 *ids, const f64 *h, const f64 *vxyz, const f64 *uint_,
-                 const f64 *omega, const f64 *axyz, Pack4 *A, Pack4 *B, Pack4 *C, Pack4 *D);
+                 const f64 *omega, const f64 *axyz, Pack4 *A, Pack4 *B, Pack4 *C, Pack4 *D, const u32 *dst_map = nullptr);
 void unpack_ghost_fields(cudaStream_t s, u32 cnt, const Pack4 *sA, const Pack4 *sB, const Pack4 *sC, const Pack4 *sD,
-                         Pack4 *A, Pack4 *B, Pack4 *C, Pack4 *D);
-void pack_alpha(cudaStream_t s, u32 cnt, const u32 *ids, const f64 *alpha, Pack4 *C);
-void unpack_cs(cudaStream_t s, u32 n, const Pack4 *C, f64 *cs);
-void unpack_comp(cudaStream_t s, u32 n, const Pack4 *P, int first, int nc, f64 *out);
+                         Pack4 *A, Pack4 *B, Pack4 *C, Pack4 *D, const u32 *dst_map = nullptr);
+void pack_alpha(cudaStream_t s, u32 cnt, const u32 *ids, const f64 *alpha, Pack4 *C, const u32 *dst_map = nullptr);
+void unpack_cs(cudaStream_t s, u32 n, const Pack4 *C, f64 *cs, const u32 *src_map = nullptr);
+void unpack_comp(cudaStream_t s, u32 n, const Pack4 *P, int first, int nc, f64 *out, const u32 *src_map = nullptr);
 void max_reduce(cudaStream_t s, u32 n, const f64 *v, u64 *red);
 } // namespace sb

@@ -16,8 +16,6 @@
 
 namespace sb {
 
-unsigned long long g_launch_count = 0;
-
 // =============================================================================================
 // bounding box (K1) : min/max of the positions, widened by one ulp (BuildTrees.cpp:41-56)
 // =============================================================================================

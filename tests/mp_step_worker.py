@@ -17,6 +17,7 @@ from tests.test_gpu_step import INT_NAMES, close  # noqa: E402
 
 def main():
     which = sys.argv[1]
+    fp_mode = sys.argv[2] if len(sys.argv) > 2 else "strict"
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -31,11 +32,11 @@ def main():
     else:
         sc = S.disc(8000, "M4", grid=(2, 2, 2))
         steps, rtol = 2, 1e-12
-    strict = b"strict" in _capi.lib().shamb200_build_info()
+    strict = fp_mode == "strict"
     if not strict:
         rtol = 1e-10
     o = S.make_oracle(sc)
-    m = S.make_cuda(sc, ctx=_capi.Context(local), rank=rank, world=world, nccl_id=ids[0])
+    m = S.make_cuda(sc, ctx=_capi.Context(local), rank=rank, world=world, nccl_id=ids[0], fp_mode=fp_mode)
     names = ["xyz", "vxyz", "axyz", "hpart", "uint", "duint", "step.mxyz", "step.omega", "step.pressure", "step.g_v",
              "step.vsig"]
     if sc["cfg"]["av"] == 3:
@@ -55,14 +56,15 @@ def main():
                 continue
             nloc += 1
             for nm in INT_NAMES:
-                assert np.array_equal(m.get(ip, nm), o.get(ip, nm)), (k, ip, nm)
+                if strict or k == 0:
+                    assert np.array_equal(m.get(ip, nm), o.get(ip, nm)), (k, ip, nm)
             for nm in names:
                 ok, msg = close(m.get(ip, nm), o.get(ip, nm), rtol)
                 assert ok, (k, ip, nm, msg)
     assert nloc > 0
     moved = sum(o.patch_size(ip) for ip in range(o.patch_count))
     dist.barrier()
-    print(f"rank {rank}: {which} ok ({nloc} patch-steps checked, N={moved})", flush=True)
+    print(f"rank {rank}: {which} {fp_mode} ok ({nloc} patch-steps checked, N={moved})", flush=True)
     m.close()
     dist.destroy_process_group()
 

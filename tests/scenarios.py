@@ -129,7 +129,7 @@ def make_oracle(sc):
     return s
 
 
-def make_cuda(sc, ctx=None, keep_step_data=True, rank=0, world=1, nccl_id=None):
+def make_cuda(sc, ctx=None, keep_step_data=True, rank=0, world=1, nccl_id=None, fp_mode="strict"):
     from shamrock_b200 import _capi
 
     ctx = ctx or _capi.Context(0)
@@ -139,6 +139,7 @@ def make_cuda(sc, ctx=None, keep_step_data=True, rank=0, world=1, nccl_id=None):
         setattr(cfg, k, int(v) if isinstance(cur, int) else float(v))
     cfg.sort_mode = _capi.SORT_MODES[sc.get("sort_mode", "bitonic")]
     cfg.keep_step_data = int(keep_step_data)
+    cfg.fp_mode = _capi.FP_MODES[fp_mode]
     for i, (c, r) in enumerate(sc["kill"]):
         for d in range(3):
             cfg.kill_center[i][d] = c[d]

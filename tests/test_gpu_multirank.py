@@ -13,12 +13,13 @@ torch = pytest.importorskip("torch")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+@pytest.mark.parametrize("fp_mode", ["strict", "fast"])
 @pytest.mark.parametrize("which", ["periodic", "sod", "disc"])
-def test_two_rank_step_matches_oracle(which):
+def test_two_rank_step_matches_oracle(which, fp_mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "mp_step_worker.py"), which]
+           "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "mp_step_worker.py"), which, fp_mode]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + "\n" + r.stderr[-6000:]
-    assert r.stdout.count(f"{which} ok") == 2
+    assert r.stdout.count(f"{which} {fp_mode} ok") == 2

@@ -1,12 +1,13 @@
 """GPU parity, whole path: shamb200_model_evolve_once (Solver::evolve_once on the B200) against the
 CPU oracle on the same seeded initial conditions.
 
-Strict build (default, -fmad=false): every integer output (Morton codes, sort permutation, tree,
-neighbour lists) and every float64 field must be BIT-IDENTICAL to the oracle, which evaluates the
-reference's expressions in the reference's order without FMA contraction.  The one exception is the
-LP07 equation of state (`pow`, not correctly rounded on either side): 1e-12 relative there.
-Fast build (SHAMB200_FAST_MATH=1): north-star tolerance, 1e-10 relative per particle
-(|d| <= 1e-10 * max(|x|, mean|x|))."""
+fp_mode strict (default): every integer output (Morton codes, sort permutation, tree, neighbour
+lists) and every float64 field must be BIT-IDENTICAL to the oracle, which evaluates the reference's
+expressions in the reference's order without FMA contraction.  The one exception is the LP07 equation
+of state (`pow`, not correctly rounded on either side): 1e-12 relative there.
+fp_mode fast (the bench mode): north-star tolerance, 1e-10 relative per particle
+(|d| <= 1e-10 * max(|x|, mean|x|)); integer outputs are exact whenever the inputs are
+(first step); afterwards the float64 inputs of the tree differ in the last bits."""
 import numpy as np
 import pytest
 
@@ -25,8 +26,7 @@ STEP = ["step.mxyz", "step.rint", "step.omega", "step.pressure", "step.soundspee
         "step.g_v", "step.g_omega", "step.vsig", "step.cfl_dt", "tree.aabb_min", "tree.aabb_max"]
 
 
-def strict():
-    return b"strict" in _capi.lib().shamb200_build_info()
+FP_MODES = ["strict", "fast"]
 
 
 def close(a, b, rtol):
@@ -44,7 +44,7 @@ def close(a, b, rtol):
     return bool((err <= rtol).all()), f"max rel err {err.max():.3e}"
 
 
-def compare(m, o, sc, rtol, names_extra=()):
+def compare(m, o, sc, rtol, names_extra=(), ints_exact=True):
     cfg = sc["cfg"]
     names = list(MAIN) + list(STEP) + list(names_extra)
     if cfg["av"] in (2, 3):
@@ -61,7 +61,10 @@ def compare(m, o, sc, rtol, names_extra=()):
             continue
         for nm in INT_NAMES:
             g, r = m.get(ip, nm), o.get(ip, nm)
-            assert g.shape == r.shape and np.array_equal(g, r), f"patch {ip} {nm} differs (bit-exact contract)"
+            if ints_exact:
+                assert g.shape == r.shape and np.array_equal(g, r), f"patch {ip} {nm} differs (bit-exact contract)"
+            else:  # float inputs differ in the last bits: a borderline pair / cell may flip
+                assert abs(len(g) - len(r)) <= 1e-5 * len(r) + 2, f"patch {ip} {nm} size"
         for nm in names:
             ok, msg = close(m.get(ip, nm), o.get(ip, nm), rtol)
             if not ok:
@@ -69,65 +72,82 @@ def compare(m, o, sc, rtol, names_extra=()):
     assert not report, "\n".join(report)
 
 
-def run_and_compare(sc, steps=2, rtol=None):
+def run_and_compare(sc, steps=2, rtol=None, fp_mode="strict"):
+    exact = fp_mode == "strict"
     if rtol is None:
-        rtol = 0.0 if strict() else 1e-10
+        rtol = 0.0 if exact else 1e-10
+    if not exact:
+        rtol = max(rtol, 1e-10)
     o = S.make_oracle(sc)
-    m = S.make_cuda(sc)
+    m = S.make_cuda(sc, fp_mode=fp_mode)
     for k in range(steps):
         so, sm = o.evolve_once(), m.evolve_once()
-        for key in ("h_subcycles", "h_iters_last", "corrector_iter", "npart"):
+        for key in ("h_subcycles", "corrector_iter", "npart") + (("h_iters_last",) if exact else ()):
             assert so[key] == sm[key], (k, key, so[key], sm[key])
         for key in ("time", "dt", "cfl_multiplier"):
             ok, msg = close([sm[key]], [so[key]], rtol)
             assert ok, (k, key, so[key], sm[key])
         # eps_v = sqrt(max dv^2) / sqrt(sum v^2 / N): the sum is a parallel reduction (order differs)
-        assert abs(sm["eps_v"] - so["eps_v"]) <= 1e-12 * max(abs(so["eps_v"]), 1e-300) + 0.0, (k, so["eps_v"], sm["eps_v"])
-        compare(m, o, sc, rtol)
+        assert abs(sm["eps_v"] - so["eps_v"]) <= max(rtol, 1e-12) * max(abs(so["eps_v"]), 1e-300), (k, so["eps_v"], sm["eps_v"])
+        compare(m, o, sc, rtol, ints_exact=exact or k == 0)
     m.close()
     return so
 
 
+@pytest.mark.parametrize("fp_mode", FP_MODES)
 @pytest.mark.parametrize("kernel,av,two_stage", [("M4", "cd10", True), ("M6", "cd10", True), ("M4", "mm97", False),
                                                  ("M6", "constant", True)])
-def test_periodic_box_step(kernel, av, two_stage):
+def test_periodic_box_step(kernel, av, two_stage, fp_mode):
     """BASELINE configs C3/C4 geometry (sph_homogeneous_benchmark.py), one patch, 27 periodic self-images"""
-    run_and_compare(S.periodic_box(6000, kernel, av, jitter=0.15, two_stage=two_stage))
+    run_and_compare(S.periodic_box(6000, kernel, av, jitter=0.15, two_stage=two_stage), fp_mode=fp_mode)
 
 
-def test_periodic_box_lattice_ties():
+@pytest.mark.parametrize("fp_mode", FP_MODES)
+def test_periodic_box_lattice_ties(fp_mode):
     """unperturbed HCP lattice: exact ties in distances and Morton codes"""
-    run_and_compare(S.periodic_box(9000, "M4", "cd10", jitter=0.0))
+    run_and_compare(S.periodic_box(9000, "M4", "cd10", jitter=0.0), fp_mode=fp_mode)
 
 
+@pytest.mark.parametrize("fp_mode", FP_MODES)
 @pytest.mark.parametrize("grid", [(2, 1, 1), (2, 2, 2), (4, 2, 1)])
-def test_periodic_box_multi_patch(grid):
+def test_periodic_box_multi_patch(grid, fp_mode):
     """several patches on one GPU: interfaces between patches + periodic images, particle migration"""
-    run_and_compare(S.periodic_box(12000, "M4", "cd10", jitter=0.2, grid=grid), steps=3)
+    run_and_compare(S.periodic_box(12000, "M4", "cd10", jitter=0.2, grid=grid), steps=3, fp_mode=fp_mode)
 
 
-def test_sod_tube():
+@pytest.mark.parametrize("fp_mode", FP_MODES)
+def test_sod_tube(fp_mode):
     """BASELINE config C1 geometry (sod_tube_sph.py, M6 + CD10 + periodic), two patches; the density
     jump makes the first prestep go through several ghost-zone sub-cycles (eps = -1 path)"""
-    so = run_and_compare(S.sod_tube(16, "M6"), steps=2)
+    so = run_and_compare(S.sod_tube(16, "M6"), steps=2, fp_mode=fp_mode)
     assert so["npart"] > 0
 
 
-def test_sod_tube_m4_many_subcycles():
+@pytest.mark.parametrize("fp_mode", FP_MODES)
+def test_sod_tube_m4_many_subcycles(fp_mode):
     sc = S.sod_tube(12, "M4", grid=(1, 1, 1))
     o = S.make_oracle(sc)
     st = o.evolve_once()
     assert st["h_subcycles"] > 1  # exercises the rebuild path
-    run_and_compare(sc, steps=1)
+    run_and_compare(sc, steps=1, fp_mode=fp_mode)
 
 
-def test_disc_point_mass_free_boundaries():
+@pytest.mark.parametrize("fp_mode", FP_MODES)
+def test_disc_point_mass_free_boundaries(fp_mode):
     """BASELINE config C5 physics: free BC, LP07 EOS, ConstantDisc AV, point mass with accretion, kill sphere"""
-    run_and_compare(S.disc(5000, "M4"), steps=2, rtol=1e-12 if strict() else 1e-10)
+    run_and_compare(S.disc(5000, "M4"), steps=2, rtol=1e-12, fp_mode=fp_mode)
 
 
-def test_disc_multi_patch_m6():
-    run_and_compare(S.disc(8000, "M6", grid=(2, 2, 1)), steps=2, rtol=1e-12 if strict() else 1e-10)
+@pytest.mark.parametrize("fp_mode", FP_MODES)
+def test_disc_multi_patch_m6(fp_mode):
+    run_and_compare(S.disc(8000, "M6", grid=(2, 2, 1)), steps=2, rtol=1e-12, fp_mode=fp_mode)
+
+
+def test_epsilon_h_other_than_default_uses_the_sweep_loop():
+    """epsilon_h != 1e-6 falls back to one launch per sweep (LoopSmoothingLengthIter semantics)"""
+    sc = S.periodic_box(4000, "M4", "cd10", jitter=0.15)
+    sc["cfg"]["epsilon_h"] = 1e-4
+    run_and_compare(sc, steps=2)
 
 
 def test_radix_mode_within_tolerance():
@@ -135,7 +155,7 @@ def test_radix_mode_within_tolerance():
     floats within 1e-10 relative of the oracle (north-star tolerance)"""
     sc = S.periodic_box(8000, "M4", "cd10", jitter=0.1, sort_mode="radix")
     o = S.make_oracle(sc)
-    m = S.make_cuda(sc)
+    m = S.make_cuda(sc, fp_mode="fast")
     for _ in range(2):
         so, sm = o.evolve_once(), m.evolve_once()
     assert so["npart"] == sm["npart"] and so["h_subcycles"] == sm["h_subcycles"]
@@ -172,7 +192,7 @@ def test_dt_zero_replay_is_stationary():
 def test_momentum_conservation_bench_size():
     """size-independent property at a larger size (no oracle): pairwise-antisymmetric forces sum to ~0"""
     sc = S.periodic_box(400000, "M4", "cd10", jitter=0.1)
-    m = S.make_cuda(sc, keep_step_data=False)
+    m = S.make_cuda(sc, keep_step_data=False, fp_mode="fast")
     st = m.evolve_once()
     a = m.get(0, "axyz")
     assert st["npart"] == len(sc["xyz"])

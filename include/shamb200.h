@@ -70,6 +70,11 @@ int shamb200_ctx_destroy(shamb200_ctx *ctx);
 void *shamb200_ctx_stream(shamb200_ctx *ctx);
 int shamb200_ctx_synchronize(shamb200_ctx *ctx);
 
+/* roofline denominators measured on this device (pattern of the reference's own micro-benchmarks,
+ * shamsys/src/MicroBenchmark.cpp:51-77): what = 0 FP64 FMA chains [TFLOP/s, FMA = 2 flop],
+ * what = 1 streaming copy [GB/s, read + write]. */
+int shamb200_microbench(shamb200_ctx *ctx, int what, double *out);
+
 /* ---- tree (shamtree::CompressedLeafBVH<u32, f64_3, 3>) ----------------------------------------
  * Device-resident output of rebuild_from_positions; contract of SURVEY.md §3.3. */
 typedef struct shamb200_tree {

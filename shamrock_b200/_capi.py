@@ -77,6 +77,7 @@ SYMBOLS = [
     "shamb200_model_set_field", "shamb200_model_evolve_once", "shamb200_model_state",
     "shamb200_model_set_next_dt", "shamb200_model_set_time", "shamb200_model_set_cfl_multiplier",
     "shamb200_model_stage_times", "shamb200_plan_patch_grid", "shamb200_plan_interfaces",
+    "shamb200_microbench",
 ]
 
 _lib = None
@@ -142,6 +143,12 @@ class Context:
             self.close()
         except Exception:
             pass
+
+    def microbench(self, what):
+        """'fp64' -> TFLOP/s of FP64 FMA chains, 'copy' -> GB/s of a streaming copy (read + write)"""
+        out = C.c_double()
+        check(lib().shamb200_microbench(self.h, {"fp64": 0, "copy": 1}[what], C.byref(out)))
+        return out.value
 
     @property
     def stream(self):

@@ -20,6 +20,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off"]
 SOURCES = {
     "runtime.cu": ["-fmad=false"],
+    "microbench.cu": ["-fmad=true"],
     "tree.cu": ["-fmad=false"],
     "neigh.cu": ["-fmad=false"],
     "stream_kernels.cu": ["-fmad=false"],

@@ -205,6 +205,13 @@ int shamb200_compute_omega(
     });
 }
 
+int shamb200_microbench(shamb200_ctx *ctx, int what, double *out) {
+    return guard([&] {
+        SB_CUDA_CHECK(cudaSetDevice(ctx->c.device));
+        *out = microbench(ctx->c, what);
+    });
+}
+
 // ---- planning (host only) -------------------------------------------------------------------------
 int shamb200_plan_patch_grid(
     const double bmin[3], const double bmax[3], uint32_t nx, uint32_t ny, uint32_t nz, int world_size,

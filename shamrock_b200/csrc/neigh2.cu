@@ -142,11 +142,11 @@ struct NodeRegs {
     u32 left, right;
 };
 __device__ __forceinline__ NodeRegs load_node(const NodePack *p) {
-    const double2 *q = reinterpret_cast<const double2 *>(p);
-    double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
+    const Pack4 *q = reinterpret_cast<const Pack4 *>(p); // two 256-bit loads
+    Pack4 a = ld4(q), b = ld4(q + 1);
     NodeRegs n;
-    n.lo0 = a.x, n.lo1 = a.y, n.lo2 = b.x, n.hi0 = b.y, n.hi1 = c.x, n.hi2 = c.y, n.rint = d.x;
-    u64 ch  = (u64) __double_as_longlong(d.y);
+    n.lo0 = a.a, n.lo1 = a.b, n.lo2 = a.c, n.hi0 = a.d, n.hi1 = b.a, n.hi2 = b.b, n.rint = b.c;
+    u64 ch  = (u64) __double_as_longlong(b.d);
     n.left  = u32(ch & 0xffffffffull);
     n.right = u32(ch >> 32);
     return n;
@@ -305,10 +305,9 @@ __global__ void __launch_bounds__(S2_WARPS * 32) neigh_mask_kernel(
             continue;
         __syncwarp();
         if (va) {
-            const double2 *q = reinterpret_cast<const double2 *>(SA + r);
-            double2 lo = __ldg(q), hi = __ldg(q + 1);
-            f64 rint_a = hi.y * h_tolerance;
-            w.pa[__popc(bal & ((1u << lane) - 1u))] = Pack4{lo.x, lo.y, hi.x, rint_a * rint_a * Rker2};
+            Pack4 q    = ld4(SA + r);
+            f64 rint_a = q.d * h_tolerance;
+            w.pa[__popc(bal & ((1u << lane) - 1u))] = Pack4{q.a, q.b, q.c, rint_a * rint_a * Rker2};
         }
         __syncwarp();
         u32 mycount = 0;
@@ -317,11 +316,10 @@ __global__ void __launch_bounds__(S2_WARPS * 32) neigh_mask_kernel(
             bool vb = j < ncand;
             f64 bx = 0, by = 0, bz = 0, lim_b = 0;
             if (vb) {
-                u32 rank_b       = cand_rank(w, nr, j);
-                const double2 *q = reinterpret_cast<const double2 *>(SA + rank_b);
-                double2 lo = __ldg(q), hi = __ldg(q + 1);
-                bx = lo.x, by = lo.y, bz = hi.x;
-                f64 rint_b = hi.y * h_tolerance;
+                u32 rank_b = cand_rank(w, nr, j);
+                Pack4 q    = ld4(SA + rank_b);
+                bx = q.a, by = q.b, bz = q.c;
+                f64 rint_b = q.d * h_tolerance;
                 lim_b      = rint_b * rint_b * Rker2;
             }
             u32 mymask = 0;

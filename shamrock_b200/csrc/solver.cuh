@@ -142,6 +142,8 @@ struct Model {
     void read_red(int n);
 };
 
+f64 microbench(Ctx &c, int what); ///< microbench.cu
+
 // NCCL plumbing (solver_comm.cu)
 void comm_unique_id(void *out128);
 void comm_init(Model &m, int rank, int world, const void *id128);

@@ -21,12 +21,7 @@
 
 namespace sb {
 
-__device__ __forceinline__ Pack4 ldg4(const Pack4 *p) {
-    // one 32-byte sector: two 16-byte read-only loads
-    const double2 *q = reinterpret_cast<const double2 *>(p);
-    double2 lo = __ldg(q), hi = __ldg(q + 1);
-    return Pack4{lo.x, lo.y, hi.x, hi.y};
-}
+__device__ __forceinline__ Pack4 ldg4(const Pack4 *p) { return ld4(p); }
 
 constexpr int SPH_BLOCK = 128;
 

@@ -10,6 +10,17 @@ struct alignas(32) Pack4 {
     f64 a, b, c, d;
 };
 
+#ifdef __CUDACC__
+/// one 32-byte record = ONE 256-bit read-only load (LDG.E.256 on sm_100a).  The neighbour loops are bound
+/// by L1 tag lookups (one per distinct 128-byte line per load instruction), so a record must not be
+/// fetched as two 16-byte halves.
+__device__ __forceinline__ Pack4 ld4(const Pack4 *p) {
+    Pack4 r;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.a), "=d"(r.b), "=d"(r.c), "=d"(r.d) : "l"(p));
+    return r;
+}
+#endif
+
 struct CsrView {
     const u32 *cnt, *scanned, *list;
     u32 N;

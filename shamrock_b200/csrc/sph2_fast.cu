@@ -2,9 +2,10 @@
 //
 // Same algorithm and the same neighbour lists as sph2_strict.cu; what changes is how the FP64 pipe — the
 // binding roof of these loops on B200 — is used:
-//  * G lanes per particle stride over its neighbour list (G = 8 for M4, 16 for M6), so a warp's loads
-//    are runs of consecutive ranks (Morton-sorted records) and no lane waits on a longer list;
-//    partial sums are combined with warp shuffles;
+//  * G lanes per particle stride over its neighbour list and combine their partial sums with warp
+//    shuffles.  Measured on B200 (profiles/): with Morton-sorted records a small G wins (G = 2 for M4):
+//    adjacent lanes are adjacent particles whose j-th neighbours sit in the same few cache lines, and
+//    the per-particle prologue / reduction is amortised over more trips;
 //  * everything that depends on ONE particle only (1/h, norm/h^4, rho, 1/(rho^2 Ω), 1/(rho Ω), α c_s,
 //    P/(rho^2 Ω)) is computed once per particle (derive_fast) instead of once per pair: the pair math
 //    has one rsqrt, one reciprocal and one sqrt left (the reference's has ~12 divisions / 2 sqrt);
@@ -13,18 +14,13 @@
 // mode to 1e-10 relative per particle (north-star tolerance).  Reference loops: see sph2_strict.cu.
 #include "sph2.cuh"
 #include "sphkern.cuh"
+#include <cstdlib>
 
 namespace sb {
 
 namespace {
 
 constexpr int BLK = 128;
-
-__device__ __forceinline__ Pack4 ld4(const Pack4 *p) {
-    const double2 *q = reinterpret_cast<const double2 *>(p);
-    double2 lo = __ldg(q), hi = __ldg(q + 1);
-    return Pack4{lo.x, lo.y, hi.x, hi.y};
-}
 
 /// sum over the G lanes of a group, result broadcast from the group's first lane (identical in all lanes)
 /// lanes of this thread's group (groups of one warp may sit in different loop trips: the shuffles name
@@ -33,6 +29,8 @@ template<int G>
 __device__ __forceinline__ u32 group_mask() {
     if (G >= 32)
         return 0xffffffffu;
+    if (G == 1)
+        return 1u << (threadIdx.x & 31u);
     u32 lane = threadIdx.x & 31u;
     return ((1u << G) - 1u) << (lane & ~u32(G - 1));
 }
@@ -62,8 +60,14 @@ __device__ __forceinline__ void density_sums(
     const f64 hinv = 1. / h_a;
     const f64 lim  = h_a * h_a * (K::Rkern * K::Rkern);
     f64 f_acc = 0, g_acc = 0;
-    for (u32 j = s0 + sub; j < s1; j += G) {
-        Pack4 b = ld4(SA + c.list[j]);
+    u32 j  = s0 + sub;
+    u32 rb = j < s1 ? c.list[j] : 0u;
+    while (j < s1) { // the next index is fetched one trip ahead (one memory latency per trip)
+        const u32 jn  = j + G;
+        const u32 rbn = jn < s1 ? c.list[jn] : rb;
+        const Pack4 b = ld4(SA + rb);
+        j  = jn;
+        rb = rbn;
         f64 dx = a.a - b.a, dy = a.b - b.b, dz = a.c - b.c;
         f64 r2 = dx * dx + dy * dy + dz * dz;
         if (r2 > lim)
@@ -201,9 +205,15 @@ __global__ void __launch_bounds__(BLK) av_operators_fast_kernel(
         }
     }
     const u32 s0 = c.off[kk], s1 = s0 + c.cnt[kk];
-    for (u32 j = s0 + sub; j < s1; j += G) {
-        u32 rb   = c.list[j];
-        Pack4 pb = ld4(SA + rb);
+    u32 j  = s0 + sub;
+    u32 rb = j < s1 ? c.list[j] : 0u;
+    while (j < s1) { // next index one trip ahead, the records of this trip requested together
+        const u32 jn  = j + G;
+        const u32 rbn = jn < s1 ? c.list[jn] : rb;
+        const Pack4 pb = ld4(SA + rb), vb = ld4(SB + rb);
+        const Pack4 ab = MAT ? ld4(SD + rb) : Pack4{0, 0, 0, 0};
+        j  = jn;
+        rb = rbn;
         f64 dx = pa.a - pb.a, dy = pa.b - pb.b, dz = pa.c - pb.c;
         f64 r2  = dx * dx + dy * dy + dz * dz;
         f64 h_b = pb.d;
@@ -213,7 +223,6 @@ __global__ void __launch_bounds__(BLK) av_operators_fast_kernel(
         f64 q    = (r2 * rinv) * hinv;
         f64 gs   = dWn_a * K::df(q) * rinv; // ∇W_ab(h_a) = gs · r_ab  (mass factored out)
         f64 gx = gs * dx, gy = gs * dy, gz = gs * dz;
-        Pack4 vb = ld4(SB + rb);
         f64 vx = va.a - vb.a, vy = va.b - vb.b, vz = va.c - vb.c;
         if (SPHDIV) {
             snv += vx * gx + vy * gy + vz * gz;
@@ -224,7 +233,6 @@ __global__ void __launch_bounds__(BLK) av_operators_fast_kernel(
             }
         }
         if (MAT) {
-            Pack4 ab  = ld4(SD + rb);
             f64 v[3]  = {vx, vy, vz};
             f64 a[3]  = {aa.a - ab.a, aa.b - ab.b, aa.c - ab.c};
             f64 rr[3] = {dx, dy, dz};
@@ -310,6 +318,8 @@ __global__ void __launch_bounds__(BLK) av_operators_fast_kernel(
 }
 
 // ---- per-particle derived factors ----------------------------------------------------------------------
+/// SE = (x, y, z, 1/h), SF = (1/(rho² Ω), α c_s, P, rho): with SB = (v, u) the force loop reads THREE
+/// 32-byte records per neighbour (the loop is bound by L1 tag lookups, one per record and line)
 template<class K>
 __global__ void __launch_bounds__(256) derive_fast_kernel(
     u32 M, bool vary, f64 alpha_const, const Pack4 *__restrict__ SA, const Pack4 *__restrict__ SC, f64 pmass,
@@ -317,17 +327,16 @@ __global__ void __launch_bounds__(256) derive_fast_kernel(
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M)
         return;
-    f64 h    = SA[i].d;
+    Pack4 pa = SA[i];
     Pack4 cc = SC[i]; // (P, omega, cs, alpha)
-    f64 hinv = 1. / h;
+    f64 hinv = 1. / pa.d;
     f64 hfh  = K::hfactd * hinv;
     f64 rho  = pmass * hfh * hfh * hfh;
     f64 sub  = rho * rho * cc.b;
     f64 iro2 = (sub != 0. && sub == sub) ? 1. / sub : 0.; // inv_sat_zero
-    f64 iro  = 1. / (rho * cc.b);
     f64 alpha = vary ? cc.d : alpha_const;
-    SE[i] = Pack4{hinv, K::norm_3d * (hinv * hinv) * (hinv * hinv), rho, iro2};
-    SF[i] = Pack4{iro, alpha * cc.c, cc.a * iro2, cc.a};
+    SE[i] = Pack4{pa.a, pa.b, pa.c, hinv};
+    SF[i] = Pack4{iro2, alpha * cc.c, cc.a, rho};
 }
 
 // ---- forces + v_sig + CFL --------------------------------------------------------------------------------
@@ -346,21 +355,31 @@ __global__ void __launch_bounds__(BLK) force_cfl_fast_kernel(
     const u32 id     = c.index_map[r];
     constexpr f64 Rker2 = K::Rkern * K::Rkern;
     constexpr bool DISC = (AV == AVK_DISC);
-    const Pack4 pa = ld4(SA + r), va = ld4(SB + r), ea = ld4(SE + r), fa = ld4(SF + r);
-    const f64 h_a = pa.d, u_a = va.d;
-    const f64 hinv_a = ea.a, dWn_a = ea.b, rho_a = ea.c, iro2_a = ea.d;
-    const f64 iro_a = fa.a, acs_a = fa.b, Pfac_a = fa.c, P_a = fa.d;
-    const f64 cs_a  = SC[r].c;
-    const f64 lim_a = h_a * h_a * Rker2;
+    const Pack4 pa = ld4(SE + r), va = ld4(SB + r), fa = ld4(SF + r);
+    const f64 u_a = va.d;
+    const f64 hinv_a = pa.d, h_a = SA[r].d;
+    const f64 iro2_a = fa.a, acs_a = fa.b, P_a = fa.c, rho_a = fa.d;
+    const f64 dWn_a  = K::norm_3d * (hinv_a * hinv_a) * (hinv_a * hinv_a);
+    const f64 iro_a  = iro2_a * rho_a;
+    const f64 Pfac_a = P_a * iro2_a;
+    const f64 cs_a   = SC[r].c;
+    const f64 lim_a  = h_a * h_a * Rker2;
     f64 fx = 0, fy = 0, fz = 0, dU1 = 0, dU2 = 0, vsig_max = 0;
     const u32 s0 = c.off[kk], s1 = s0 + c.cnt[kk];
-    for (u32 j = s0 + sub; j < s1; j += G) {
-        u32 rb   = c.list[j];
-        Pack4 pb = ld4(SA + rb);
+    // software pipeline: the index of the next neighbour is fetched one trip ahead and the three records of
+    // the current one are requested together (one 256-bit load each), so a trip waits for ONE memory latency
+    u32 j  = s0 + sub;
+    u32 rb = j < s1 ? c.list[j] : 0u;
+    while (j < s1) {
+        const u32 jn  = j + G;
+        const u32 rbn = jn < s1 ? c.list[jn] : rb;
+        const Pack4 pb = ld4(SE + rb), vb = ld4(SB + rb), fb = ld4(SF + rb);
+        j  = jn;
+        rb = rbn;
         f64 dx = pa.a - pb.a, dy = pa.b - pb.b, dz = pa.c - pb.c;
-        f64 r2  = dx * dx + dy * dy + dz * dz;
-        f64 h_b = pb.d;
-        if (r2 > lim_a && r2 > h_b * h_b * Rker2)
+        f64 r2     = dx * dx + dy * dy + dz * dz;
+        f64 hinv_b = pb.d;
+        if (r2 > lim_a && r2 * (hinv_b * hinv_b) > Rker2)
             continue;
         if (r2 < 1e-18) { // r < 1e-9 (the particle itself): zero unit vector, only v_sig sees the pair
             vsig_max = fmax(vsig_max, cs_a);
@@ -368,33 +387,34 @@ __global__ void __launch_bounds__(BLK) force_cfl_fast_kernel(
         }
         f64 rinv = rsqrt(r2);
         f64 rab  = r2 * rinv;
-        Pack4 eb = ld4(SE + rb), vb = ld4(SB + rb), fb = ld4(SF + rb);
         f64 vx = va.a - vb.a, vy = va.b - vb.b, vz = va.c - vb.c;
         f64 vr  = (vx * dx + vy * dy + vz * dz) * rinv;
         f64 avr = fabs(vr);
+        f64 hb2 = hinv_b * hinv_b;
         f64 Fa  = dWn_a * K::df(rab * hinv_a);
-        f64 Fb  = eb.b * K::df(rab * eb.a);
+        f64 Fb  = (K::norm_3d * K::df(rab * hinv_b)) * (hb2 * hb2);
         f64 vsig_a = acs_a + p.beta_AV * avr;
         f64 vsig_b = fb.b + p.beta_AV * avr;
+        f64 rho_b  = fb.d;
         f64 qa_ab, qb_ab;
         if (DISC) { // q_av_disc (q_ab.hpp:42-60)
             f64 vd_a = (vr < 0.) ? vsig_a : acs_a;
             f64 vd_b = (vr < 0.) ? vsig_b : fb.b;
             qa_ab    = (-0.5 * rho_a * rinv * h_a) * vd_a * vr;
-            qb_ab    = (-0.5 * eb.c * rinv * h_b) * vd_b * vr;
+            qb_ab    = (-0.5 * rho_b * rinv * __drcp_rn(hinv_b)) * vd_b * vr;
         } else { // q_av (q_ab.hpp:37-40)
             qa_ab = fmax(-0.5 * rho_a * vsig_a * vr, 0.);
-            qb_ab = fmax(-0.5 * eb.c * vsig_b * vr, 0.);
+            qb_ab = fmax(-0.5 * rho_b * vsig_b * vr, 0.);
         }
         f64 ka = Pfac_a + qa_ab * iro2_a; // (P_a + q_a) / (rho_a² Ω_a)
-        f64 kb = fb.c + qb_ab * eb.d;
+        f64 kb = (fb.c + qb_ab) * fb.a;
         f64 cf = (ka * Fa + kb * Fb) * rinv;
         fx += cf * dx;
         fy += cf * dy;
         fz += cf * dz;
         dU1 += ka * vr * Fa;
-        f64 vsig_u = sqrt(fabs(P_a - fb.d) * 2. * __drcp_rn(rho_a + eb.c));
-        dU2 += vsig_u * (u_a - vb.d) * (Fa * iro_a + Fb * fb.a);
+        f64 vsig_u = sqrt(fabs(P_a - fb.c) * 2. * __drcp_rn(rho_a + rho_b));
+        dU2 += vsig_u * (u_a - vb.d) * (Fa * iro_a + Fb * (fb.a * rho_b));
         vsig_max = fmax(vsig_max, cs_a + 2.0 * avr);
     }
     fx       = group_sum<G>(fx);
@@ -439,17 +459,37 @@ unsigned grid_groups(u32 N) {
 
 } // namespace
 
-// lanes per particle: ~60 accepted pairs (M4) / ~150 (M6) per list
+// lanes per particle.  Default: measured optimum per kernel shape (profiles/); SHAMB200_LANES overrides
+// (1, 2, 4, 8, 16, 32) for tuning runs.
+static int lanes_override() {
+    static int v = [] {
+        const char *e = getenv("SHAMB200_LANES");
+        return e ? atoi(e) : 0;
+    }();
+    return v;
+}
+#define SB_G_CASE(GV, CALL)                                                                      \
+    case GV: {                                                                                   \
+        constexpr int G = GV;                                                                    \
+        CALL;                                                                                    \
+    } break;
 #define SB_KDG(kernel, CALL)                                                                     \
     do {                                                                                         \
+        int g_ = lanes_override();                                                               \
         if ((kernel) == KERN_M4) {                                                               \
-            using KT        = KM4;                                                               \
-            constexpr int G = 8;                                                                 \
-            CALL;                                                                                \
+            using KT = KM4;                                                                      \
+            switch (g_ ? g_ : 2) {                                                               \
+                SB_G_CASE(1, CALL) SB_G_CASE(2, CALL) SB_G_CASE(4, CALL) SB_G_CASE(8, CALL)      \
+                SB_G_CASE(16, CALL) SB_G_CASE(32, CALL)                                          \
+            default: throw std::invalid_argument("SHAMB200_LANES must be 1, 2, 4, 8, 16 or 32"); \
+            }                                                                                    \
         } else {                                                                                 \
-            using KT        = KM6;                                                               \
-            constexpr int G = 16;                                                                \
-            CALL;                                                                                \
+            using KT = KM6;                                                                      \
+            switch (g_ ? g_ : 4) {                                                               \
+                SB_G_CASE(1, CALL) SB_G_CASE(2, CALL) SB_G_CASE(4, CALL) SB_G_CASE(8, CALL)      \
+                SB_G_CASE(16, CALL) SB_G_CASE(32, CALL)                                          \
+            default: throw std::invalid_argument("SHAMB200_LANES must be 1, 2, 4, 8, 16 or 32"); \
+            }                                                                                    \
         }                                                                                        \
         SB_COUNT_LAUNCH();                                                                       \
         SB_LAUNCH_CHECK();                                                                       \

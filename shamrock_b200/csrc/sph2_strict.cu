@@ -19,12 +19,6 @@ namespace {
 
 constexpr int BLK = 128;
 
-__device__ __forceinline__ Pack4 ld4(const Pack4 *p) {
-    const double2 *q = reinterpret_cast<const double2 *>(p);
-    double2 lo = __ldg(q), hi = __ldg(q + 1);
-    return Pack4{lo.x, lo.y, hi.x, hi.y};
-}
-
 // ---- h Newton iteration (all sweeps) + Ω ------------------------------------------------------------
 template<class K>
 __global__ void __launch_bounds__(BLK) h_solve_kernel(

@@ -29,7 +29,9 @@ STEP = ["step.mxyz", "step.rint", "step.omega", "step.pressure", "step.soundspee
 FP_MODES = ["strict", "fast"]
 
 
-def close(a, b, rtol):
+def close(a, b, rtol, floor=0.0):
+    """|a - b| <= rtol * max(|b|, mean|b|, floor); rtol == 0: bit-identical.  `floor` is the magnitude of the
+    individual terms of a sum that cancels (e.g. forces on a perfect lattice): round-off is relative to it."""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     if a.shape != b.shape:
         return False, f"shape {a.shape} vs {b.shape}"
@@ -39,9 +41,19 @@ def close(a, b, rtol):
         ok = np.array_equal(a, b)
         bad = np.argwhere(a != b)
         return ok, "" if ok else f"{len(bad)} mismatches, first {bad[:3].tolist()}, max |d| {np.abs(a - b).max():.3e}"
-    scale = np.maximum(np.abs(b), np.abs(b).mean())
+    scale = np.maximum(np.maximum(np.abs(b), np.abs(b).mean()), floor)
     err = np.abs(a - b) / np.where(scale > 0, scale, 1.0)
     return bool((err <= rtol).all()), f"max rel err {err.max():.3e}"
+
+
+def term_floors(o, ip):
+    """1e-4 x the size of one pair term of the SPH sums: with rtol = 1e-10 this floor tolerates 1e-14 of a
+    term, i.e. the round-off of ~60 cancelling terms (perfect lattice, v = 0: curl v is pure round-off)"""
+    v, a, h = np.abs(o.get(ip, "vxyz")).max(), np.abs(o.get(ip, "axyz")).max(), o.get(ip, "hpart").min()
+    cs2 = (o.get(ip, "step.soundspeed") ** 2).max()
+    dv = 1e-4 * v / h
+    return {"divv": dv, "curlv": dv, "dtdivv": 1e-4 * (a / h + (v / h) ** 2), "axyz": 1e-4 * cs2 / h,
+            "duint": 1e-4 * cs2 * max(v, np.sqrt(cs2)) / h, "step.g_a": 1e-4 * cs2 / h}
 
 
 def compare(m, o, sc, rtol, names_extra=(), ints_exact=True):
@@ -65,8 +77,9 @@ def compare(m, o, sc, rtol, names_extra=(), ints_exact=True):
                 assert g.shape == r.shape and np.array_equal(g, r), f"patch {ip} {nm} differs (bit-exact contract)"
             else:  # float inputs differ in the last bits: a borderline pair / cell may flip
                 assert abs(len(g) - len(r)) <= 1e-5 * len(r) + 2, f"patch {ip} {nm} size"
+        floors = term_floors(o, ip) if rtol else {}
         for nm in names:
-            ok, msg = close(m.get(ip, nm), o.get(ip, nm), rtol)
+            ok, msg = close(m.get(ip, nm), o.get(ip, nm), rtol, floors.get(nm, 0.0))
             if not ok:
                 report.append(f"patch {ip} {nm}: {msg}")
     assert not report, "\n".join(report)
@@ -88,7 +101,9 @@ def run_and_compare(sc, steps=2, rtol=None, fp_mode="strict"):
             ok, msg = close([sm[key]], [so[key]], rtol)
             assert ok, (k, key, so[key], sm[key])
         # eps_v = sqrt(max dv^2) / sqrt(sum v^2 / N): the sum is a parallel reduction (order differs)
-        assert abs(sm["eps_v"] - so["eps_v"]) <= max(rtol, 1e-12) * max(abs(so["eps_v"]), 1e-300), (k, so["eps_v"], sm["eps_v"])
+        # (it only gates the corrector at 1e-2; on a perfect lattice dv is round-off of cancelling sums)
+        assert abs(sm["eps_v"] - so["eps_v"]) <= max(rtol, 1e-12) * max(abs(so["eps_v"]), 1e-2 if rtol else 1e-300), (
+            k, so["eps_v"], sm["eps_v"])
         compare(m, o, sc, rtol, ints_exact=exact or k == 0)
     m.close()
     return so

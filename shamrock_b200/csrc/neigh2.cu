@@ -156,17 +156,15 @@ constexpr int WALK_STACK = 32; // tree depth <= 30 (u32 Morton codes) + 1
 
 __global__ void __launch_bounds__(128) leaf_ranges_kernel(
     const NodePack *__restrict__ nodes, u32 I, u32 L, const u32 *__restrict__ real_prefix, f64 Rkern, u32 cap,
-    u32 *__restrict__ ranges, u32 *__restrict__ nrange, u32 *__restrict__ ncand, u32 *__restrict__ mask_words,
-    u32 *__restrict__ max_ranges) {
+    u32 *__restrict__ ranges, u32 *__restrict__ nrange, u32 *__restrict__ ncand, u32 *__restrict__ max_ranges) {
     u32 g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= L)
         return;
     NodeRegs a = load_node(nodes + I + g);
     u32 nreal  = real_prefix[a.right] - real_prefix[a.left];
     if (nreal == 0) { // a leaf of ghosts only: nobody needs its list
-        nrange[g]     = 0;
-        ncand[g]      = 0;
-        mask_words[g] = 0;
+        nrange[g] = 0;
+        ncand[g]  = 0;
         return;
     }
     f64 a_rint = a.rint * Rkern;
@@ -182,9 +180,11 @@ __global__ void __launch_bounds__(128) leaf_ranges_kernel(
         u32 id     = stack[--sp];
         NodeRegs n = load_node(nodes + id);
         f64 r      = n.rint * Rkern;
-        bool hit   = cella_neigh_b2(a.lo0, a.lo1, a.lo2, a.hi0, a.hi1, a.hi2, n.lo0 - r, n.lo1 - r, n.lo2 - r,
-                                    n.hi0 + r, n.hi1 + r, n.hi2 + r)
-                   || cella_neigh_b2(e0x, e0y, e0z, e1x, e1y, e1z, n.lo0, n.lo1, n.lo2, n.hi0, n.hi1, n.hi2);
+        // cella_neigh_b(a, n ⊕ r) || cella_neigh_b(a ⊕ ra, n): fmax(x,y) <= fmin(u,v) ⟺ x<=v && y<=u when
+        // x<=u and y<=v hold by construction (boxes are not inverted, r >= 0): same booleans, fewer FP64 ops
+        bool hit = (a.lo0 <= n.hi0 + r && n.lo0 - r <= a.hi0 && a.lo1 <= n.hi1 + r && n.lo1 - r <= a.hi1
+                    && a.lo2 <= n.hi2 + r && n.lo2 - r <= a.hi2)
+                   || (e0x <= n.hi0 && n.lo0 <= e1x && e0y <= n.hi1 && n.lo1 <= e1y && e0z <= n.hi2 && n.lo2 <= e1z);
         if (!hit)
             continue;
         if (id >= I) { // leaf: ranks [left, right); DFS visits leaves in ascending order
@@ -214,9 +214,8 @@ __global__ void __launch_bounds__(128) leaf_ranges_kernel(
         }
         nr++;
     }
-    nrange[g]     = nr;
-    ncand[g]      = cand;
-    mask_words[g] = nreal * ((cand + 31) >> 5);
+    nrange[g] = nr < cap ? nr : cap; // clamped: an overflowing search is redone by the host
+    ncand[g]  = cand;
     if (nr > cap)
         atomicMax(max_ranges, nr);
 }
@@ -274,42 +273,59 @@ __device__ __forceinline__ u32 cand_rank(const WarpScratch &w, u32 nr, u32 j) {
     return w.start[lo] + (j - w.pre[lo]);
 }
 
-__global__ void __launch_bounds__(S2_WARPS * 32) neigh_mask_kernel(
+constexpr u32 BALLOT_WORDS = 512; ///< per-warp shared ballot store: (particles of the batch) x (chunks)
+constexpr u32 RANK_CACHE   = 512; ///< per-warp cache of candidate ranks (16 chunks)
+
+struct WarpScratch2 {
+    u32 ball[BALLOT_WORDS];
+    u32 rankc[RANK_CACHE];
+};
+
+/// Stage 2, one launch: warp per leaf, lanes = candidates.  Pass 1 tests every (particle, candidate) pair
+/// and keeps the ballots in shared memory; the warp then reserves the leaf's list space with one atomic
+/// on a global cursor (lists are contiguous per leaf, leaves in completion order — the internal CSR does
+/// not need a global order, the exported ObjectCache is rebuilt by id) and pass 2 replays the ballots.
+/// Leaves whose ballots do not fit the shared store re-test in pass 2 instead.
+__global__ void __launch_bounds__(S2_WARPS * 32) neigh_lists_kernel(
     const NodePack *__restrict__ nodes, u32 I, u32 L, const Pack4 *__restrict__ SA, const u8 *__restrict__ real_flag,
     const u32 *__restrict__ real_prefix, const u32 *__restrict__ ranges, u32 cap, const u32 *__restrict__ nrange,
-    const u32 *__restrict__ ncand_arr, const u32 *__restrict__ mask_off, f64 Rker2, f64 h_tolerance,
-    u32 *__restrict__ masks, u32 *__restrict__ cnt_s) {
+    f64 Rker2, f64 h_tolerance, u64 list_cap, unsigned long long *__restrict__ cursor, u32 *__restrict__ cnt_s,
+    u32 *__restrict__ off_s, u32 *__restrict__ list_s) {
     __shared__ WarpScratch ws[S2_WARPS];
+    __shared__ WarpScratch2 ws2[S2_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const u32 lt   = (1u << lane) - 1u;
     u32 leaf = blockIdx.x * S2_WARPS + warp;
     if (leaf >= L)
         return;
     u32 nr = nrange[leaf];
     if (nr == 0)
         return;
-    WarpScratch &w = ws[warp];
+    WarpScratch &w   = ws[warp];
+    WarpScratch2 &w2 = ws2[warp];
     const u32 p0 = reinterpret_cast<const u32 *>(&nodes[I + leaf].rint)[2];
     const u32 p1 = reinterpret_cast<const u32 *>(&nodes[I + leaf].rint)[3];
     const u32 ncand  = load_ranges(w, ranges, leaf, cap, nr, lane);
     const u32 nchunk = (ncand + 31) >> 5;
     const u32 slot0  = real_prefix[p0];
-    const u32 nreal  = real_prefix[p1] - slot0;
-    const u32 mbase  = mask_off[leaf];
+    const bool cache_ranks = nchunk * 32 <= RANK_CACHE;
     u32 a_base = 0;
     for (u32 rb = p0; rb < p1; rb += 32) {
-        u32 r      = rb + lane;
-        bool va    = r < p1 && real_flag[r];
-        u32 bal    = __ballot_sync(0xffffffffu, va);
-        u32 nb     = __popc(bal);
+        u32 r   = rb + lane;
+        bool va = r < p1 && real_flag[r];
+        u32 bal = __ballot_sync(0xffffffffu, va);
+        u32 nb  = __popc(bal);
         if (nb == 0)
             continue;
+        const bool keep_ballots = nb * nchunk <= BALLOT_WORDS;
         __syncwarp();
         if (va) {
             Pack4 q    = ld4(SA + r);
             f64 rint_a = q.d * h_tolerance;
-            w.pa[__popc(bal & ((1u << lane) - 1u))] = Pack4{q.a, q.b, q.c, rint_a * rint_a * Rker2};
+            w.pa[__popc(bal & lt)] = Pack4{q.a, q.b, q.c, rint_a * rint_a * Rker2};
         }
         __syncwarp();
+        // ---- pass 1: ballots + counts
         u32 mycount = 0;
         for (u32 c = 0; c < nchunk; c++) {
             u32 j   = c * 32 + lane;
@@ -317,7 +333,9 @@ __global__ void __launch_bounds__(S2_WARPS * 32) neigh_mask_kernel(
             f64 bx = 0, by = 0, bz = 0, lim_b = 0;
             if (vb) {
                 u32 rank_b = cand_rank(w, nr, j);
-                Pack4 q    = ld4(SA + rank_b);
+                if (cache_ranks)
+                    w2.rankc[j] = rank_b;
+                Pack4 q = ld4(SA + rank_b);
                 bx = q.a, by = q.b, bz = q.c;
                 f64 rint_b = q.d * h_tolerance;
                 lim_b      = rint_b * rint_b * Rker2;
@@ -334,51 +352,68 @@ __global__ void __launch_bounds__(S2_WARPS * 32) neigh_mask_kernel(
                     mycount += __popc(m);
                 }
             }
-            if (lane < int(nb))
-                masks[mbase + u64(c) * nreal + a_base + lane] = mymask;
+            if (keep_ballots && lane < int(nb))
+                w2.ball[c * nb + lane] = mymask;
         }
-        if (lane < int(nb))
+        // ---- reserve the list space of this batch: exclusive prefix of the counts + one atomic
+        u32 inc = lane < int(nb) ? mycount : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            u32 t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o)
+                inc += t;
+        }
+        u32 total = __shfl_sync(0xffffffffu, inc, 31);
+        unsigned long long base = 0;
+        if (lane == 0)
+            base = atomicAdd(cursor, (unsigned long long) total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        u32 myoff = u32(base) + inc - (lane < int(nb) ? mycount : 0u);
+        if (lane < int(nb)) {
             cnt_s[slot0 + a_base + lane] = mycount;
+            off_s[slot0 + a_base + lane] = myoff;
+        }
         a_base += nb;
-    }
-}
-
-__global__ void __launch_bounds__(S2_WARPS * 32) neigh_fill_kernel(
-    const NodePack *__restrict__ nodes, u32 I, u32 L, const u8 *__restrict__ real_flag,
-    const u32 *__restrict__ real_prefix, const u32 *__restrict__ ranges, u32 cap, const u32 *__restrict__ nrange,
-    const u32 *__restrict__ mask_off, const u32 *__restrict__ masks, const u32 *__restrict__ off_s,
-    u32 *__restrict__ list_s) {
-    __shared__ WarpScratch ws[S2_WARPS];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    u32 leaf = blockIdx.x * S2_WARPS + warp;
-    if (leaf >= L)
-        return;
-    u32 nr = nrange[leaf];
-    if (nr == 0)
-        return;
-    WarpScratch &w = ws[warp];
-    const u32 p0 = reinterpret_cast<const u32 *>(&nodes[I + leaf].rint)[2];
-    const u32 p1 = reinterpret_cast<const u32 *>(&nodes[I + leaf].rint)[3];
-    const u32 ncand  = load_ranges(w, ranges, leaf, cap, nr, lane);
-    const u32 nchunk = (ncand + 31) >> 5;
-    const u32 slot0  = real_prefix[p0];
-    const u32 nreal  = real_prefix[p1] - slot0;
-    const u32 mbase  = mask_off[leaf];
-    const u32 lt     = (1u << lane) - 1u;
-    for (u32 a_base = 0; a_base < nreal; a_base += 32) {
-        u32 nb    = min(32u, nreal - a_base);
-        u32 myoff = lane < int(nb) ? off_s[slot0 + a_base + lane] : 0u;
+        if (base + total > list_cap)
+            continue; // the list array is too small: the host reads the cursor and runs the search again
+        __syncwarp();
+        // ---- pass 2: ordered fill
         for (u32 c = 0; c < nchunk; c++) {
             u32 j      = c * 32 + lane;
-            u32 rank_b = j < ncand ? cand_rank(w, nr, j) : 0u;
-            u32 mymask = lane < int(nb) ? masks[mbase + u64(c) * nreal + a_base + lane] : 0u;
-            for (u32 a = 0; a < nb; a++) {
-                u32 m    = __shfl_sync(0xffffffffu, mymask, a);
-                u32 base = __shfl_sync(0xffffffffu, myoff, a);
-                if ((m >> lane) & 1u)
-                    list_s[base + __popc(m & lt)] = rank_b;
+            bool vb    = j < ncand;
+            u32 rank_b = 0;
+            if (vb)
+                rank_b = cache_ranks ? w2.rankc[j] : cand_rank(w, nr, j);
+            if (keep_ballots) {
+                u32 mymask = lane < int(nb) ? w2.ball[c * nb + lane] : 0u;
+                for (u32 a = 0; a < nb; a++) {
+                    u32 m  = __shfl_sync(0xffffffffu, mymask, a);
+                    u32 bo = __shfl_sync(0xffffffffu, myoff, a);
+                    if ((m >> lane) & 1u)
+                        list_s[bo + __popc(m & lt)] = rank_b;
+                }
+                myoff += __popc(mymask);
+            } else { // ballots did not fit: test again
+                f64 bx = 0, by = 0, bz = 0, lim_b = 0;
+                if (vb) {
+                    Pack4 q = ld4(SA + rank_b);
+                    bx = q.a, by = q.b, bz = q.c;
+                    f64 rint_b = q.d * h_tolerance;
+                    lim_b      = rint_b * rint_b * Rker2;
+                }
+                for (u32 a = 0; a < nb; a++) {
+                    Pack4 pa = w.pa[a];
+                    f64 dx = pa.a - bx, dy = pa.b - by, dz = pa.c - bz;
+                    f64 rab2         = dx * dx + dy * dy + dz * dz;
+                    bool no_interact = rab2 > pa.d && rab2 > lim_b;
+                    u32 m            = __ballot_sync(0xffffffffu, vb && !no_interact);
+                    u32 bo           = __shfl_sync(0xffffffffu, myoff, a);
+                    if ((m >> lane) & 1u)
+                        list_s[bo + __popc(m & lt)] = rank_b;
+                    if (lane == int(a))
+                        myoff += __popc(m);
+                }
             }
-            myoff += __popc(mymask);
         }
     }
 }
@@ -393,51 +428,51 @@ void search_build(
     SB_COUNT_LAUNCH();
     sb.nrange.ensure(L, 1.1);
     sb.ncand.ensure(L, 1.1);
-    sb.mask_words.ensure(L, 1.1);
-    sb.mask_off.ensure(L, 1.1);
-    u32 *d_maxr = reinterpret_cast<u32 *>(sb.scalars.p + 2);
-    for (;;) {
-        if (sb.range_cap > RANGE_CAP_DEFAULT * 4)
-            throw std::runtime_error("neighbour search: more than 256 candidate rank ranges for one leaf");
-        sb.ranges.ensure(size_t(L) * sb.range_cap * 2, 1.1);
-        SB_CUDA_CHECK(cudaMemsetAsync(d_maxr, 0, sizeof(u64), s));
-        leaf_ranges_kernel<<<grid_for(L, 128), 128, 0, s>>>(
-            sb.nodes.p, I, L, sb.real_prefix.p, Rkern, sb.range_cap, sb.ranges.p, sb.nrange.p, sb.ncand.p,
-            sb.mask_words.p, d_maxr);
-        SB_COUNT_LAUNCH();
-        exclusive_scan<u32>(s, sb.mask_words.p, sb.mask_off.p, L, sb.scan_tmp, sb.scalars.p + 3);
-        SB_CUDA_CHECK(cudaMemcpyAsync(sb.h_scalars.p + 2, sb.scalars.p + 2, 2 * sizeof(u64), cudaMemcpyDeviceToHost, s));
-        SB_CUDA_CHECK(cudaStreamSynchronize(s));
-        u32 maxr = u32(sb.h_scalars.p[2] & 0xffffffffull);
-        if (maxr <= sb.range_cap)
-            break;
-        while (sb.range_cap < maxr)
-            sb.range_cap *= 2; // rare: a leaf sees more merged ranges than the slot holds; redo wider
-    }
-    u64 mask_total = sb.h_scalars.p[3];
-    if (mask_total > 0xFFFFFFFFull)
-        throw std::overflow_error("neighbour search: ballot storage overflows u32 offsets (use smaller patches)");
-    sb.masks.ensure(mask_total, 1.1);
     sb.cnt_s.ensure(sb.N, 1.1);
     sb.off_s.ensure(sb.N, 1.1);
     const f64 Rker2 = Rkern * Rkern;
-    neigh_mask_kernel<<<grid_for(L, S2_WARPS), S2_WARPS * 32, 0, s>>>(
-        sb.nodes.p, I, L, sb.SA.p, sb.real_flag.p, sb.real_prefix.p, sb.ranges.p, sb.range_cap, sb.nrange.p,
-        sb.ncand.p, sb.mask_off.p, Rker2, h_tolerance, sb.masks.p, sb.cnt_s.p);
-    SB_COUNT_LAUNCH();
-    exclusive_scan<u32>(s, sb.cnt_s.p, sb.off_s.p, sb.N, sb.scan_tmp, sb.scalars.p + 4);
-    SB_CUDA_CHECK(cudaMemcpyAsync(sb.h_scalars.p + 4, sb.scalars.p + 4, sizeof(u64), cudaMemcpyDeviceToHost, s));
-    SB_CUDA_CHECK(cudaStreamSynchronize(s));
-    sb.K = sb.h_scalars.p[4];
-    if (sb.K > 0xFFFFFFFFull)
-        throw std::overflow_error(
-            "neighbour count overflows u32 (sum_neigh_cnt is u32 in the reference, TreeTraversal.hpp:378): "
-            "use more / smaller patches");
-    sb.list_s.ensure(sb.K, 1.05);
-    neigh_fill_kernel<<<grid_for(L, S2_WARPS), S2_WARPS * 32, 0, s>>>(
-        sb.nodes.p, I, L, sb.real_flag.p, sb.real_prefix.p, sb.ranges.p, sb.range_cap, sb.nrange.p, sb.mask_off.p,
-        sb.masks.p, sb.off_s.p, sb.list_s.p);
-    SB_COUNT_LAUNCH();
+    // list capacity: what the previous search of this patch needed (+ slack), ~96 entries per particle the
+    // first time.  ONE host synchronisation per search: it reads the list cursor (= K) and the largest
+    // range count; if either ran past its capacity the exact need is known and the search is repeated.
+    if (sb.list_s.cap == 0)
+        sb.list_s.ensure(size_t(sb.N) * 96 + 1024);
+    u32 *d_maxr                  = reinterpret_cast<u32 *>(sb.scalars.p + 2);
+    unsigned long long *d_cursor = reinterpret_cast<unsigned long long *>(sb.scalars.p + 3);
+    for (int attempt = 0;; attempt++) {
+        if (sb.range_cap > RANGE_CAP_DEFAULT * 4)
+            throw std::runtime_error("neighbour search: more than 256 candidate rank ranges for one leaf");
+        sb.ranges.ensure(size_t(L) * sb.range_cap * 2, 1.1);
+        SB_CUDA_CHECK(cudaMemsetAsync(sb.scalars.p + 2, 0, 2 * sizeof(u64), s));
+        leaf_ranges_kernel<<<grid_for(L, 128), 128, 0, s>>>(
+            sb.nodes.p, I, L, sb.real_prefix.p, Rkern, sb.range_cap, sb.ranges.p, sb.nrange.p, sb.ncand.p, d_maxr);
+        SB_COUNT_LAUNCH();
+        neigh_lists_kernel<<<grid_for(L, S2_WARPS), S2_WARPS * 32, 0, s>>>(
+            sb.nodes.p, I, L, sb.SA.p, sb.real_flag.p, sb.real_prefix.p, sb.ranges.p, sb.range_cap, sb.nrange.p, Rker2,
+            h_tolerance, u64(sb.list_s.cap), d_cursor, sb.cnt_s.p, sb.off_s.p, sb.list_s.p);
+        SB_COUNT_LAUNCH();
+        SB_CUDA_CHECK(cudaMemcpyAsync(sb.h_scalars.p + 2, sb.scalars.p + 2, 2 * sizeof(u64), cudaMemcpyDeviceToHost, s));
+        SB_CUDA_CHECK(cudaStreamSynchronize(s));
+        u32 maxr = u32(sb.h_scalars.p[2] & 0xffffffffull);
+        sb.K     = sb.h_scalars.p[3];
+        bool redo = false;
+        if (maxr > sb.range_cap) { // rare: a leaf sees more merged ranges than its slot holds
+            while (sb.range_cap < maxr)
+                sb.range_cap *= 2;
+            redo = true;
+        } else if (sb.K > 0xFFFFFFFFull) {
+            throw std::overflow_error(
+                "neighbour count overflows u32 (sum_neigh_cnt is u32 in the reference, TreeTraversal.hpp:378): "
+                "use more / smaller patches");
+        }
+        if (sb.K > sb.list_s.cap && sb.K <= 0xFFFFFFFFull) {
+            sb.list_s.ensure(sb.K, 1.1);
+            redo = true;
+        }
+        if (!redo)
+            break;
+        if (attempt >= 3)
+            throw std::runtime_error("neighbour search: capacity retry failed");
+    }
     SB_LAUNCH_CHECK();
 }
 

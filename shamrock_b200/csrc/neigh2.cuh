@@ -29,10 +29,9 @@ struct SearchBuffers {
     DevBuf<u32> real_prefix; // [M+1] exclusive scan of real_flag over ranks (slot of a real rank)
     DevBuf<u32> slot_rank;   // [N] rank of slot k
     DevBuf<u32> ranges;      // [L * cap * 2]
-    DevBuf<u32> nrange, ncand, mask_words, mask_off; // [L]
-    DevBuf<u32> masks;
+    DevBuf<u32> nrange, ncand; // [L]
     DevBuf<u32> cnt_s, off_s; // [N]
-    DevBuf<u32> list_s;       // [K] ranks, ascending inside each list
+    DevBuf<u32> list_s;       // [K] ranks, ascending inside each list; lists of one leaf contiguous
     DevBuf<u32> scan_tmp;
     DevBuf<u64> scalars;
     PinnedBuf<u64> h_scalars;

@@ -521,40 +521,69 @@ void Model::build_ghost_cache() {
     std::vector<IfaceCand> cand
         = plan_interfaces(std::vector<PatchBox>(patches.begin(), patches.end()), box_min, box_max,
                           cfg.bc == SHAMB200_BC_PERIODIC, interactR, pcount);
-    // counts of every candidate with a local sender: one kernel per sender patch
+    // ghost selection, pass A: every local sender classifies its particles against all of its cut boxes at
+    // once (64 per launch) — counts per interface, block offsets kept for pass B
     std::vector<u64> counts(cand.size(), 0);
+    std::vector<std::vector<size_t>> mine(np);
+    for (size_t q = 0; q < cand.size(); q++)
+        mine[cand[q].sender].push_back(q);
     for (size_t sd = 0; sd < np; sd++) {
-        if (!is_local(patches[sd]) || !patches[sd].f.n)
+        PatchD &S = patches[sd];
+        if (!is_local(S) || !S.f.n || mine[sd].empty())
             continue;
-        std::vector<size_t> mine;
-        for (size_t q = 0; q < cand.size(); q++)
-            if (cand[q].sender == sd)
-                mine.push_back(q);
-        if (mine.empty())
-            continue;
-        std::vector<f64> hb(mine.size() * 6);
-        for (size_t j = 0; j < mine.size(); j++)
+        const u32 n = S.f.n, nblocks = grid_for(n, 256);
+        const size_t nch = (mine[sd].size() + 63) / 64;
+        std::vector<f64> hb(nch * 64 * 6, 0.);
+        for (size_t j = 0; j < mine[sd].size(); j++)
             for (int d = 0; d < 3; d++) {
-                hb[6 * j + d]     = cand[mine[j]].cut_lo[d];
-                hb[6 * j + 3 + d] = cand[mine[j]].cut_hi[d];
+                hb[6 * j + d]     = cand[mine[sd][j]].cut_lo[d];
+                hb[6 * j + 3 + d] = cand[mine[sd][j]].cut_hi[d];
             }
         field_tmp.ensure(hb.size());
-        box_counts.ensure(mine.size());
         SB_CUDA_CHECK(cudaMemcpyAsync(field_tmp.p, hb.data(), hb.size() * sizeof(f64), cudaMemcpyHostToDevice, s()));
-        SB_CUDA_CHECK(cudaMemsetAsync(box_counts.p, 0, mine.size() * sizeof(u32), s()));
-        u32 n       = patches[sd].f.n;
-        unsigned nb = (unsigned) std::min<u64>(u64(kNumSM) * 8, (u64(n) + 255) / 256);
-        count_in_boxes_kernel<<<nb, 256, mine.size() * sizeof(u32), s()>>>(
-            n, patches[sd].f.xyz.p, u32(mine.size()), field_tmp.p, box_counts.p);
-        SB_COUNT_LAUNCH();
-        std::vector<u32> hc(mine.size());
-        SB_CUDA_CHECK(cudaMemcpyAsync(hc.data(), box_counts.p, mine.size() * sizeof(u32), cudaMemcpyDeviceToHost, s()));
+        S.st.gmask.ensure(size_t(n) * nch, 1.1);
+        S.st.gblock.ensure(size_t(nblocks) * 64 * nch, 1.1);
+        S.st.gtotals.ensure(64 * nch);
+        for (size_t ch = 0; ch < nch; ch++) {
+            u32 nbox = u32(std::min<size_t>(64, mine[sd].size() - ch * 64));
+            ghost_select_count(
+                s(), n, S.f.xyz.p, nbox, field_tmp.p + ch * 64 * 6, S.st.gmask.p + ch * n,
+                S.st.gblock.p + ch * 64 * size_t(nblocks), S.st.gtotals.p + ch * 64);
+        }
+        std::vector<u32> hc(64 * nch);
+        SB_CUDA_CHECK(cudaMemcpyAsync(hc.data(), S.st.gtotals.p, hc.size() * sizeof(u32), cudaMemcpyDeviceToHost, s()));
         SB_CUDA_CHECK(cudaStreamSynchronize(s()));
-        for (size_t j = 0; j < mine.size(); j++)
-            counts[mine[j]] = hc[j];
+        for (size_t j = 0; j < mine[sd].size(); j++)
+            counts[mine[sd][j]] = hc[j];
     }
     comm_allreduce_host_u64(*this, counts.data(), counts.size(), 1);
-    // keep the non-empty interfaces ("prevent sending empty patches"), build their id lists
+    // pass B: ids of every interface with a local sender (ascending inside an interface)
+    std::vector<u32 *> ids_of(cand.size(), nullptr);
+    for (size_t sd = 0; sd < np; sd++) {
+        PatchD &S = patches[sd];
+        if (!is_local(S) || !S.f.n || mine[sd].empty())
+            continue;
+        const u32 n = S.f.n, nblocks = grid_for(n, 256);
+        const size_t nch = (mine[sd].size() + 63) / 64;
+        std::vector<u64> base(64 * nch, 0);
+        u64 run = 0;
+        for (size_t j = 0; j < mine[sd].size(); j++) {
+            base[j] = run;
+            run += counts[mine[sd][j]];
+        }
+        S.st.ids_pool.ensure(run, 1.1);
+        S.st.gbase.ensure(base.size());
+        SB_CUDA_CHECK(cudaMemcpyAsync(S.st.gbase.p, base.data(), base.size() * sizeof(u64), cudaMemcpyHostToDevice, s()));
+        for (size_t ch = 0; ch < nch; ch++) {
+            u32 nbox = u32(std::min<size_t>(64, mine[sd].size() - ch * 64));
+            ghost_select_scatter(
+                s(), n, S.st.gmask.p + ch * n, nbox, S.st.gblock.p + ch * 64 * size_t(nblocks), S.st.gbase.p + ch * 64,
+                S.st.ids_pool.p);
+        }
+        for (size_t j = 0; j < mine[sd].size(); j++)
+            ids_of[mine[sd][j]] = S.st.ids_pool.p + base[j];
+    }
+    // keep the non-empty interfaces ("prevent sending empty patches")
     ifaces.clear();
     std::vector<u32> ghost_run(np, 0);
     for (size_t q = 0; q < cand.size(); q++) {
@@ -572,15 +601,7 @@ void Model::build_ghost_cache() {
         itf.count   = u32(counts[q]);
         itf.dst_off = ghost_run[itf.receiver];
         ghost_run[itf.receiver] += itf.count;
-        PatchD &S = patches[itf.sender];
-        if (is_local(S)) {
-            flag.ensure(S.f.n);
-            pos.ensure(S.f.n);
-            flag_in_box(s(), S.f.n, S.f.xyz.p, itf.cut_lo, itf.cut_hi, flag.p);
-            exclusive_scan<u8>(s(), flag.p, pos.p, S.f.n, scan_tmp, red.p + 5);
-            itf.ids.ensure(itf.count);
-            scatter_ids(s(), S.f.n, flag.p, pos.p, itf.ids.p);
-        }
+        itf.ids = ids_of[q];
         ifaces.push_back(std::move(itf));
     }
     // staging offsets of the interfaces this rank sends to another rank
@@ -611,10 +632,10 @@ void Model::merge_position_ghost() {
         PatchD &R = patches[itf.receiver];
         PatchD &S = patches[itf.sender];
         if (is_local(R) && is_local(S)) {
-            ghost_xyzh(s(), itf.count, itf.ids.p, S.f.xyz.p, S.f.hpart.p, itf.offset, R.st.A.p + R.st.n + itf.dst_off);
+            ghost_xyzh(s(), itf.count, itf.ids, S.f.xyz.p, S.f.hpart.p, itf.offset, R.st.A.p + R.st.n + itf.dst_off);
         } else if (is_local(S)) { // C1: positions + h of the ghosts, 32 B each, straight from the gather
             Pack4 *stg = send_stage.p + itf.stage_off;
-            ghost_xyzh(s(), itf.count, itf.ids.p, S.f.xyz.p, S.f.hpart.p, itf.offset, stg);
+            ghost_xyzh(s(), itf.count, itf.ids, S.f.xyz.p, S.f.hpart.p, itf.offset, stg);
             comm_send(*this, stg, size_t(itf.count) * sizeof(Pack4), R.owner);
         } else if (is_local(R)) {
             comm_recv(*this, R.st.A.p + R.st.n + itf.dst_off, size_t(itf.count) * sizeof(Pack4), S.owner);
@@ -785,15 +806,15 @@ void Model::communicate_merge_ghosts_fields() {
         if (is_local(R) && is_local(S)) {
             u32 o = R.st.n + itf.dst_off;
             pack_fields(
-                s(), itf.count, itf.ids.p, S.f.hpart.p, S.f.vxyz.p, S.f.uint_.p, S.st.omega.p,
+                s(), itf.count, itf.ids, S.f.hpart.p, S.f.vxyz.p, S.f.uint_.p, S.st.omega.p,
                 has_a ? S.f.axyz.p : nullptr, R.st.srch.SA.p, R.st.SB.p, R.st.SC.p, has_a ? R.st.SD.p : nullptr,
                 R.st.srch.inv_map.p + o);
         } else if (is_local(S)) {
             Pack4 *sA = send_stage.p + itf.stage_off * nblk;
             Pack4 *sB = sA + itf.count, *sC = sB + itf.count, *sD = has_a ? sC + itf.count : nullptr;
-            ghost_xyzh(s(), itf.count, itf.ids.p, S.f.xyz.p, S.f.hpart.p, itf.offset, sA);
+            ghost_xyzh(s(), itf.count, itf.ids, S.f.xyz.p, S.f.hpart.p, itf.offset, sA);
             pack_fields(
-                s(), itf.count, itf.ids.p, S.f.hpart.p, S.f.vxyz.p, S.f.uint_.p, S.st.omega.p,
+                s(), itf.count, itf.ids, S.f.hpart.p, S.f.vxyz.p, S.f.uint_.p, S.st.omega.p,
                 has_a ? S.f.axyz.p : nullptr, sA, sB, sC, sD);
             comm_send(*this, sA, bytes * nblk, R.owner);
         } else if (is_local(R)) {
@@ -836,9 +857,9 @@ void Model::exchange_alpha_ghosts() {
         PatchD &R = patches[itf.receiver];
         PatchD &S = patches[itf.sender];
         if (is_local(R) && is_local(S)) {
-            pack_alpha(s(), itf.count, itf.ids.p, S.st.alpha_updated.p, R.st.SC.p, R.st.srch.inv_map.p + R.st.n + itf.dst_off);
+            pack_alpha(s(), itf.count, itf.ids, S.st.alpha_updated.p, R.st.SC.p, R.st.srch.inv_map.p + R.st.n + itf.dst_off);
         } else if (is_local(S)) {
-            gather_field(s(), itf.count, 1, itf.ids.p, S.st.alpha_updated.p, send_stage_f.p + itf.stage_off);
+            gather_field(s(), itf.count, 1, itf.ids, S.st.alpha_updated.p, send_stage_f.p + itf.stage_off);
             comm_send(*this, send_stage_f.p + itf.stage_off, size_t(itf.count) * sizeof(f64), R.owner);
         } else if (is_local(R)) {
             comm_recv(*this, recv_stage_f.p + roff, size_t(itf.count) * sizeof(f64), S.owner);

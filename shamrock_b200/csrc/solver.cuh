@@ -51,7 +51,7 @@ struct Iface {
     u32 count   = 0;
     u32 dst_off = 0; ///< offset inside the receiver's ghost range
     size_t stage_off = 0; ///< offset (objects) in the send staging when the receiver is on another rank
-    DevBuf<u32> ids;
+    u32 *ids = nullptr;   ///< ascending sender-local ids (inside the sender patch's ids pool; local senders only)
 };
 
 struct PatchStep {
@@ -64,6 +64,9 @@ struct PatchStep {
     SearchBuffers srch;
     DevBuf<f64> omega, alpha_updated, vsig, cfl_dt, eps, h_old, a_old, du_old;
     DevBuf<f64> mh_snapshot; ///< pre-iteration merged h (keep_step_data only)
+    // ghost selection scratch of this patch as a sender (stream_kernels.cu: ghost_select_*)
+    DevBuf<u64> gmask, gbase;
+    DevBuf<u32> gblock, gtotals, ids_pool;
 };
 
 struct PatchD : PatchBox {

@@ -226,6 +226,154 @@ void scatter_ids(cudaStream_t s, u32 n, const u8 *flag, const u32 *pos, u32 *ids
     SB_LAUNCH_CHECK();
 }
 
+// ---- ghost selection: all interfaces of one sender patch in two passes ---------------------------------
+// replaces one get_ids_where (flag + stream compaction, BasicSPHGhosts.cpp:526-531) PER INTERFACE: pass A
+// classifies every particle against up to 64 cut boxes at once (bit mask) and counts per 256-particle
+// block, a scan per interface turns the block counts into offsets, pass B writes the ids — ascending
+// inside every interface, as the reference's stream compaction does.
+constexpr int GS_THREADS = 256;
+
+__global__ void __launch_bounds__(GS_THREADS) ghost_mask_kernel(
+    u32 n, const f64 *__restrict__ xyz, u32 nbox, const f64 *__restrict__ boxes, u64 *__restrict__ mask,
+    u32 nblocks, u32 *__restrict__ block_counts) {
+    __shared__ f64 sbox[64 * 6];
+    __shared__ u32 scnt[64];
+    for (u32 j = threadIdx.x; j < nbox * 6; j += GS_THREADS)
+        sbox[j] = boxes[j];
+    if (threadIdx.x < 64)
+        scnt[threadIdx.x] = 0;
+    __syncthreads();
+    u32 i  = blockIdx.x * GS_THREADS + threadIdx.x;
+    u64 mk = 0;
+    if (i < n) {
+        f64 x = xyz[3 * u64(i)], y = xyz[3 * u64(i) + 1], z = xyz[3 * u64(i) + 2];
+        for (u32 b = 0; b < nbox; b++) {
+            const f64 *q = sbox + 6 * b;
+            if (q[0] <= x && x < q[3] && q[1] <= y && y < q[4] && q[2] <= z && z < q[5])
+                mk |= (1ull << b);
+        }
+        mask[i] = mk;
+    }
+    u32 lo = __reduce_or_sync(0xffffffffu, u32(mk)), hi = __reduce_or_sync(0xffffffffu, u32(mk >> 32));
+    u64 any = (u64(hi) << 32) | lo;
+    while (any) {
+        int b    = __ffsll((long long) any) - 1;
+        any &= any - 1;
+        u32 bal = __ballot_sync(0xffffffffu, (mk >> b) & 1ull);
+        if ((threadIdx.x & 31) == 0)
+            atomicAdd(&scnt[b], __popc(bal));
+    }
+    __syncthreads();
+    if (threadIdx.x < nbox && scnt[threadIdx.x])
+        block_counts[u64(threadIdx.x) * nblocks + blockIdx.x] = scnt[threadIdx.x];
+}
+
+/// one CTA per interface: exclusive scan of its block counts (in place), total -> totals[b]
+__global__ void __launch_bounds__(1024) ghost_scan_kernel(u32 *block_counts, u32 nblocks, u32 *totals) {
+    __shared__ u32 warp_s[32];
+    __shared__ u32 carry_s;
+    u32 *c = block_counts + u64(blockIdx.x) * nblocks;
+    if (threadIdx.x == 0)
+        carry_s = 0;
+    __syncthreads();
+    for (u32 base = 0; base < nblocks; base += 1024) {
+        u32 i   = base + threadIdx.x;
+        u32 v   = i < nblocks ? c[i] : 0u;
+        u32 inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            u32 t = __shfl_up_sync(0xffffffffu, inc, o);
+            if ((threadIdx.x & 31) >= o)
+                inc += t;
+        }
+        if ((threadIdx.x & 31) == 31)
+            warp_s[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            u32 w = warp_s[threadIdx.x], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                u32 t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (threadIdx.x >= o)
+                    wi += t;
+            }
+            warp_s[threadIdx.x] = wi - w;
+        }
+        __syncthreads();
+        u32 excl = carry_s + warp_s[threadIdx.x >> 5] + (inc - v);
+        if (i < nblocks)
+            c[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023)
+            carry_s = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+        totals[blockIdx.x] = carry_s;
+}
+
+/// pass B: ids_pool[base[b] + offset] = i for every particle i inside box b, ascending in i
+__global__ void __launch_bounds__(GS_THREADS) ghost_scatter_kernel(
+    u32 n, const u64 *__restrict__ mask, u32 nbox, u32 nblocks, const u32 *__restrict__ block_offsets,
+    const u64 *__restrict__ base, u32 *__restrict__ ids_pool) {
+    __shared__ u32 wcnt[GS_THREADS / 32][64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    u32 i  = blockIdx.x * GS_THREADS + threadIdx.x;
+    u64 mk = i < n ? mask[i] : 0ull;
+    u32 lo = __reduce_or_sync(0xffffffffu, u32(mk)), hi = __reduce_or_sync(0xffffffffu, u32(mk >> 32));
+    u64 anyw = (u64(hi) << 32) | lo;
+    if (__syncthreads_or(anyw != 0) == 0)
+        return; // no ghost in this block
+    for (int b = lane; b < 64; b += 32)
+        wcnt[warp][b] = 0;
+    __syncwarp();
+    u64 any = anyw;
+    while (any) {
+        int b = __ffsll((long long) any) - 1;
+        any &= any - 1;
+        u32 bal = __ballot_sync(0xffffffffu, (mk >> b) & 1ull);
+        if (lane == 0)
+            wcnt[warp][b] = __popc(bal);
+    }
+    __syncthreads();
+    any = anyw;
+    while (any) {
+        int b = __ffsll((long long) any) - 1;
+        any &= any - 1;
+        u32 bal = __ballot_sync(0xffffffffu, (mk >> b) & 1ull);
+        if ((mk >> b) & 1ull) {
+            u32 off = block_offsets[u64(b) * nblocks + blockIdx.x];
+            for (int w = 0; w < warp; w++)
+                off += wcnt[w][b];
+            ids_pool[base[b] + off + __popc(bal & ((1u << lane) - 1u))] = i;
+        }
+    }
+}
+
+void ghost_select_count(
+    cudaStream_t s, u32 n, const f64 *xyz, u32 nbox, const f64 *d_boxes, u64 *mask, u32 *block_counts, u32 *d_totals) {
+    if (!n || !nbox)
+        return;
+    if (nbox > 64)
+        throw std::invalid_argument("ghost_select: at most 64 boxes per pass");
+    u32 nblocks = grid_for(n, GS_THREADS);
+    SB_CUDA_CHECK(cudaMemsetAsync(block_counts, 0, size_t(nbox) * nblocks * sizeof(u32), s));
+    ghost_mask_kernel<<<nblocks, GS_THREADS, 0, s>>>(n, xyz, nbox, d_boxes, mask, nblocks, block_counts);
+    SB_COUNT_LAUNCH();
+    ghost_scan_kernel<<<nbox, 1024, 0, s>>>(block_counts, nblocks, d_totals);
+    SB_COUNT_LAUNCH();
+    SB_LAUNCH_CHECK();
+}
+void ghost_select_scatter(
+    cudaStream_t s, u32 n, const u64 *mask, u32 nbox, const u32 *block_offsets, const u64 *d_base, u32 *ids_pool) {
+    if (!n || !nbox)
+        return;
+    u32 nblocks = grid_for(n, GS_THREADS);
+    ghost_scatter_kernel<<<nblocks, GS_THREADS, 0, s>>>(n, mask, nbox, nblocks, block_offsets, d_base, ids_pool);
+    SB_COUNT_LAUNCH();
+    SB_LAUNCH_CHECK();
+}
+
 // ---- gathers ------------------------------------------------------------------------------------------
 /// dst[k*nvar + c] = src[ids[k]*nvar + c]   (append_subset_to / keep_ids)
 __global__ void __launch_bounds__(256) gather_field_kernel(u32 cnt, int nvar, const u32 *__restrict__ ids, const f64 *__restrict__ src, f64 *__restrict__ dst) {

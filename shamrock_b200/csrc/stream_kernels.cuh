@@ -13,6 +13,11 @@ void flag_sphere(cudaStream_t s, u32 n, const f64 *xyz, const f64 c[3], f64 rad,
 void patch_owner(cudaStream_t s, u32 n, const f64 *xyz, u32 npatch, const f64 *d_boxes, u32 self, u8 *stay_flag, u32 *owner);
 void flag_equal(cudaStream_t s, u32 n, const u32 *v, u32 val, u8 *flag);
 void scatter_ids(cudaStream_t s, u32 n, const u8 *flag, const u32 *pos, u32 *ids);
+/// ghost selection of one sender patch against up to 64 cut boxes (d_boxes: nbox*6 doubles, [lo,hi))
+void ghost_select_count(cudaStream_t s, u32 n, const f64 *xyz, u32 nbox, const f64 *d_boxes, u64 *mask, u32 *block_counts,
+                        u32 *d_totals);
+void ghost_select_scatter(cudaStream_t s, u32 n, const u64 *mask, u32 nbox, const u32 *block_offsets, const u64 *d_base,
+                          u32 *ids_pool);
 void gather_field(cudaStream_t s, u32 cnt, int nvar, const u32 *ids, const f64 *src, f64 *dst);
 void pack_xyzh(cudaStream_t s, u32 n, const f64 *xyz, const f64 *h, Pack4 *A);
 void ghost_xyzh(cudaStream_t s, u32 cnt, const u32 *ids, const f64 *xyz, const f64 *h, const f64 off[3], Pack4 *A_dst);

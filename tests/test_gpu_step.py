@@ -47,13 +47,13 @@ def close(a, b, rtol, floor=0.0):
 
 
 def term_floors(o, ip):
-    """1e-4 x the size of one pair term of the SPH sums: with rtol = 1e-10 this floor tolerates 1e-14 of a
-    term, i.e. the round-off of ~60 cancelling terms (perfect lattice, v = 0: curl v is pure round-off)"""
+    """natural scale of the derived fields (fast fp mode only): an input known to 1e-10 (v from the previous
+    step's forces) cannot give div/curl v better than 1e-10 |v|/h, whatever the cancellation inside the sum
+    (perfect lattice + spherical blast: curl v is 1e-3 of |v|/h)."""
     v, a, h = np.abs(o.get(ip, "vxyz")).max(), np.abs(o.get(ip, "axyz")).max(), o.get(ip, "hpart").min()
     cs2 = (o.get(ip, "step.soundspeed") ** 2).max()
-    dv = 1e-4 * v / h
-    return {"divv": dv, "curlv": dv, "dtdivv": 1e-4 * (a / h + (v / h) ** 2), "axyz": 1e-4 * cs2 / h,
-            "duint": 1e-4 * cs2 * max(v, np.sqrt(cs2)) / h, "step.g_a": 1e-4 * cs2 / h}
+    return {"divv": v / h, "curlv": v / h, "dtdivv": a / h + (v / h) ** 2, "axyz": cs2 / h,
+            "duint": cs2 * max(v, np.sqrt(cs2)) / h, "step.g_a": cs2 / h}
 
 
 def compare(m, o, sc, rtol, names_extra=(), ints_exact=True):

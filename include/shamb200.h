@@ -227,6 +227,33 @@ int64_t shamb200_model_get(shamb200_model *m, uint32_t ip, const char *name, voi
 int shamb200_model_set_field(shamb200_model *m, uint32_t ip, const char *name, const double *in, uint64_t count);
 /* Solver::evolve_once (Solver.cpp:1942).  Runs one full step; synchronises at the end. */
 int shamb200_model_evolve_once(shamb200_model *m);
+/* Solver::evolve_once on HOST-resident patch data: the call a host code that keeps its PatchDataLayer
+ * fields in its own memory makes once per step (the reference's fields live in sham::DeviceBuffer /
+ * PatchDataField, shamrock/include/shamrock/patch/PatchDataField.hpp; main layout SolverConfig.cpp:24-121).
+ * `in`: the step's inputs (xyz vxyz axyz hpart uint duint, alpha_AV for MM97/CD10); the other main-layout
+ * fields are outputs of the step and are never read (NULL allowed everywhere in `in` = keep the device
+ * copy).  `out`: every non-NULL pointer receives the field after the step; out->n is the capacity
+ * (objects) of the out arrays on entry and the object count of the patch on return.
+ * Copies run on two copy streams and overlap with the kernels: the positions are drifted and the tree /
+ * neighbour cache built while uint, duint, alpha_AV are still uploading; xyz, hpart, axyz_ext go back
+ * during the CD10 operators, divv curlv dtdivv alpha_AV during the force loop; only vxyz uint axyz duint
+ * soundspeed follow the corrector.  Host memory should be page-locked (shamb200_host_register) for the
+ * copies to be asynchronous.  One local patch per call (`ip`); a model with several local patches,
+ * kill spheres, a point mass or free boundaries takes the same call without the overlap. */
+typedef struct shamb200_host_patchdata {
+    uint64_t n;
+    double *xyz, *vxyz, *axyz, *axyz_ext; /* 3 doubles per object */
+    double *hpart, *uint_, *duint, *alpha_AV, *divv, *dtdivv;
+    double *curlv; /* 3 doubles per object */
+    double *soundspeed;
+} shamb200_host_patchdata;
+int shamb200_model_evolve_once_host(shamb200_model *m, uint32_t ip, const shamb200_host_patchdata *in,
+                                    shamb200_host_patchdata *out);
+/* page-lock / unlock caller memory (cudaHostRegister) so that the copies above are asynchronous */
+int shamb200_host_register(void *p, uint64_t bytes);
+int shamb200_host_unregister(void *p);
+/* bytes moved by the last shamb200_model_evolve_once_host: out[0] host->device, out[1] device->host */
+int shamb200_model_host_traffic(shamb200_model *m, uint64_t out[2]);
 /* state: {time, next dt, cfl_multiplier, eps_v, h_subcycles, h_iters_last, corrector_iter,
  *         npart(global), t_step seconds (host wall), rate(part/s, this rank), K (local neighbour count)} */
 int shamb200_model_state(shamb200_model *m, double out[12]);

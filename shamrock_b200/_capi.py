@@ -74,11 +74,21 @@ SYMBOLS = [
     "shamb200_model_set_config", "shamb200_model_set_box", "shamb200_nccl_unique_id",
     "shamb200_model_init_comm", "shamb200_model_push_particles", "shamb200_model_patch_count",
     "shamb200_model_patch_is_local", "shamb200_model_patch_size", "shamb200_model_get",
-    "shamb200_model_set_field", "shamb200_model_evolve_once", "shamb200_model_state",
+    "shamb200_model_set_field", "shamb200_model_evolve_once", "shamb200_model_evolve_once_host",
+    "shamb200_host_register", "shamb200_host_unregister", "shamb200_model_host_traffic", "shamb200_model_state",
     "shamb200_model_set_next_dt", "shamb200_model_set_time", "shamb200_model_set_cfl_multiplier",
     "shamb200_model_stage_times", "shamb200_plan_patch_grid", "shamb200_plan_interfaces",
     "shamb200_microbench",
 ]
+
+HOST_FIELDS = (("xyz", 3), ("vxyz", 3), ("axyz", 3), ("axyz_ext", 3), ("hpart", 1), ("uint", 1), ("duint", 1),
+               ("alpha_AV", 1), ("divv", 1), ("dtdivv", 1), ("curlv", 3), ("soundspeed", 1))
+
+
+class HostPatchData(C.Structure):
+    """shamb200_host_patchdata: host pointers of the main-layout fields of one patch"""
+    _fields_ = [("n", C.c_uint64)] + [(nm if nm != "uint" else "uint_", C.c_void_p) for nm, _ in HOST_FIELDS]
+
 
 _lib = None
 
@@ -298,6 +308,22 @@ class Model:
     def evolve_once(self):
         check(lib().shamb200_model_evolve_once(self.h))
         return self.state()
+
+    def evolve_once_host(self, ip, n, inputs, outputs):
+        """Solver::evolve_once on host-resident patch data.  `inputs` / `outputs`: dict field name ->
+        host address (int, page-locked memory) of n * nvar doubles; missing names are not copied."""
+        hin, hout = HostPatchData(), HostPatchData()
+        hin.n = hout.n = int(n)
+        for h, d in ((hin, inputs), (hout, outputs)):
+            for nm, addr in d.items():
+                setattr(h, nm if nm != "uint" else "uint_", C.c_void_p(int(addr)))
+        check(lib().shamb200_model_evolve_once_host(self.h, C.c_uint32(ip), C.byref(hin), C.byref(hout)))
+        return int(hout.n)
+
+    def host_traffic(self):
+        o = (C.c_uint64 * 2)()
+        check(lib().shamb200_model_host_traffic(self.h, o))
+        return int(o[0]), int(o[1])
 
     def state(self):
         o = (C.c_double * 12)()

@@ -334,6 +334,22 @@ int shamb200_model_set_field(shamb200_model *m, uint32_t ip, const char *name, c
 int shamb200_model_evolve_once(shamb200_model *m) {
     return guard([&] { m->m.evolve_once(); });
 }
+int shamb200_model_evolve_once_host(shamb200_model *m, uint32_t ip, const shamb200_host_patchdata *in,
+                                    shamb200_host_patchdata *out) {
+    return guard([&] { m->m.evolve_once_host(ip, in, out); });
+}
+int shamb200_host_register(void *p, uint64_t bytes) {
+    return guard([&] { SB_CUDA_CHECK(cudaHostRegister(p, size_t(bytes), cudaHostRegisterDefault)); });
+}
+int shamb200_host_unregister(void *p) {
+    return guard([&] { SB_CUDA_CHECK(cudaHostUnregister(p)); });
+}
+int shamb200_model_host_traffic(shamb200_model *m, uint64_t out[2]) {
+    return guard([&] {
+        out[0] = m->m.pipe.bytes_h2d;
+        out[1] = m->m.pipe.bytes_d2h;
+    });
+}
 int shamb200_model_state(shamb200_model *m, double out[12]) {
     return guard([&] {
         Model &M = m->m;

@@ -895,9 +895,15 @@ void Model::evolve_once() {
 
     timer.mark(s(), "predictor");
     point_mass_accrete_particles();
+    // host-resident patch data (evolve_once_host): copies overlap the kernels
+    const bool piped_in = pipe.active && pipe.defer_in2, piped = pipe.active && pipe.early_out;
     for (auto &p : patches)
-        if (is_local(p) && p.f.n)
-            leapfrog_predictor(s(), p.f.n, dt_, p.f.xyz.p, p.f.vxyz.p, p.f.axyz.p, p.f.uint_.p, p.f.duint.p);
+        if (is_local(p) && p.f.n) {
+            if (piped_in) // uint / duint are still uploading: drift the positions now, u after the prestep
+                leapfrog_predictor_pos(s(), p.f.n, dt_, p.f.xyz.p, p.f.vxyz.p, p.f.axyz.p);
+            else
+                leapfrog_predictor(s(), p.f.n, dt_, p.f.xyz.p, p.f.vxyz.p, p.f.axyz.p, p.f.uint_.p, p.f.duint.p);
+        }
     kill_particles();
     compute_ext_forces_indep_v();
     timer.mark(s(), "position_boundary");
@@ -909,6 +915,16 @@ void Model::evolve_once() {
     comm_allreduce_host_u64(*this, &npart_all, 1, 0);
 
     sph_prestep();
+    if (piped) {
+        static const char *const early[] = {"xyz", "hpart", "axyz_ext"};
+        pipe_download(early, 3); // final since the drift / the h iteration: go back during the CD10 operators
+    }
+    if (piped_in) {
+        SB_CUDA_CHECK(cudaStreamWaitEvent(s(), pipe.ev_in2, 0));
+        for (auto &p : patches)
+            if (is_local(p) && p.f.n)
+                leapfrog_predictor_u(s(), p.f.n, dt_, p.f.uint_.p, p.f.duint.p);
+    }
 
     SphParams sp{cfg.gpart_mass, cfg.alpha_u, cfg.alpha_AV, cfg.beta_AV};
     f64 next_cfl              = 0;
@@ -961,6 +977,10 @@ void Model::evolve_once() {
                         s(), cfg.kernel, cfg.av, p.st.m, p.st.srch.SA.p, p.st.SB.p, p.st.SC.p, cfg.gpart_mass,
                         cfg.alpha_AV, p.st.SE.p, p.st.SF.p);
                 }
+        if (piped && corrector_iter_cnt == 0) {
+            static const char *const mid[] = {"divv", "curlv", "dtdivv", "alpha_AV@updated"};
+            pipe_download(mid, has_alpha ? 4 : 0); // go back during the force loop
+        }
         timer.mark(s(), "forces");
         // forces, v_sig and the CFL dt come out of one pass over the neighbour lists.  The CFL uses the cfl
         // multiplier in force at launch: if the corrector test below halves it, the whole pass is redone.
@@ -1022,6 +1042,12 @@ void Model::evolve_once() {
         corrector_iter_cnt++;
     } while (need_rerun_corrector);
     corrector_iter = corrector_iter_cnt;
+    if (piped) {
+        static const char *const tail[] = {"vxyz", "uint", "axyz", "duint", "soundspeed",
+                                           "divv", "curlv", "dtdivv", "alpha_AV"};
+        // a repeated corrector pass recomputed the CD10 operators: send them again
+        pipe_download(tail, corrector_iter_cnt > 1 && has_alpha ? 9 : 5);
+    }
     timer.end_step(s());
     SB_CUDA_CHECK(cudaStreamSynchronize(s()));
 
@@ -1030,6 +1056,131 @@ void Model::evolve_once() {
     f64 stiff      = cfg.cfl_multiplier_stiffness;
     cfl_multiplier = (cfl_multiplier * stiff + 1.) / (stiff + 1.);
     t_step         = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-resident patch data (shamb200_model_evolve_once_host)
+// ---------------------------------------------------------------------------------------------
+static f64 *host_field(const shamb200_host_patchdata &h, const std::string &nm) {
+    if (nm == "xyz") return h.xyz;
+    if (nm == "vxyz") return h.vxyz;
+    if (nm == "axyz") return h.axyz;
+    if (nm == "axyz_ext") return h.axyz_ext;
+    if (nm == "hpart") return h.hpart;
+    if (nm == "uint") return h.uint_;
+    if (nm == "duint") return h.duint;
+    if (nm == "alpha_AV") return h.alpha_AV;
+    if (nm == "divv") return h.divv;
+    if (nm == "dtdivv") return h.dtdivv;
+    if (nm == "curlv") return h.curlv;
+    if (nm == "soundspeed") return h.soundspeed;
+    return nullptr;
+}
+
+/// device -> host copies of the named fields on the download stream, ordered after the work queued so
+/// far on the main stream ("alpha_AV@updated": the new alpha before it is committed to the field)
+void Model::pipe_download(const char *const *names, int count) {
+    if (!pipe.out || count <= 0)
+        return;
+    PatchD &p = patches[pipe.ip];
+    SB_CUDA_CHECK(cudaEventRecord(pipe.ev_stage, s()));
+    SB_CUDA_CHECK(cudaStreamWaitEvent(pipe.d2h, pipe.ev_stage, 0));
+    for (int k = 0; k < count; k++) {
+        std::string nm(names[k]);
+        const f64 *src = nullptr;
+        int nvar       = 1;
+        if (nm == "alpha_AV@updated") {
+            nm  = "alpha_AV";
+            src = p.st.alpha_updated.p;
+        } else {
+            for (auto &r : p.f.all())
+                if (nm == r.name) {
+                    src  = r.buf->p;
+                    nvar = r.nvar;
+                }
+        }
+        f64 *dst = host_field(*pipe.out, nm);
+        if (!dst || !src || !p.f.n)
+            continue;
+        if (p.f.n > pipe.out_cap)
+            throw std::length_error("evolve_once_host: the patch holds more objects than out->n (capacity)");
+        size_t bytes = size_t(p.f.n) * nvar * sizeof(f64);
+        SB_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, pipe.d2h));
+        pipe.bytes_d2h += bytes;
+    }
+}
+
+void Model::evolve_once_host(u32 ip, const shamb200_host_patchdata *in, shamb200_host_patchdata *out) {
+    SB_CUDA_CHECK(cudaSetDevice(ctx->device));
+    PatchD &p = patches.at(ip);
+    if (!is_local(p))
+        throw std::invalid_argument("patch is not local");
+    if (!pipe.h2d) {
+        SB_CUDA_CHECK(cudaStreamCreateWithFlags(&pipe.h2d, cudaStreamNonBlocking));
+        SB_CUDA_CHECK(cudaStreamCreateWithFlags(&pipe.d2h, cudaStreamNonBlocking));
+        SB_CUDA_CHECK(cudaEventCreateWithFlags(&pipe.ev_in1, cudaEventDisableTiming));
+        SB_CUDA_CHECK(cudaEventCreateWithFlags(&pipe.ev_in2, cudaEventDisableTiming));
+        SB_CUDA_CHECK(cudaEventCreateWithFlags(&pipe.ev_stage, cudaEventDisableTiming));
+    }
+    u32 nlocal = 0;
+    for (auto &q : patches)
+        nlocal += is_local(q) ? 1 : 0;
+    const bool has_alpha = cfg.av == SHAMB200_AV_MM97 || cfg.av == SHAMB200_AV_CD10;
+    // outputs can leave early once the object count and order are final (after the prestep); the second
+    // input group may only arrive late when nothing reorders the patch before (kill, accretion, migration)
+    pipe.early_out = nlocal == 1;
+    pipe.defer_in2 = pipe.early_out && world == 1 && !cfg.has_point_mass && cfg.n_kill_spheres == 0
+                     && cfg.bc == SHAMB200_BC_PERIODIC;
+    pipe.ip = ip, pipe.in = in, pipe.out = out;
+    pipe.out_cap = out ? out->n : 0;
+    pipe.bytes_h2d = pipe.bytes_d2h = 0;
+    SB_CUDA_CHECK(cudaStreamSynchronize(s())); // nothing of a previous call may still read the fields
+    if (in && in->n != p.f.n) {                // the host owns the data: the patch takes its size
+        if (in->n > 0xFFFFFFF0ull)
+            throw std::invalid_argument("patch too large");
+        p.f.reserve(u32(in->n), s());
+        p.f.n = u32(in->n);
+        SB_CUDA_CHECK(cudaStreamSynchronize(s()));
+    }
+    auto upload = [&](const char *const *names, int count, cudaEvent_t done) {
+        for (int k = 0; in && k < count; k++) {
+            const f64 *src = host_field(*in, names[k]);
+            if (!src || !p.f.n)
+                continue;
+            for (auto &r : p.f.all())
+                if (std::string(names[k]) == r.name) {
+                    size_t bytes = size_t(p.f.n) * r.nvar * sizeof(f64);
+                    SB_CUDA_CHECK(cudaMemcpyAsync(r.buf->p, src, bytes, cudaMemcpyHostToDevice, pipe.h2d));
+                    pipe.bytes_h2d += bytes;
+                }
+        }
+        SB_CUDA_CHECK(cudaEventRecord(done, pipe.h2d));
+    };
+    static const char *const in1[] = {"xyz", "vxyz", "axyz", "hpart"}; // what the drift and the search read
+    static const char *const in2[] = {"uint", "duint", "alpha_AV"};
+    upload(in1, 4, pipe.ev_in1);
+    upload(in2, has_alpha ? 3 : 2, pipe.ev_in2);
+    SB_CUDA_CHECK(cudaStreamWaitEvent(s(), pipe.ev_in1, 0));
+    if (!pipe.defer_in2)
+        SB_CUDA_CHECK(cudaStreamWaitEvent(s(), pipe.ev_in2, 0));
+    pipe.active = true;
+    try {
+        evolve_once();
+    } catch (...) {
+        pipe.active = false;
+        cudaStreamSynchronize(pipe.h2d);
+        cudaStreamSynchronize(pipe.d2h);
+        throw;
+    }
+    pipe.active = false;
+    if (!pipe.early_out) { // several local patches: all at the end
+        static const char *const every[] = {"xyz", "vxyz", "axyz", "axyz_ext", "hpart", "uint", "duint",
+                                            "alpha_AV", "divv", "dtdivv", "curlv", "soundspeed"};
+        pipe_download(every, 12);
+    }
+    SB_CUDA_CHECK(cudaStreamSynchronize(pipe.d2h));
+    if (out)
+        out->n = p.f.n;
 }
 
 } // namespace sb

@@ -116,6 +116,18 @@ struct Model {
     DevBuf<u64> comm_dev;
     PinnedBuf<u64> comm_host;
 
+    /// host-resident patch data of the running step (evolve_once_host): copy streams + hand-over events
+    struct HostPipe {
+        bool active = false, early_out = false, defer_in2 = false;
+        u32 ip = 0;
+        const shamb200_host_patchdata *in = nullptr;
+        shamb200_host_patchdata *out      = nullptr;
+        cudaStream_t h2d = nullptr, d2h = nullptr;
+        cudaEvent_t ev_in1 = nullptr, ev_in2 = nullptr, ev_stage = nullptr;
+        u64 bytes_h2d = 0, bytes_d2h = 0, out_cap = 0;
+    } pipe;
+    void pipe_download(const char *const *names, int count);
+
     explicit Model(Ctx *c, const shamb200_solver_config &cf) : ctx(c), cfg(cf) {}
     cudaStream_t s() const { return ctx->stream; }
     bool is_local(const PatchD &p) const { return p.owner == rank; }
@@ -123,6 +135,7 @@ struct Model {
     void set_box(const f64 bmin[3], const f64 bmax[3], u32 nx, u32 ny, u32 nz);
     void push_particles(u64 n, const f64 *xyz, const f64 *vxyz, const f64 *h, const f64 *u);
     void evolve_once();
+    void evolve_once_host(u32 ip, const shamb200_host_patchdata *in, shamb200_host_patchdata *out);
     int64_t get(u32 ip, const std::string &name, void *out, int64_t cap);
     void set_field(u32 ip, const std::string &name, const f64 *in, u64 count);
 

@@ -16,10 +16,10 @@ namespace sb {
 
 // ---- leapfrog predictor: v+=½dt a ; u+=½dt du ; x+=dt v ; v+=½dt a ; u+=½dt du -----------------
 __global__ void __launch_bounds__(256) predictor_kernel(
-    u32 n, f64 dt, f64 dt_half, f64 *__restrict__ xyz, f64 *__restrict__ vxyz, const f64 *__restrict__ axyz,
-    f64 *__restrict__ uint_, const f64 *__restrict__ duint) {
+    u32 n_pos, u32 n_u, f64 dt, f64 dt_half, f64 *__restrict__ xyz, f64 *__restrict__ vxyz,
+    const f64 *__restrict__ axyz, f64 *__restrict__ uint_, const f64 *__restrict__ duint) {
     u64 i = u64(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i < u64(n) * 3) {
+    if (i < u64(n_pos) * 3) {
         f64 a  = axyz[i];
         f64 v  = vxyz[i];
         v      = v + dt_half * a;
@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(256) predictor_kernel(
         v      = v + dt_half * a;
         vxyz[i] = v;
     }
-    if (i < n) {
+    if (i < n_u) {
         f64 du = duint[i];
         f64 u  = uint_[i];
         u      = u + dt_half * du;
@@ -38,7 +38,23 @@ __global__ void __launch_bounds__(256) predictor_kernel(
 void leapfrog_predictor(cudaStream_t s, u32 n, f64 dt, f64 *xyz, f64 *vxyz, const f64 *axyz, f64 *uint_, const f64 *duint) {
     if (!n)
         return;
-    predictor_kernel<<<grid_for(u64(n) * 3, 256), 256, 0, s>>>(n, dt, dt / 2, xyz, vxyz, axyz, uint_, duint);
+    predictor_kernel<<<grid_for(u64(n) * 3, 256), 256, 0, s>>>(n, n, dt, dt / 2, xyz, vxyz, axyz, uint_, duint);
+    SB_COUNT_LAUNCH();
+    SB_LAUNCH_CHECK();
+}
+/// the two halves of the predictor on their own (host-resident patch data: `uint` may still be in flight
+/// while the positions are already being drifted; the updates are independent element by element)
+void leapfrog_predictor_pos(cudaStream_t s, u32 n, f64 dt, f64 *xyz, f64 *vxyz, const f64 *axyz) {
+    if (!n)
+        return;
+    predictor_kernel<<<grid_for(u64(n) * 3, 256), 256, 0, s>>>(n, 0, dt, dt / 2, xyz, vxyz, axyz, nullptr, nullptr);
+    SB_COUNT_LAUNCH();
+    SB_LAUNCH_CHECK();
+}
+void leapfrog_predictor_u(cudaStream_t s, u32 n, f64 dt, f64 *uint_, const f64 *duint) {
+    if (!n)
+        return;
+    predictor_kernel<<<grid_for(n, 256), 256, 0, s>>>(0, n, dt, dt / 2, nullptr, nullptr, nullptr, uint_, duint);
     SB_COUNT_LAUNCH();
     SB_LAUNCH_CHECK();
 }

@@ -11,7 +11,8 @@
 //
 // B200 mapping: particles are gathered into Morton order first, so a leaf's particles and every
 // candidate run are contiguous (coalesced 32-byte records).  Stage 1 walks the packed 64-byte nodes
-// once per leaf and emits merged candidate rank ranges into a capped slot (no count pass).  Stage 2 is
+// once per GROUP of 8 consecutive leaves, one warp per group, 32 frontier nodes per step, and emits the
+// group's candidate leaves with the mask of the members each one hits (exact per-leaf test).  Stage 2 is
 // warp-per-leaf with the 32 lanes holding 32 CANDIDATES; the leaf's particles are broadcast from shared
 // memory, each (particle, chunk) produces one ballot word.  The fill pass replays the ballots only.
 #include "neigh2.cuh"
@@ -129,14 +130,8 @@ __global__ void __launch_bounds__(256) pack_nodes_kernel(
 }
 
 // ---------------------------------------------------------------------------------------------
-// stage 1: candidate rank ranges of every leaf (one capped walk, no count pass)
+// stage 1: candidate leaves of every GROUP of GL consecutive leaves (one warp-cooperative walk per group)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool cella_neigh_b2(
-    f64 ax0, f64 ay0, f64 az0, f64 ax1, f64 ay1, f64 az1, f64 bx0, f64 by0, f64 bz0, f64 bx1, f64 by1, f64 bz1) {
-    return (fmax(ax0, bx0) <= fmin(ax1, bx1)) && (fmax(ay0, by0) <= fmin(ay1, by1))
-           && (fmax(az0, bz0) <= fmin(az1, bz1));
-}
-
 struct NodeRegs {
     f64 lo0, lo1, lo2, hi0, hi1, hi2, rint;
     u32 left, right;
@@ -152,96 +147,316 @@ __device__ __forceinline__ NodeRegs load_node(const NodePack *p) {
     return n;
 }
 
-constexpr int WALK_STACK = 32; // tree depth <= 30 (u32 Morton codes) + 1
+constexpr int WALK_WARPS = 4;
 
-__global__ void __launch_bounds__(128) leaf_ranges_kernel(
-    const NodePack *__restrict__ nodes, u32 I, u32 L, const u32 *__restrict__ real_prefix, f64 Rkern, u32 cap,
-    u32 *__restrict__ ranges, u32 *__restrict__ nrange, u32 *__restrict__ ncand, u32 *__restrict__ max_ranges) {
-    u32 g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= L)
+/// box of one leaf of the group and the same box grown by its own interaction radius
+struct LeafBox {
+    f64 lo[3], hi[3], e0[3], e1[3];
+};
+
+__device__ __forceinline__ f64 warp_min8(f64 v) { // lanes >= 8 hold the neutral element
+#pragma unroll
+    for (int o = 4; o >= 1; o >>= 1)
+        v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return __shfl_sync(0xffffffffu, v, 0);
+}
+__device__ __forceinline__ f64 warp_max8(f64 v) {
+#pragma unroll
+    for (int o = 4; o >= 1; o >>= 1)
+        v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return __shfl_sync(0xffffffffu, v, 0);
+}
+
+/// The reference walks the tree once per leaf a and keeps the leaves b with
+///   hit(a, b) = cella_neigh_b(a, b ⊕ rint_b·R) || cella_neigh_b(a ⊕ rint_a·R, b);
+/// internal nodes are pruned with the same test.  Boxes and rint only grow towards the root and every
+/// operation of the test is monotonic in floating point, so the set of leaves a walk reaches is exactly
+/// {b : hit(a, b)} — however the tree is traversed.  Here ONE warp walks for GL consecutive leaves: the
+/// frontier (shared memory, left-to-right order kept by an ordered compaction) is tested 32 nodes at a
+/// time, first against the union of the group's boxes (a superset of every member's test: cheap reject),
+/// then exactly against each member that still hit the parent; every entry carries the 8-bit mask of
+/// the members it hits, so the frontier is the union of the members' own walks and nothing more.
+/// Output per group: (first rank, mask << 24 | length) of the candidate leaves in ascending rank order.
+__global__ void __launch_bounds__(WALK_WARPS * 32) group_walk_kernel(
+    const NodePack *__restrict__ nodes, u32 I, u32 L, const u32 *__restrict__ real_prefix, f64 Rkern, u32 F, u32 capG,
+    uint2 *__restrict__ gcand, u32 *__restrict__ gcount, u32 *__restrict__ flags) {
+    extern __shared__ __align__(16) unsigned char walk_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t per_warp = sizeof(LeafBox) * GL + size_t(2) * F * sizeof(uint2);
+    LeafBox *lb = reinterpret_cast<LeafBox *>(walk_smem + warp * per_warp);
+    uint2 *cur  = reinterpret_cast<uint2 *>(lb + GL);
+    uint2 *nxt  = cur + F;
+    const u32 G = (L + GL - 1) / GL;
+    const u32 g = blockIdx.x * WALK_WARPS + warp;
+    if (g >= G)
         return;
-    NodeRegs a = load_node(nodes + I + g);
-    u32 nreal  = real_prefix[a.right] - real_prefix[a.left];
-    if (nreal == 0) { // a leaf of ghosts only: nobody needs its list
-        nrange[g] = 0;
-        ncand[g]  = 0;
-        return;
-    }
-    f64 a_rint = a.rint * Rkern;
-    f64 e0x = a.lo0 - a_rint, e0y = a.lo1 - a_rint, e0z = a.lo2 - a_rint;
-    f64 e1x = a.hi0 + a_rint, e1y = a.hi1 + a_rint, e1z = a.hi2 + a_rint;
-    u32 stack[WALK_STACK];
-    int sp      = 0;
-    stack[sp++] = 0; // root (node 0; when I == 0 it is the only leaf)
-    u32 nr = 0, cand = 0;
-    u32 cur_s = 0xffffffffu, cur_e = 0xffffffffu;
-    u32 *out = ranges + u64(g) * cap * 2;
-    while (sp > 0) {
-        u32 id     = stack[--sp];
-        NodeRegs n = load_node(nodes + id);
-        f64 r      = n.rint * Rkern;
-        // cella_neigh_b(a, n ⊕ r) || cella_neigh_b(a ⊕ ra, n): fmax(x,y) <= fmin(u,v) ⟺ x<=v && y<=u when
-        // x<=u and y<=v hold by construction (boxes are not inverted, r >= 0): same booleans, fewer FP64 ops
-        bool hit = (a.lo0 <= n.hi0 + r && n.lo0 - r <= a.hi0 && a.lo1 <= n.hi1 + r && n.lo1 - r <= a.hi1
-                    && a.lo2 <= n.hi2 + r && n.lo2 - r <= a.hi2)
-                   || (e0x <= n.hi0 && n.lo0 <= e1x && e0y <= n.hi1 && n.lo1 <= e1y && e0z <= n.hi2 && n.lo2 <= e1z);
-        if (!hit)
-            continue;
-        if (id >= I) { // leaf: ranks [left, right); DFS visits leaves in ascending order
-            cand += n.right - n.left;
-            if (n.left == cur_e) {
-                cur_e = n.right;
-            } else {
-                if (cur_s != 0xffffffffu) {
-                    if (nr < cap) {
-                        out[2 * nr]     = cur_s;
-                        out[2 * nr + 1] = cur_e;
-                    }
-                    nr++;
-                }
-                cur_s = n.left;
-                cur_e = n.right;
+    const f64 inf = __longlong_as_double(0x7ff0000000000000ll);
+    f64 l0 = inf, l1 = inf, l2 = inf, h0 = -inf, h1 = -inf, h2 = -inf;
+    f64 p0 = inf, p1 = inf, p2 = inf, q0 = -inf, q1 = -inf, q2 = -inf;
+    bool valid = false;
+    {
+        u32 leaf = g * GL + lane;
+        if (lane < GL && leaf < L) {
+            NodeRegs a = load_node(nodes + I + leaf);
+            valid      = real_prefix[a.right] != real_prefix[a.left]; // a leaf of ghosts only needs no list
+            f64 ar     = a.rint * Rkern;
+            LeafBox b;
+            b.lo[0] = a.lo0, b.lo[1] = a.lo1, b.lo[2] = a.lo2, b.hi[0] = a.hi0, b.hi[1] = a.hi1, b.hi[2] = a.hi2;
+            b.e0[0] = a.lo0 - ar, b.e0[1] = a.lo1 - ar, b.e0[2] = a.lo2 - ar;
+            b.e1[0] = a.hi0 + ar, b.e1[1] = a.hi1 + ar, b.e1[2] = a.hi2 + ar;
+            lb[lane] = b;
+            if (valid) {
+                l0 = b.lo[0], l1 = b.lo[1], l2 = b.lo[2], h0 = b.hi[0], h1 = b.hi[1], h2 = b.hi[2];
+                p0 = b.e0[0], p1 = b.e0[1], p2 = b.e0[2], q0 = b.e1[0], q1 = b.e1[1], q2 = b.e1[2];
             }
-        } else {
-            stack[sp++] = n.right;
-            stack[sp++] = n.left;
         }
     }
-    if (cur_s != 0xffffffffu) {
-        if (nr < cap) {
-            out[2 * nr]     = cur_s;
-            out[2 * nr + 1] = cur_e;
-        }
-        nr++;
+    const u32 vmask = __ballot_sync(0xffffffffu, valid);
+    if (vmask == 0) {
+        if (lane == 0)
+            gcount[g] = 0;
+        return;
     }
-    nrange[g] = nr < cap ? nr : cap; // clamped: an overflowing search is redone by the host
-    ncand[g]  = cand;
-    if (nr > cap)
-        atomicMax(max_ranges, nr);
+    l0 = warp_min8(l0), l1 = warp_min8(l1), l2 = warp_min8(l2);
+    h0 = warp_max8(h0), h1 = warp_max8(h1), h2 = warp_max8(h2);
+    p0 = warp_min8(p0), p1 = warp_min8(p1), p2 = warp_min8(p2);
+    q0 = warp_max8(q0), q1 = warp_max8(q1), q2 = warp_max8(q2);
+    // a compact group (the usual case: 8 neighbouring leaves) prunes internal nodes with the union test
+    // only; a spread one (Morton-consecutive leaves far apart) runs the member tests at every level
+    f64 m0 = -inf, m1 = -inf, m2 = -inf;
+    if (valid) {
+        const LeafBox &b = lb[lane];
+        m0 = b.e1[0] - b.e0[0], m1 = b.e1[1] - b.e0[1], m2 = b.e1[2] - b.e0[2];
+    }
+    m0 = warp_max8(m0), m1 = warp_max8(m1), m2 = warp_max8(m2);
+    const bool spread = (q0 - p0 > 2. * m0) || (q1 - p1 > 2. * m1) || (q2 - p2 > 2. * m2);
+    if (lane == 0)
+        cur[0] = make_uint2(0u, vmask << 24); // root (node 0; when I == 0 it is the only leaf); length 0: not tested yet
+    u32 ncur  = 1;
+    bool more = true;
+    while (more) {
+        __syncwarp();
+        u32 nn       = 0;
+        bool pending = false;
+        for (u32 base = 0; base < ncur; base += 32) {
+            const u32 k = base + lane;
+            u32 emit    = 0;
+            uint2 o0 = make_uint2(0u, 0u), o1 = o0;
+            if (k < ncur) {
+                uint2 e = cur[k];
+                if (e.y & 0xffffffu) { // a candidate leaf found in an earlier round
+                    emit = 1;
+                    o0   = e;
+                } else { // node e.x, to be tested for the members in e.y >> 24 (those that hit its parent)
+                    NodeRegs n = load_node(nodes + e.x);
+                    f64 r      = n.rint * Rkern;
+                    f64 x1 = n.hi0 + r, y1 = n.hi1 + r, z1 = n.hi2 + r;
+                    f64 x0 = n.lo0 - r, y0 = n.lo1 - r, z0 = n.lo2 - r;
+                    // fmax(x,y) <= fmin(u,v)  <=>  x <= v && y <= u when x <= u and y <= v hold by construction
+                    bool hit = (l0 <= x1 && x0 <= h0 && l1 <= y1 && y0 <= h1 && l2 <= z1 && z0 <= h2)
+                               || (p0 <= n.hi0 && n.lo0 <= q0 && p1 <= n.hi1 && n.lo1 <= q1 && p2 <= n.hi2 && n.lo2 <= q2);
+                    u32 mask = 0;
+                    if (hit) {
+                        const u32 pm = e.y >> 24;
+                        if (e.x >= I || spread) { // the exact test of the reference, member by member
+#pragma unroll
+                            for (int i = 0; i < GL; i++) {
+                                if (!((vmask >> i) & 1u)) // warp-uniform
+                                    continue;
+                                const LeafBox &A = lb[i];
+                                bool c1 = (A.lo[0] <= x1) & (x0 <= A.hi[0]) & (A.lo[1] <= y1) & (y0 <= A.hi[1])
+                                          & (A.lo[2] <= z1) & (z0 <= A.hi[2]);
+                                bool c2 = (A.e0[0] <= n.hi0) & (n.lo0 <= A.e1[0]) & (A.e0[1] <= n.hi1)
+                                          & (n.lo1 <= A.e1[1]) & (A.e0[2] <= n.hi2) & (n.lo2 <= A.e1[2]);
+                                mask |= ((c1 | c2) ? 1u : 0u) << i;
+                            }
+                            mask &= pm;
+                        } else {
+                            mask = pm;
+                        }
+                    }
+                    if (mask) {
+                        if (e.x >= I) { // leaf
+                            u32 len = n.right - n.left;
+                            if (len >= (1u << 24))
+                                atomicOr(flags + 2, 1u);
+                            emit = 1;
+                            o0   = make_uint2(n.left, (mask << 24) | (len & 0xffffffu));
+                        } else {
+                            emit    = 2;
+                            o0      = make_uint2(n.left, mask << 24);
+                            o1      = make_uint2(n.right, mask << 24);
+                            pending = true;
+                        }
+                    }
+                }
+            }
+            u32 inc = emit;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                u32 t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o)
+                    inc += t;
+            }
+            const u32 total = __shfl_sync(0xffffffffu, inc, 31);
+            const u32 off   = nn + inc - emit;
+            if (nn + total <= F) {
+                if (emit >= 1)
+                    nxt[off] = o0;
+                if (emit == 2)
+                    nxt[off + 1] = o1;
+            }
+            nn += total;
+        }
+        more = __any_sync(0xffffffffu, pending);
+        if (nn > F) { // the frontier does not fit: the host repeats the search with a larger one
+            if (lane == 0) {
+                atomicMax(flags + 0, nn);
+                gcount[g] = 0;
+            }
+            return;
+        }
+        uint2 *t = cur;
+        cur      = nxt;
+        nxt      = t;
+        ncur     = nn;
+    }
+    __syncwarp();
+    if (ncur > capG) {
+        if (lane == 0) {
+            atomicMax(flags + 1, ncur);
+            gcount[g] = 0;
+        }
+        return;
+    }
+    for (u32 k = lane; k < ncur; k += 32)
+        gcand[u64(g) * capG + k] = cur[k];
+    if (lane == 0)
+        gcount[g] = ncur;
 }
 
 // ---------------------------------------------------------------------------------------------
-// stage 2: accept pass (ballots) and ordered fill
+// stage 2: accept pass (ballots) and ordered fill, warp per leaf, block per group
 // ---------------------------------------------------------------------------------------------
-constexpr int S2_WARPS = 4;
+constexpr u32 RANK_CACHE   = 1024; ///< per-warp window of candidate ranks
+constexpr u32 BALLOT_WORDS = 512;  ///< per-warp ballot store: (particles of the batch) x (chunks)
 
-struct WarpScratch {
-    u32 start[RANGE_CAP_DEFAULT * 4];   // range starts (cap <= 256)
-    u32 pre[RANGE_CAP_DEFAULT * 4 + 1]; // exclusive prefix of the range lengths
-    Pack4 pa[32];                       // (x, y, z, lim_a) of the current batch of particles
+struct alignas(32) WarpScratch {
+    Pack4 pa[32];          // (x, y, z, lim_a) of the current batch of particles
+    u32 rankc[RANK_CACHE]; // candidate ranks of the current window
+    u32 ball[BALLOT_WORDS];
 };
 
-/// loads the ranges of `leaf` into the warp scratch; returns the candidate count
-__device__ __forceinline__ u32 load_ranges(
-    WarpScratch &w, const u32 *__restrict__ ranges, u32 leaf, u32 cap, u32 nr, int lane) {
-    u32 run = 0;
-    for (u32 base = 0; base < nr; base += 32) {
-        u32 k   = base + lane;
-        u32 s = 0, len = 0;
-        if (k < nr) {
-            s   = ranges[(u64(leaf) * cap + k) * 2];
-            len = ranges[(u64(leaf) * cap + k) * 2 + 1] - s;
+/// per-batch state of one warp while it scans the candidates of its leaf
+struct ScanState {
+    u32 nb;      ///< particles in the batch
+    u32 cglob;   ///< chunks processed so far
+    u32 mycount; ///< lane a < nb: accepted so far (MODE 0) / write cursor (MODE 1)
+    bool fit;    ///< every ballot so far is in the shared store
+};
+
+/// NC chunks of 32 candidates (lane = one candidate of each chunk) against the nb particles of the batch;
+/// two chunks per pass halve the shared-memory reads of the particles and give two independent chains.
+/// MODE 0: ballots + counts;  MODE 1: test again and write (used when the ballots / ranks did not fit)
+template<int MODE, int NC>
+__device__ __forceinline__ void chunk_body(
+    WarpScratch &w, ScanState &st, const Pack4 *__restrict__ SA, const bool (&vb)[NC], const u32 (&rank_b)[NC],
+    f64 Rker2, f64 h_tolerance, int lane, u32 lt, u32 *__restrict__ list_s) {
+    f64 bx[NC], by[NC], bz[NC], lim_b[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        bx[c] = by[c] = bz[c] = lim_b[c] = 0;
+        if (vb[c]) {
+            Pack4 q = ld4(SA + rank_b[c]);
+            bx[c] = q.a, by[c] = q.b, bz[c] = q.c;
+            f64 rint_b = q.d * h_tolerance;
+            lim_b[c]   = rint_b * rint_b * Rker2;
         }
+    }
+    const bool keep = MODE == 0 && (st.cglob + NC) * st.nb <= BALLOT_WORDS;
+    u32 mymask[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++)
+        mymask[c] = 0;
+    for (u32 a = 0; a < st.nb; a++) {
+        Pack4 pa = w.pa[a];
+        u32 m[NC];
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            f64 dx = pa.a - bx[c], dy = pa.b - by[c], dz = pa.c - bz[c];
+            f64 rab2         = dx * dx + dy * dy + dz * dz;
+            bool no_interact = rab2 > pa.d && rab2 > lim_b[c];
+            m[c]             = __ballot_sync(0xffffffffu, vb[c] && !no_interact);
+        }
+        if (MODE == 0) {
+            if (lane == int(a)) {
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    mymask[c] = m[c];
+                    st.mycount += __popc(m[c]);
+                }
+            }
+        } else {
+            u32 bo = __shfl_sync(0xffffffffu, st.mycount, a);
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                if ((m[c] >> lane) & 1u)
+                    list_s[bo + __popc(m[c] & lt)] = rank_b[c];
+                bo += __popc(m[c]);
+            }
+            if (lane == int(a))
+                st.mycount = bo;
+        }
+    }
+    if (MODE == 0) {
+        if (keep) {
+            if (lane < int(st.nb)) {
+#pragma unroll
+                for (int c = 0; c < NC; c++)
+                    w.ball[(st.cglob + c) * st.nb + lane] = mymask[c];
+            }
+        } else {
+            st.fit = false;
+        }
+    }
+    st.cglob += NC;
+}
+
+/// the window of `run` ranks in w.rankc, 64 (then 32) candidates at a time
+template<int MODE>
+__device__ __forceinline__ void flush_window(
+    WarpScratch &w, ScanState &st, const Pack4 *__restrict__ SA, u32 run, f64 Rker2, f64 h_tolerance, int lane, u32 lt,
+    u32 *__restrict__ list_s) {
+    __syncwarp();
+    u32 j0 = 0;
+    for (; j0 + 32 < run; j0 += 64) {
+        const u32 jA = j0 + lane, jB = j0 + 32 + lane;
+        const bool vb[2]  = {true, jB < run};
+        const u32 rk[2]   = {w.rankc[jA], vb[1] ? w.rankc[jB] : 0u};
+        chunk_body<MODE, 2>(w, st, SA, vb, rk, Rker2, h_tolerance, lane, lt, list_s);
+    }
+    if (j0 < run) {
+        const u32 j      = j0 + lane;
+        const bool vb[1] = {j < run};
+        const u32 rk[1]  = {vb[0] ? w.rankc[j] : 0u};
+        chunk_body<MODE, 1>(w, st, SA, vb, rk, Rker2, h_tolerance, lane, lt, list_s);
+    }
+    __syncwarp();
+}
+
+/// scans the candidates of one leaf of group g: the group's entries that carry the leaf's bit, expanded
+/// into windows of ranks (shared memory) and processed 32 at a time.  Returns true when everything went
+/// through ONE window that is still in w.rankc (then `nwin` is its length and the ballots can be replayed).
+template<int MODE>
+__device__ __forceinline__ bool scan_candidates(
+    WarpScratch &w, ScanState &st, const uint2 *__restrict__ gc, u32 gn, u32 bit, const Pack4 *__restrict__ SA,
+    f64 Rker2, f64 h_tolerance, int lane, u32 lt, u32 *__restrict__ list_s, u32 &nwin) {
+    u32 run     = 0;
+    bool single = true;
+    for (u32 base = 0; base < gn; base += 32) {
+        u32 k   = base + lane;
+        uint2 e = k < gn ? gc[k] : make_uint2(0u, 0u);
+        u32 len = (e.y & bit) ? (e.y & 0xffffffu) : 0u;
         u32 inc = len;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -249,67 +464,73 @@ __device__ __forceinline__ u32 load_ranges(
             if (lane >= o)
                 inc += t;
         }
-        if (k < nr) {
-            w.start[k] = s;
-            w.pre[k]   = run + inc - len;
+        const u32 tot = __shfl_sync(0xffffffffu, inc, 31);
+        if (tot == 0)
+            continue;
+        if (tot > RANK_CACHE) { // very large leaves (many equal Morton codes): straight from the entries
+            if (run)
+                flush_window<MODE>(w, st, SA, run, Rker2, h_tolerance, lane, lt, list_s);
+            run    = 0;
+            single = false;
+            for (int kk = 0; kk < 32; kk++) {
+                u32 s0 = __shfl_sync(0xffffffffu, e.x, kk), ln = __shfl_sync(0xffffffffu, len, kk);
+                for (u32 j0 = 0; j0 < ln; j0 += 32) {
+                    const u32 j      = j0 + lane;
+                    const bool vb[1] = {j < ln};
+                    const u32 rk[1]  = {s0 + j};
+                    chunk_body<MODE, 1>(w, st, SA, vb, rk, Rker2, h_tolerance, lane, lt, list_s);
+                }
+            }
+            continue;
         }
-        run += __shfl_sync(0xffffffffu, inc, 31);
+        if (run + tot > RANK_CACHE) {
+            flush_window<MODE>(w, st, SA, run, Rker2, h_tolerance, lane, lt, list_s);
+            run    = 0;
+            single = false;
+        }
+        u32 dst = run + inc - len;
+        for (u32 t = 0; __any_sync(0xffffffffu, t < len); t++)
+            if (t < len)
+                w.rankc[dst + t] = e.x + t;
+        run += tot;
     }
-    if (lane == 0)
-        w.pre[nr] = run;
-    __syncwarp();
-    return run;
-}
-/// rank of candidate j (j < ncand): binary search of the range holding it
-__device__ __forceinline__ u32 cand_rank(const WarpScratch &w, u32 nr, u32 j) {
-    u32 lo = 0, hi = nr; // invariant: pre[lo] <= j < pre[hi]
-    while (hi - lo > 1) {
-        u32 mid = (lo + hi) >> 1;
-        if (w.pre[mid] <= j)
-            lo = mid;
-        else
-            hi = mid;
-    }
-    return w.start[lo] + (j - w.pre[lo]);
+    nwin = run;
+    if (run)
+        flush_window<MODE>(w, st, SA, run, Rker2, h_tolerance, lane, lt, list_s);
+    return single;
 }
 
-constexpr u32 BALLOT_WORDS = 512; ///< per-warp shared ballot store: (particles of the batch) x (chunks)
-constexpr u32 RANK_CACHE   = 512; ///< per-warp cache of candidate ranks (16 chunks)
+constexpr int S2_WARPS = GL; // one block = one group of leaves
 
-struct WarpScratch2 {
-    u32 ball[BALLOT_WORDS];
-    u32 rankc[RANK_CACHE];
-};
-
-/// Stage 2, one launch: warp per leaf, lanes = candidates.  Pass 1 tests every (particle, candidate) pair
-/// and keeps the ballots in shared memory; the warp then reserves the leaf's list space with one atomic
-/// on a global cursor (lists are contiguous per leaf, leaves in completion order — the internal CSR does
-/// not need a global order, the exported ObjectCache is rebuilt by id) and pass 2 replays the ballots.
-/// Leaves whose ballots do not fit the shared store re-test in pass 2 instead.
-__global__ void __launch_bounds__(S2_WARPS * 32) neigh_lists_kernel(
+/// Stage 2, one launch: warp per leaf.  Pass 1 tests every (particle, candidate) pair and keeps the ballots
+/// in shared memory; the warp then reserves the leaf's list space with one atomic on a global cursor
+/// (lists are contiguous per leaf, leaves in completion order — the internal CSR does not need a global
+/// order, the exported ObjectCache is rebuilt by id) and pass 2 replays the ballots.  Leaves whose
+/// candidates or ballots do not fit the shared stores test again in pass 2 instead.
+__global__ void __launch_bounds__(S2_WARPS * 32, 4) neigh_lists_kernel(
     const NodePack *__restrict__ nodes, u32 I, u32 L, const Pack4 *__restrict__ SA, const u8 *__restrict__ real_flag,
-    const u32 *__restrict__ real_prefix, const u32 *__restrict__ ranges, u32 cap, const u32 *__restrict__ nrange,
+    const u32 *__restrict__ real_prefix, const uint2 *__restrict__ gcand, u32 capG, const u32 *__restrict__ gcount,
     f64 Rker2, f64 h_tolerance, u64 list_cap, unsigned long long *__restrict__ cursor, u32 *__restrict__ cnt_s,
     u32 *__restrict__ off_s, u32 *__restrict__ list_s) {
-    __shared__ WarpScratch ws[S2_WARPS];
-    __shared__ WarpScratch2 ws2[S2_WARPS];
+    extern __shared__ __align__(32) unsigned char s2_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const u32 lt   = (1u << lane) - 1u;
-    u32 leaf = blockIdx.x * S2_WARPS + warp;
+    const u32 g    = blockIdx.x;
+    const u32 leaf = g * GL + warp;
     if (leaf >= L)
         return;
-    u32 nr = nrange[leaf];
-    if (nr == 0)
+    const u32 gn = gcount[g];
+    if (gn == 0)
         return;
-    WarpScratch &w   = ws[warp];
-    WarpScratch2 &w2 = ws2[warp];
-    const u32 p0 = reinterpret_cast<const u32 *>(&nodes[I + leaf].rint)[2];
-    const u32 p1 = reinterpret_cast<const u32 *>(&nodes[I + leaf].rint)[3];
-    const u32 ncand  = load_ranges(w, ranges, leaf, cap, nr, lane);
-    const u32 nchunk = (ncand + 31) >> 5;
-    const u32 slot0  = real_prefix[p0];
-    const bool cache_ranks = nchunk * 32 <= RANK_CACHE;
-    u32 a_base = 0;
+    WarpScratch &w = reinterpret_cast<WarpScratch *>(s2_smem)[warp];
+    const u32 p0   = reinterpret_cast<const u32 *>(&nodes[I + leaf].rint)[2];
+    const u32 p1   = reinterpret_cast<const u32 *>(&nodes[I + leaf].rint)[3];
+    const u32 slot0 = real_prefix[p0];
+    if (real_prefix[p1] == slot0)
+        return; // no real particle in this leaf
+    const uint2 *gc = gcand + u64(g) * capG;
+    const u32 bit   = 1u << (24 + warp);
+    u32 a_base      = 0;
     for (u32 rb = p0; rb < p1; rb += 32) {
         u32 r   = rb + lane;
         bool va = r < p1 && real_flag[r];
@@ -317,7 +538,6 @@ __global__ void __launch_bounds__(S2_WARPS * 32) neigh_lists_kernel(
         u32 nb  = __popc(bal);
         if (nb == 0)
             continue;
-        const bool keep_ballots = nb * nchunk <= BALLOT_WORDS;
         __syncwarp();
         if (va) {
             Pack4 q    = ld4(SA + r);
@@ -326,37 +546,12 @@ __global__ void __launch_bounds__(S2_WARPS * 32) neigh_lists_kernel(
         }
         __syncwarp();
         // ---- pass 1: ballots + counts
-        u32 mycount = 0;
-        for (u32 c = 0; c < nchunk; c++) {
-            u32 j   = c * 32 + lane;
-            bool vb = j < ncand;
-            f64 bx = 0, by = 0, bz = 0, lim_b = 0;
-            if (vb) {
-                u32 rank_b = cand_rank(w, nr, j);
-                if (cache_ranks)
-                    w2.rankc[j] = rank_b;
-                Pack4 q = ld4(SA + rank_b);
-                bx = q.a, by = q.b, bz = q.c;
-                f64 rint_b = q.d * h_tolerance;
-                lim_b      = rint_b * rint_b * Rker2;
-            }
-            u32 mymask = 0;
-            for (u32 a = 0; a < nb; a++) {
-                Pack4 pa = w.pa[a];
-                f64 dx = pa.a - bx, dy = pa.b - by, dz = pa.c - bz;
-                f64 rab2         = dx * dx + dy * dy + dz * dz;
-                bool no_interact = rab2 > pa.d && rab2 > lim_b;
-                u32 m            = __ballot_sync(0xffffffffu, vb && !no_interact);
-                if (lane == int(a)) {
-                    mymask = m;
-                    mycount += __popc(m);
-                }
-            }
-            if (keep_ballots && lane < int(nb))
-                w2.ball[c * nb + lane] = mymask;
-        }
+        ScanState st{nb, 0u, 0u, true};
+        u32 nwin    = 0;
+        bool single = scan_candidates<0>(w, st, gc, gn, bit, SA, Rker2, h_tolerance, lane, lt, list_s, nwin);
+        const u32 mycount = lane < int(nb) ? st.mycount : 0u;
         // ---- reserve the list space of this batch: exclusive prefix of the counts + one atomic
-        u32 inc = lane < int(nb) ? mycount : 0u;
+        u32 inc = mycount;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             u32 t = __shfl_up_sync(0xffffffffu, inc, o);
@@ -368,7 +563,7 @@ __global__ void __launch_bounds__(S2_WARPS * 32) neigh_lists_kernel(
         if (lane == 0)
             base = atomicAdd(cursor, (unsigned long long) total);
         base = __shfl_sync(0xffffffffu, base, 0);
-        u32 myoff = u32(base) + inc - (lane < int(nb) ? mycount : 0u);
+        u32 myoff = u32(base) + inc - mycount;
         if (lane < int(nb)) {
             cnt_s[slot0 + a_base + lane] = mycount;
             off_s[slot0 + a_base + lane] = myoff;
@@ -378,42 +573,27 @@ __global__ void __launch_bounds__(S2_WARPS * 32) neigh_lists_kernel(
             continue; // the list array is too small: the host reads the cursor and runs the search again
         __syncwarp();
         // ---- pass 2: ordered fill
-        for (u32 c = 0; c < nchunk; c++) {
-            u32 j      = c * 32 + lane;
-            bool vb    = j < ncand;
-            u32 rank_b = 0;
-            if (vb)
-                rank_b = cache_ranks ? w2.rankc[j] : cand_rank(w, nr, j);
-            if (keep_ballots) {
-                u32 mymask = lane < int(nb) ? w2.ball[c * nb + lane] : 0u;
+        if (single && st.fit) { // replay the ballots of the one window
+            const u32 nchunk = (nwin + 31) >> 5;
+            for (u32 c = 0; c < nchunk; c += 2) { // two chunks per pass
+                const u32 jA = c * 32 + lane, jB = jA + 32;
+                const bool two = c + 1 < nchunk;
+                const u32 rkA = jA < nwin ? w.rankc[jA] : 0u, rkB = jB < nwin ? w.rankc[jB] : 0u;
+                const u32 mkA = lane < int(nb) ? w.ball[c * nb + lane] : 0u;
+                const u32 mkB = two && lane < int(nb) ? w.ball[(c + 1) * nb + lane] : 0u;
                 for (u32 a = 0; a < nb; a++) {
-                    u32 m  = __shfl_sync(0xffffffffu, mymask, a);
+                    u32 mA = __shfl_sync(0xffffffffu, mkA, a), mB = __shfl_sync(0xffffffffu, mkB, a);
                     u32 bo = __shfl_sync(0xffffffffu, myoff, a);
-                    if ((m >> lane) & 1u)
-                        list_s[bo + __popc(m & lt)] = rank_b;
+                    if ((mA >> lane) & 1u)
+                        list_s[bo + __popc(mA & lt)] = rkA;
+                    if ((mB >> lane) & 1u)
+                        list_s[bo + __popc(mA) + __popc(mB & lt)] = rkB;
                 }
-                myoff += __popc(mymask);
-            } else { // ballots did not fit: test again
-                f64 bx = 0, by = 0, bz = 0, lim_b = 0;
-                if (vb) {
-                    Pack4 q = ld4(SA + rank_b);
-                    bx = q.a, by = q.b, bz = q.c;
-                    f64 rint_b = q.d * h_tolerance;
-                    lim_b      = rint_b * rint_b * Rker2;
-                }
-                for (u32 a = 0; a < nb; a++) {
-                    Pack4 pa = w.pa[a];
-                    f64 dx = pa.a - bx, dy = pa.b - by, dz = pa.c - bz;
-                    f64 rab2         = dx * dx + dy * dy + dz * dz;
-                    bool no_interact = rab2 > pa.d && rab2 > lim_b;
-                    u32 m            = __ballot_sync(0xffffffffu, vb && !no_interact);
-                    u32 bo           = __shfl_sync(0xffffffffu, myoff, a);
-                    if ((m >> lane) & 1u)
-                        list_s[bo + __popc(m & lt)] = rank_b;
-                    if (lane == int(a))
-                        myoff += __popc(m);
-                }
+                myoff += __popc(mkA) + __popc(mkB);
             }
+        } else { // did not fit: scan and test again, writing as we go
+            ScanState st2{nb, 0u, myoff, true};
+            scan_candidates<1>(w, st2, gc, gn, bit, SA, Rker2, h_tolerance, lane, lt, list_s, nwin);
         }
     }
 }
@@ -426,51 +606,68 @@ void search_build(
         I, L, tb.aabb_min.p, tb.aabb_max.p, d_rint, tb.lchild.p, tb.rchild.p, tb.lflag.p, tb.rflag.p,
         tb.reduc_index_map.p, sb.nodes.p);
     SB_COUNT_LAUNCH();
-    sb.nrange.ensure(L, 1.1);
-    sb.ncand.ensure(L, 1.1);
+    const u32 G = (L + GL - 1) / GL;
+    sb.gcount.ensure(G, 1.1);
     sb.cnt_s.ensure(sb.N, 1.1);
     sb.off_s.ensure(sb.N, 1.1);
     const f64 Rker2 = Rkern * Rkern;
+    static bool attr_set = false;
+    const size_t s2_bytes = sizeof(WarpScratch) * S2_WARPS;
+    if (!attr_set) {
+        SB_CUDA_CHECK(cudaFuncSetAttribute(neigh_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(s2_bytes)));
+        SB_CUDA_CHECK(cudaFuncSetAttribute(group_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
     // list capacity: what the previous search of this patch needed (+ slack), ~96 entries per particle the
     // first time.  ONE host synchronisation per search: it reads the list cursor (= K) and the largest
-    // range count; if either ran past its capacity the exact need is known and the search is repeated.
+    // frontier / candidate-leaf counts; if any ran past its capacity the exact need is known and the
+    // search is repeated.
     if (sb.list_s.cap == 0)
         sb.list_s.ensure(size_t(sb.N) * 96 + 1024);
-    u32 *d_maxr                  = reinterpret_cast<u32 *>(sb.scalars.p + 2);
-    unsigned long long *d_cursor = reinterpret_cast<unsigned long long *>(sb.scalars.p + 3);
+    u32 *d_flags                 = reinterpret_cast<u32 *>(sb.scalars.p + 2); // [0] frontier need, [1] candidate need, [2] errors
+    unsigned long long *d_cursor = reinterpret_cast<unsigned long long *>(sb.scalars.p + 4);
     for (int attempt = 0;; attempt++) {
-        if (sb.range_cap > RANGE_CAP_DEFAULT * 4)
-            throw std::runtime_error("neighbour search: more than 256 candidate rank ranges for one leaf");
-        sb.ranges.ensure(size_t(L) * sb.range_cap * 2, 1.1);
-        SB_CUDA_CHECK(cudaMemsetAsync(sb.scalars.p + 2, 0, 2 * sizeof(u64), s));
-        leaf_ranges_kernel<<<grid_for(L, 128), 128, 0, s>>>(
-            sb.nodes.p, I, L, sb.real_prefix.p, Rkern, sb.range_cap, sb.ranges.p, sb.nrange.p, sb.ncand.p, d_maxr);
+        const size_t per_warp = sizeof(LeafBox) * GL + size_t(2) * sb.frontier_cap * sizeof(uint2);
+        if (per_warp * WALK_WARPS > 200 * 1024)
+            throw std::runtime_error("neighbour search: the tree-walk frontier of one leaf group exceeds shared memory");
+        sb.gcand.ensure(size_t(G) * sb.group_cap, 1.1);
+        SB_CUDA_CHECK(cudaMemsetAsync(sb.scalars.p + 2, 0, 3 * sizeof(u64), s));
+        group_walk_kernel<<<grid_for(G, WALK_WARPS), WALK_WARPS * 32, per_warp * WALK_WARPS, s>>>(
+            sb.nodes.p, I, L, sb.real_prefix.p, Rkern, sb.frontier_cap, sb.group_cap, sb.gcand.p, sb.gcount.p, d_flags);
         SB_COUNT_LAUNCH();
-        neigh_lists_kernel<<<grid_for(L, S2_WARPS), S2_WARPS * 32, 0, s>>>(
-            sb.nodes.p, I, L, sb.SA.p, sb.real_flag.p, sb.real_prefix.p, sb.ranges.p, sb.range_cap, sb.nrange.p, Rker2,
+        neigh_lists_kernel<<<G, S2_WARPS * 32, s2_bytes, s>>>(
+            sb.nodes.p, I, L, sb.SA.p, sb.real_flag.p, sb.real_prefix.p, sb.gcand.p, sb.group_cap, sb.gcount.p, Rker2,
             h_tolerance, u64(sb.list_s.cap), d_cursor, sb.cnt_s.p, sb.off_s.p, sb.list_s.p);
         SB_COUNT_LAUNCH();
-        SB_CUDA_CHECK(cudaMemcpyAsync(sb.h_scalars.p + 2, sb.scalars.p + 2, 2 * sizeof(u64), cudaMemcpyDeviceToHost, s));
+        SB_CUDA_CHECK(cudaMemcpyAsync(sb.h_scalars.p + 2, sb.scalars.p + 2, 3 * sizeof(u64), cudaMemcpyDeviceToHost, s));
         SB_CUDA_CHECK(cudaStreamSynchronize(s));
-        u32 maxr = u32(sb.h_scalars.p[2] & 0xffffffffull);
-        sb.K     = sb.h_scalars.p[3];
+        const u32 need_f = u32(sb.h_scalars.p[2] & 0xffffffffull), need_c = u32(sb.h_scalars.p[2] >> 32);
+        const u32 err    = u32(sb.h_scalars.p[3] & 0xffffffffull);
+        sb.K             = sb.h_scalars.p[4];
+        if (err)
+            throw std::runtime_error("neighbour search: a tree leaf holds 2^24 or more objects");
         bool redo = false;
-        if (maxr > sb.range_cap) { // rare: a leaf sees more merged ranges than its slot holds
-            while (sb.range_cap < maxr)
-                sb.range_cap *= 2;
+        if (need_f > sb.frontier_cap) { // rare: the walk of a group holds more nodes than its frontier
+            while (sb.frontier_cap < need_f)
+                sb.frontier_cap *= 2;
             redo = true;
-        } else if (sb.K > 0xFFFFFFFFull) {
+        }
+        if (need_c > sb.group_cap) { // rare: a group sees more candidate leaves than its slot holds
+            while (sb.group_cap < need_c)
+                sb.group_cap *= 2;
+            redo = true;
+        }
+        if (!redo && sb.K > 0xFFFFFFFFull)
             throw std::overflow_error(
                 "neighbour count overflows u32 (sum_neigh_cnt is u32 in the reference, TreeTraversal.hpp:378): "
                 "use more / smaller patches");
-        }
-        if (sb.K > sb.list_s.cap && sb.K <= 0xFFFFFFFFull) {
+        if (!redo && sb.K > sb.list_s.cap) {
             sb.list_s.ensure(sb.K, 1.1);
             redo = true;
         }
         if (!redo)
             break;
-        if (attempt >= 3)
+        if (attempt >= 8)
             throw std::runtime_error("neighbour search: capacity retry failed");
     }
     SB_LAUNCH_CHECK();

@@ -1,6 +1,6 @@
-// neigh2.cuh — the B200 neighbour search: Morton-sorted particle storage, packed tree nodes, one capped
-// tree walk per leaf (candidate rank ranges), a warp-cooperative accept pass whose lanes are the
-// candidates (ballot masks), and an ordered fill.  Output: a CSR over the REAL particles in sorted
+// neigh2.cuh — the B200 neighbour search: Morton-sorted particle storage, packed tree nodes, one
+// warp-cooperative tree walk per group of 8 leaves (candidate leaves + member masks), a warp-cooperative
+// accept pass whose lanes are the candidates (ballot masks), and an ordered fill.  Output: a CSR over the REAL particles in sorted
 // (Morton rank) order whose entries are RANKS; `export_object_cache` converts it to the reference's
 // ObjectCache layout (by particle id, ids) — bit-identical to NeighbourCache.cpp:223-604.
 #pragma once
@@ -16,20 +16,21 @@ struct alignas(64) NodePack {
     u32 left, right; ///< internal: child node ids (leaves are offset by I); leaf: rank range [left, right)
 };
 
-constexpr int RANGE_CAP_DEFAULT = 64;
+constexpr int GL = 8; ///< leaves per walk group (the member mask lives in the top 8 bits of an entry)
 
 struct SearchBuffers {
     u32 N = 0, M = 0, L = 0, I = 0;
     u64 K        = 0; ///< total neighbour count
-    u32 range_cap = RANGE_CAP_DEFAULT;
+    u32 group_cap    = 192; ///< candidate leaves kept per group (doubled on demand)
+    u32 frontier_cap = 384; ///< walk frontier entries per group in shared memory (doubled on demand)
     DevBuf<NodePack> nodes;  // [I+L]
     DevBuf<Pack4> SA;        // [M] (x,y,z,h) in sorted order
     DevBuf<u32> inv_map;     // [M] rank of merged index i
     DevBuf<u8> real_flag;    // [M+1]
     DevBuf<u32> real_prefix; // [M+1] exclusive scan of real_flag over ranks (slot of a real rank)
     DevBuf<u32> slot_rank;   // [N] rank of slot k
-    DevBuf<u32> ranges;      // [L * cap * 2]
-    DevBuf<u32> nrange, ncand; // [L]
+    DevBuf<uint2> gcand;     // [G * group_cap] (first rank, member mask << 24 | length) per candidate leaf
+    DevBuf<u32> gcount;      // [G]
     DevBuf<u32> cnt_s, off_s; // [N]
     DevBuf<u32> list_s;       // [K] ranks, ascending inside each list; lists of one leaf contiguous
     DevBuf<u32> scan_tmp;

@@ -177,7 +177,7 @@ __device__ __forceinline__ f64 warp_max8(f64 v) {
 /// then exactly against each member that still hit the parent; every entry carries the 8-bit mask of
 /// the members it hits, so the frontier is the union of the members' own walks and nothing more.
 /// Output per group: (first rank, mask << 24 | length) of the candidate leaves in ascending rank order.
-__global__ void __launch_bounds__(WALK_WARPS * 32) group_walk_kernel(
+__global__ void __launch_bounds__(WALK_WARPS * 32, 6) group_walk_kernel(
     const NodePack *__restrict__ nodes, u32 I, u32 L, const u32 *__restrict__ real_prefix, f64 Rkern, u32 F, u32 capG,
     uint2 *__restrict__ gcand, u32 *__restrict__ gcount, u32 *__restrict__ flags) {
     extern __shared__ __align__(16) unsigned char walk_smem[];
@@ -186,8 +186,9 @@ __global__ void __launch_bounds__(WALK_WARPS * 32) group_walk_kernel(
     LeafBox *lb = reinterpret_cast<LeafBox *>(walk_smem + warp * per_warp);
     uint2 *cur  = reinterpret_cast<uint2 *>(lb + GL);
     uint2 *nxt  = cur + F;
-    const u32 G = (L + GL - 1) / GL;
-    const u32 g = blockIdx.x * WALK_WARPS + warp;
+    const u32 G  = (L + GL - 1) / GL;
+    const u32 g  = blockIdx.x * WALK_WARPS + warp;
+    const u32 lt = (1u << lane) - 1u;
     if (g >= G)
         return;
     const f64 inf = __longlong_as_double(0x7ff0000000000000ll);
@@ -242,8 +243,15 @@ __global__ void __launch_bounds__(WALK_WARPS * 32) group_walk_kernel(
             const u32 k = base + lane;
             u32 emit    = 0;
             uint2 o0 = make_uint2(0u, 0u), o1 = o0;
+            const uint2 e = k < ncur ? cur[k] : make_uint2(0u, 1u);
+            if (__all_sync(0xffffffffu, (e.y & 0xffffffu) != 0)) { // only candidate leaves of earlier rounds: copy
+                const u32 cnt = min(32u, ncur - base);
+                if (nn + cnt <= F && k < ncur)
+                    nxt[nn + lane] = e;
+                nn += cnt;
+                continue;
+            }
             if (k < ncur) {
-                uint2 e = cur[k];
                 if (e.y & 0xffffffu) { // a candidate leaf found in an earlier round
                     emit = 1;
                     o0   = e;
@@ -268,7 +276,8 @@ __global__ void __launch_bounds__(WALK_WARPS * 32) group_walk_kernel(
                                           & (A.lo[2] <= z1) & (z0 <= A.hi[2]);
                                 bool c2 = (A.e0[0] <= n.hi0) & (n.lo0 <= A.e1[0]) & (A.e0[1] <= n.hi1)
                                           & (n.lo1 <= A.e1[1]) & (A.e0[2] <= n.hi2) & (n.lo2 <= A.e1[2]);
-                                mask |= ((c1 | c2) ? 1u : 0u) << i;
+                                if (c1 | c2)
+                                    mask |= 1u << i;
                             }
                             mask &= pm;
                         } else {
@@ -291,15 +300,10 @@ __global__ void __launch_bounds__(WALK_WARPS * 32) group_walk_kernel(
                     }
                 }
             }
-            u32 inc = emit;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                u32 t = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o)
-                    inc += t;
-            }
-            const u32 total = __shfl_sync(0xffffffffu, inc, 31);
-            const u32 off   = nn + inc - emit;
+            // ordered compaction: emit is 0, 1 or 2 -> two ballots give the exclusive prefix
+            const u32 b1 = __ballot_sync(0xffffffffu, emit >= 1), b2 = __ballot_sync(0xffffffffu, emit == 2);
+            const u32 total = __popc(b1) + __popc(b2);
+            const u32 off   = nn + __popc(b1 & lt) + __popc(b2 & lt);
             if (nn + total <= F) {
                 if (emit >= 1)
                     nxt[off] = o0;

@@ -147,7 +147,7 @@ __device__ __forceinline__ NodeRegs load_node(const NodePack *p) {
     return n;
 }
 
-constexpr int WALK_WARPS = 4;
+constexpr int WALK_WARPS = 1; // one walk per block: walks differ in length, a block would wait for its slowest warp
 
 /// box of one leaf of the group and the same box grown by its own interaction radius
 struct LeafBox {
@@ -177,14 +177,14 @@ __device__ __forceinline__ f64 warp_max8(f64 v) {
 /// then exactly against each member that still hit the parent; every entry carries the 8-bit mask of
 /// the members it hits, so the frontier is the union of the members' own walks and nothing more.
 /// Output per group: (first rank, mask << 24 | length) of the candidate leaves in ascending rank order.
-__global__ void __launch_bounds__(WALK_WARPS * 32, 6) group_walk_kernel(
+__global__ void __launch_bounds__(WALK_WARPS * 32, 32) group_walk_kernel(
     const NodePack *__restrict__ nodes, u32 I, u32 L, const u32 *__restrict__ real_prefix, f64 Rkern, u32 F, u32 capG,
     uint2 *__restrict__ gcand, u32 *__restrict__ gcount, u32 *__restrict__ flags) {
     extern __shared__ __align__(16) unsigned char walk_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t per_warp = sizeof(LeafBox) * GL + size_t(2) * F * sizeof(uint2);
-    LeafBox *lb = reinterpret_cast<LeafBox *>(walk_smem + warp * per_warp);
-    uint2 *cur  = reinterpret_cast<uint2 *>(lb + GL);
+    const size_t per_warp = sizeof(LeafBox) * (GL + 1) + size_t(2) * F * sizeof(uint2);
+    LeafBox *lb = reinterpret_cast<LeafBox *>(walk_smem + warp * per_warp); // members, then their union
+    uint2 *cur  = reinterpret_cast<uint2 *>(lb + GL + 1);
     uint2 *nxt  = cur + F;
     const u32 G  = (L + GL - 1) / GL;
     const u32 g  = blockIdx.x * WALK_WARPS + warp;
@@ -231,8 +231,14 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, 6) group_walk_kernel(
     }
     m0 = warp_max8(m0), m1 = warp_max8(m1), m2 = warp_max8(m2);
     const bool spread = (q0 - p0 > 2. * m0) || (q1 - p1 > 2. * m1) || (q2 - p2 > 2. * m2);
-    if (lane == 0)
-        cur[0] = make_uint2(0u, vmask << 24); // root (node 0; when I == 0 it is the only leaf); length 0: not tested yet
+    if (lane == 0) {
+        LeafBox u; // kept in shared memory (broadcast reads) rather than in 24 registers
+        u.lo[0] = l0, u.lo[1] = l1, u.lo[2] = l2, u.hi[0] = h0, u.hi[1] = h1, u.hi[2] = h2;
+        u.e0[0] = p0, u.e0[1] = p1, u.e0[2] = p2, u.e1[0] = q0, u.e1[1] = q1, u.e1[2] = q2;
+        lb[GL]  = u;
+        cur[0]  = make_uint2(0u, vmask << 24);
+    }
+    const LeafBox &U = lb[GL]; // root (node 0; when I == 0 it is the only leaf); length 0: not tested yet
     u32 ncur  = 1;
     bool more = true;
     while (more) {
@@ -261,8 +267,10 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, 6) group_walk_kernel(
                     f64 x1 = n.hi0 + r, y1 = n.hi1 + r, z1 = n.hi2 + r;
                     f64 x0 = n.lo0 - r, y0 = n.lo1 - r, z0 = n.lo2 - r;
                     // fmax(x,y) <= fmin(u,v)  <=>  x <= v && y <= u when x <= u and y <= v hold by construction
-                    bool hit = (l0 <= x1 && x0 <= h0 && l1 <= y1 && y0 <= h1 && l2 <= z1 && z0 <= h2)
-                               || (p0 <= n.hi0 && n.lo0 <= q0 && p1 <= n.hi1 && n.lo1 <= q1 && p2 <= n.hi2 && n.lo2 <= q2);
+                    bool hit = ((U.lo[0] <= x1) & (x0 <= U.hi[0]) & (U.lo[1] <= y1) & (y0 <= U.hi[1])
+                                & (U.lo[2] <= z1) & (z0 <= U.hi[2]))
+                               | ((U.e0[0] <= n.hi0) & (n.lo0 <= U.e1[0]) & (U.e0[1] <= n.hi1) & (n.lo1 <= U.e1[1])
+                                  & (U.e0[2] <= n.hi2) & (n.lo2 <= U.e1[2]));
                     u32 mask = 0;
                     if (hit) {
                         const u32 pm = e.y >> 24;
@@ -631,7 +639,7 @@ void search_build(
     u32 *d_flags                 = reinterpret_cast<u32 *>(sb.scalars.p + 2); // [0] frontier need, [1] candidate need, [2] errors
     unsigned long long *d_cursor = reinterpret_cast<unsigned long long *>(sb.scalars.p + 4);
     for (int attempt = 0;; attempt++) {
-        const size_t per_warp = sizeof(LeafBox) * GL + size_t(2) * sb.frontier_cap * sizeof(uint2);
+        const size_t per_warp = sizeof(LeafBox) * (GL + 1) + size_t(2) * sb.frontier_cap * sizeof(uint2);
         if (per_warp * WALK_WARPS > 200 * 1024)
             throw std::runtime_error("neighbour search: the tree-walk frontier of one leaf group exceeds shared memory");
         sb.gcand.ensure(size_t(G) * sb.group_cap, 1.1);

@@ -22,7 +22,7 @@ struct SearchBuffers {
     u32 N = 0, M = 0, L = 0, I = 0;
     u64 K        = 0; ///< total neighbour count
     u32 group_cap    = 192; ///< candidate leaves kept per group (doubled on demand)
-    u32 frontier_cap = 384; ///< walk frontier entries per group in shared memory (doubled on demand)
+    u32 frontier_cap = 320; ///< walk frontier entries per group in shared memory (doubled on demand)
     DevBuf<NodePack> nodes;  // [I+L]
     DevBuf<Pack4> SA;        // [M] (x,y,z,h) in sorted order
     DevBuf<u32> inv_map;     // [M] rank of merged index i

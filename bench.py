@@ -108,7 +108,11 @@ def workload(npart_per_gpu, n_gpus, kernel="M4"):
 def alg_work(stage, N, M, K, L, sweeps):
     K_acc = K / 1.1**3
     return {
-        "neigh_cache": (64 * M + 4 * K + 12 * N, 10.0 * K),
+        # the search = one tree walk per group of 8 leaves + the accept / fill kernel; SURVEY.md §8d's figure
+        # for the whole cache (64 M + 4 K + 12 N) split over the two launches: packed nodes (64 B, I + L = 2 L)
+        # and candidate entries for the walk; sorted records (32 B), list and count / offset writes for the lists
+        "neigh_walk": (64 * 2 * L + 8 * 12 * L, 30.0 * 2 * L),
+        "neigh_lists": (32 * M + 4 * K + 8 * N, 10.0 * K),
         "h_iteration": (4 * K + 32 * M + 40 * N, (sweeps + 1) * (10.0 * K + 39.0 * K_acc)),
         "divv_curlv_dtdivv": (4 * K + 96 * M + 40 * N, 10.0 * K + 175.0 * K_acc),
         "forces": (4 * K + 128 * M + 64 * N, 10.0 * K + 155.0 * K_acc),
@@ -309,7 +313,7 @@ def main():
         # stage = device time between CUDA-event marks on the step's stream; each heavy stage is ONE kernel
         # (h_solve / av_operators / force_cfl) or the search kernels.  Roof = slower of HBM and FP64 pipe.
         N, K = n_local, int(st["K_local"])
-        M, L = int(N * 1.0), N // 7
+        M, L = int(N * 1.0), int(N / 3.6)  # ~3.6 objects per leaf at reduction level 3 on the HCP lattice
         sweeps = int(st["h_iters_last"]) + 1
         per_stage = {k: v / args.steps for k, v in stage_acc.items()}
         table = {}
@@ -323,10 +327,19 @@ def main():
                         "GB/s": w[0] / (ms_k * 1e-3) / 1e9, "TFLOP/s": w[1] / (ms_k * 1e-3) / 1e12}
         top = max(table, key=lambda k: table[k]["ms"])
         tt = table[top]
+        # DRAM bytes of one launch of that kernel from the committed ncu --set full capture of this workload
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "traffic_17M.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if abs(tj["npart"] - n_local) <= 0.01 * n_local and top in tj["stages"]:
+                traffic, traffic_src = tj["stages"][top]["traffic"], "profiles/traffic_17M.json (" + tj["stages"][top]["kernel"] + ")"
         roofline = {"bound": tt["bound"], "kernel": top,
                     "achieved": tt["TFLOP/s"] if tt["bound"] == "fp64" else tt["GB/s"],
                     "peak": fp64_peak if tt["bound"] == "fp64" else hbm_peak,
-                    "unit": "TFLOP/s" if tt["bound"] == "fp64" else "GB/s", "frac": tt["frac"], "traffic": None,
+                    "unit": "TFLOP/s" if tt["bound"] == "fp64" else "GB/s", "frac": tt["frac"], "traffic": traffic, "traffic_source": traffic_src,
+                    "algorithmic_bytes": alg_work(top, N, M, K, L, sweeps)[0],
+                    "algorithmic_flops": alg_work(top, N, M, K, L, sweeps)[1],
                     "peak_source": {"hbm_gbs": hbm_peak, "hbm": peak_src, "fp64_tflops": fp64_peak,
                                     "fp64": "measured here: FP64 FMA chains (shamb200_microbench), FMA = 2 flop",
                                     "copy_gbs_here": copy_bw},

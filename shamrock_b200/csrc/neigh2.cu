@@ -167,6 +167,111 @@ __device__ __forceinline__ f64 warp_max8(f64 v) {
     return __shfl_sync(0xffffffffu, v, 0);
 }
 
+constexpr u32 SUPER   = 64;  ///< groups per super-group (512 leaves) sharing the top of their walks
+constexpr u32 TOP_CAP = 128; ///< start-frontier entries per super-group
+
+__device__ __forceinline__ f64 warp_min32(f64 v) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1)
+        v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ f64 warp_max32(f64 v) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1)
+        v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+/// The first ~15 levels of the walks of neighbouring groups visit the same nodes, one dependent memory
+/// latency per level.  One warp per super-group of 64 groups descends from the root with the union of all
+/// its leaves (a superset of every member group's test, so nothing a group needs is pruned) until the
+/// frontier holds 64 nodes, and leaves that frontier (node ids, left to right, untested) as the starting
+/// point of the 64 group walks.
+__global__ void __launch_bounds__(32) top_walk_kernel(
+    const NodePack *__restrict__ nodes, u32 I, u32 L, const u32 *__restrict__ real_prefix, f64 Rkern,
+    u32 *__restrict__ top_front, u32 *__restrict__ top_count) {
+    __shared__ u32 fa[TOP_CAP], fb[TOP_CAP];
+    const int lane = threadIdx.x;
+    const u32 lt   = (1u << lane) - 1u;
+    const u32 sg   = blockIdx.x;
+    const u32 leaf0 = sg * SUPER * GL, leaf1 = min(L, leaf0 + SUPER * GL);
+    const f64 inf = __longlong_as_double(0x7ff0000000000000ll);
+    f64 l0 = inf, l1 = inf, l2 = inf, h0 = -inf, h1 = -inf, h2 = -inf;
+    f64 p0 = inf, p1 = inf, p2 = inf, q0 = -inf, q1 = -inf, q2 = -inf;
+    for (u32 leaf = leaf0 + lane; leaf < leaf1; leaf += 32) {
+        NodeRegs a = load_node(nodes + I + leaf);
+        if (real_prefix[a.right] == real_prefix[a.left])
+            continue;
+        f64 ar = a.rint * Rkern;
+        l0 = fmin(l0, a.lo0), l1 = fmin(l1, a.lo1), l2 = fmin(l2, a.lo2);
+        h0 = fmax(h0, a.hi0), h1 = fmax(h1, a.hi1), h2 = fmax(h2, a.hi2);
+        p0 = fmin(p0, a.lo0 - ar), p1 = fmin(p1, a.lo1 - ar), p2 = fmin(p2, a.lo2 - ar);
+        q0 = fmax(q0, a.hi0 + ar), q1 = fmax(q1, a.hi1 + ar), q2 = fmax(q2, a.hi2 + ar);
+    }
+    l0 = warp_min32(l0), l1 = warp_min32(l1), l2 = warp_min32(l2);
+    h0 = warp_max32(h0), h1 = warp_max32(h1), h2 = warp_max32(h2);
+    p0 = warp_min32(p0), p1 = warp_min32(p1), p2 = warp_min32(p2);
+    q0 = warp_max32(q0), q1 = warp_max32(q1), q2 = warp_max32(q2);
+    if (!(l0 <= h0)) { // no real particle below this super-group: its groups return at once
+        if (lane == 0)
+            top_count[sg] = 0;
+        return;
+    }
+    u32 *cur = fa, *nxt = fb;
+    if (lane == 0)
+        cur[0] = 0u;
+    u32 ncur = 1;
+    for (;;) {
+        __syncwarp();
+        u32 nn       = 0;
+        bool pending = false;
+        for (u32 base = 0; base < ncur; base += 32) {
+            const u32 k = base + lane;
+            u32 emit = 0, o0 = 0, o1 = 0;
+            if (k < ncur) {
+                const u32 id = cur[k];
+                if (id >= I) { // leaves are left to the group walks
+                    emit = 1;
+                    o0   = id;
+                } else {
+                    NodeRegs n = load_node(nodes + id);
+                    f64 r      = n.rint * Rkern;
+                    f64 x1 = n.hi0 + r, y1 = n.hi1 + r, z1 = n.hi2 + r;
+                    f64 x0 = n.lo0 - r, y0 = n.lo1 - r, z0 = n.lo2 - r;
+                    bool hit = ((l0 <= x1) & (x0 <= h0) & (l1 <= y1) & (y0 <= h1) & (l2 <= z1) & (z0 <= h2))
+                               | ((p0 <= n.hi0) & (n.lo0 <= q0) & (p1 <= n.hi1) & (n.lo1 <= q1) & (p2 <= n.hi2)
+                                  & (n.lo2 <= q2));
+                    if (hit) {
+                        emit    = 2;
+                        o0      = n.left;
+                        o1      = n.right;
+                        pending = true;
+                    }
+                }
+            }
+            const u32 b1 = __ballot_sync(0xffffffffu, emit >= 1), b2 = __ballot_sync(0xffffffffu, emit == 2);
+            const u32 off = nn + __popc(b1 & lt) + __popc(b2 & lt);
+            if (emit >= 1)
+                nxt[off] = o0; // ncur < 64 on entry: at most 126 entries
+            if (emit == 2)
+                nxt[off + 1] = o1;
+            nn += __popc(b1) + __popc(b2);
+        }
+        u32 *t = cur;
+        cur    = nxt;
+        nxt    = t;
+        ncur   = nn;
+        if (!__any_sync(0xffffffffu, pending) || ncur >= TOP_CAP / 2)
+            break;
+    }
+    __syncwarp();
+    for (u32 k = lane; k < ncur; k += 32)
+        top_front[u64(sg) * TOP_CAP + k] = cur[k];
+    if (lane == 0)
+        top_count[sg] = ncur;
+}
+
 /// The reference walks the tree once per leaf a and keeps the leaves b with
 ///   hit(a, b) = cella_neigh_b(a, b ⊕ rint_b·R) || cella_neigh_b(a ⊕ rint_a·R, b);
 /// internal nodes are pruned with the same test.  Boxes and rint only grow towards the root and every
@@ -179,7 +284,8 @@ __device__ __forceinline__ f64 warp_max8(f64 v) {
 /// Output per group: (first rank, mask << 24 | length) of the candidate leaves in ascending rank order.
 __global__ void __launch_bounds__(WALK_WARPS * 32, 32) group_walk_kernel(
     const NodePack *__restrict__ nodes, u32 I, u32 L, const u32 *__restrict__ real_prefix, f64 Rkern, u32 F, u32 capG,
-    uint2 *__restrict__ gcand, u32 *__restrict__ gcount, u32 *__restrict__ flags) {
+    const u32 *__restrict__ top_front, const u32 *__restrict__ top_count, uint2 *__restrict__ gcand,
+    u32 *__restrict__ gcount, u32 *__restrict__ flags) {
     extern __shared__ __align__(16) unsigned char walk_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t per_warp = sizeof(LeafBox) * (GL + 1) + size_t(2) * F * sizeof(uint2);
@@ -236,10 +342,14 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, 32) group_walk_kernel(
         u.lo[0] = l0, u.lo[1] = l1, u.lo[2] = l2, u.hi[0] = h0, u.hi[1] = h1, u.hi[2] = h2;
         u.e0[0] = p0, u.e0[1] = p1, u.e0[2] = p2, u.e1[0] = q0, u.e1[1] = q1, u.e1[2] = q2;
         lb[GL]  = u;
-        cur[0]  = make_uint2(0u, vmask << 24);
     }
-    const LeafBox &U = lb[GL]; // root (node 0; when I == 0 it is the only leaf); length 0: not tested yet
-    u32 ncur  = 1;
+    const LeafBox &U = lb[GL];
+    // start: the frontier the super-group's top walk left (untested nodes, left to right); entries are
+    // (node, members to test << 24 | 0) — length 0 marks a node that is not tested yet
+    const u32 ncur0 = top_count[g / SUPER];
+    for (u32 k = lane; k < ncur0; k += 32)
+        cur[k] = make_uint2(top_front[u64(g / SUPER) * TOP_CAP + k], vmask << 24);
+    u32 ncur  = ncur0;
     bool more = true;
     while (more) {
         __syncwarp();
@@ -611,7 +721,8 @@ __global__ void __launch_bounds__(S2_WARPS * 32, 4) neigh_lists_kernel(
 }
 
 void search_build(
-    cudaStream_t s, const TreeBuffers &tb, SearchBuffers &sb, const f64 *d_rint, f64 Rkern, f64 h_tolerance) {
+    cudaStream_t s, const TreeBuffers &tb, SearchBuffers &sb, const f64 *d_rint, f64 Rkern, f64 h_tolerance,
+    const std::function<void(const char *)> &mark) {
     const u32 I = tb.I, L = tb.L;
     sb.nodes.ensure(size_t(I) + L, 1.1);
     pack_nodes_kernel<<<grid_for(size_t(I) + L, 256), 256, 0, s>>>(
@@ -644,9 +755,19 @@ void search_build(
             throw std::runtime_error("neighbour search: the tree-walk frontier of one leaf group exceeds shared memory");
         sb.gcand.ensure(size_t(G) * sb.group_cap, 1.1);
         SB_CUDA_CHECK(cudaMemsetAsync(sb.scalars.p + 2, 0, 3 * sizeof(u64), s));
-        group_walk_kernel<<<grid_for(G, WALK_WARPS), WALK_WARPS * 32, per_warp * WALK_WARPS, s>>>(
-            sb.nodes.p, I, L, sb.real_prefix.p, Rkern, sb.frontier_cap, sb.group_cap, sb.gcand.p, sb.gcount.p, d_flags);
+        if (mark)
+            mark("neigh_walk");
+        const u32 S = (G + SUPER - 1) / SUPER;
+        sb.top_front.ensure(size_t(S) * TOP_CAP, 1.1);
+        sb.top_count.ensure(S, 1.1);
+        top_walk_kernel<<<S, 32, 0, s>>>(sb.nodes.p, I, L, sb.real_prefix.p, Rkern, sb.top_front.p, sb.top_count.p);
         SB_COUNT_LAUNCH();
+        group_walk_kernel<<<grid_for(G, WALK_WARPS), WALK_WARPS * 32, per_warp * WALK_WARPS, s>>>(
+            sb.nodes.p, I, L, sb.real_prefix.p, Rkern, sb.frontier_cap, sb.group_cap, sb.top_front.p, sb.top_count.p,
+            sb.gcand.p, sb.gcount.p, d_flags);
+        SB_COUNT_LAUNCH();
+        if (mark)
+            mark("neigh_lists");
         neigh_lists_kernel<<<G, S2_WARPS * 32, s2_bytes, s>>>(
             sb.nodes.p, I, L, sb.SA.p, sb.real_flag.p, sb.real_prefix.p, sb.gcand.p, sb.group_cap, sb.gcount.p, Rker2,
             h_tolerance, u64(sb.list_s.cap), d_cursor, sb.cnt_s.p, sb.off_s.p, sb.list_s.p);

@@ -6,6 +6,7 @@
 #pragma once
 #include "sph.cuh"
 #include "tree.cuh"
+#include <functional>
 
 namespace sb {
 
@@ -31,6 +32,7 @@ struct SearchBuffers {
     DevBuf<u32> slot_rank;   // [N] rank of slot k
     DevBuf<uint2> gcand;     // [G * group_cap] (first rank, member mask << 24 | length) per candidate leaf
     DevBuf<u32> gcount;      // [G]
+    DevBuf<u32> top_front, top_count; // start frontiers of the group walks, one per 64 groups
     DevBuf<u32> cnt_s, off_s; // [N]
     DevBuf<u32> list_s;       // [K] ranks, ascending inside each list; lists of one leaf contiguous
     DevBuf<u32> scan_tmp;
@@ -59,8 +61,11 @@ void search_prepare_sorted_strided(
     cudaStream_t s, const TreeBuffers &tb, SearchBuffers &sb, const f64 *xyz, size_t stride, const f64 *h,
     size_t hstride, u32 N);
 /// the search proper (two-stage criterion of the reference).  Synchronises once (list sizing).
+/// `mark(name)`, when given, is called on the stream before the walk ("neigh_walk") and before the list
+/// kernel ("neigh_lists"): stage timing of the caller.
 void search_build(
-    cudaStream_t s, const TreeBuffers &tb, SearchBuffers &sb, const f64 *d_rint, f64 Rkern, f64 h_tolerance);
+    cudaStream_t s, const TreeBuffers &tb, SearchBuffers &sb, const f64 *d_rint, f64 Rkern, f64 h_tolerance,
+    const std::function<void(const char *)> &mark = {});
 /// ObjectCache layout of the reference (cnt / scanned by id, ids).  Synchronises.
 void export_object_cache(cudaStream_t s, const TreeBuffers &tb, SearchBuffers &sb);
 

@@ -675,7 +675,9 @@ void Model::start_neighbors_cache() {
     for (auto &p : patches)
         if (is_local(p) && p.f.n) {
             search_prepare_sorted(s(), p.st.tree, p.st.srch, p.st.A.p, p.st.n);
-            search_build(s(), p.st.tree, p.st.srch, p.st.rint.p, Rkern, cfg.htol_up_coarse_cycle);
+            search_build(
+                s(), p.st.tree, p.st.srch, p.st.rint.p, Rkern, cfg.htol_up_coarse_cycle,
+                [&](const char *name) { timer.mark(s(), name); });
             K_local += p.st.srch.K;
         }
 }
@@ -692,7 +694,7 @@ void Model::sph_prestep() {
         build_merged_pos_trees();
         timer.mark(s(), "rint");
         compute_presteps_rint();
-        timer.mark(s(), "neigh_cache");
+        timer.mark(s(), "neigh_prepare"); // sorted storage + packed nodes; then "neigh_walk", "neigh_lists"
         start_neighbors_cache();
         timer.mark(s(), "h_iteration");
         if (cfg.gpart_mass == 0)

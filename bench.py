@@ -52,20 +52,27 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None  # host time window of the timed region
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i",
                  str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
             self.proc = None
 
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.time()] + [c.strip() for c in line.split(",")])
 
     def stop(self):
         if not self.proc:
@@ -76,7 +83,10 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        # nvidia-smi needs ~1 s to start: it is launched before the warm-up and only the samples taken
+        # between begin() and end() (the timed region) count
+        rows = [r[1:] for r in self.rows if self.t0 is None or self.t0 <= r[0] <= (self.t1 or r[0])]
+        for r in rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -176,7 +186,7 @@ def cpu_baseline(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--npart-per-gpu", type=int, default=16 * 2**20)
     ap.add_argument("--cpu-sample", type=int, default=400000)
@@ -243,6 +253,9 @@ def main():
         m.set_next_dt(0.0)
         m.evolve_once()
 
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
     fp64_peak = ctx.microbench("fp64")
     copy_bw = ctx.microbench("copy")
 
@@ -254,9 +267,6 @@ def main():
     n_local = int(st["n_local"])
     n_total = int(st["npart"])
 
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     _capi.reset_launch_count()
     stage_acc = {}
 
@@ -265,7 +275,9 @@ def main():
         for k, v in m.stage_times().items():
             stage_acc[k] = stage_acc.get(k, 0.0) + v
 
+    clocks.begin()
     ms = timed(step_acc, args.steps)
+    clocks.end()
     launches = _capi.launch_count()
     clk = clocks.stop() if rank == 0 else None
     st = m.state()

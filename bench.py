@@ -102,12 +102,22 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def workload(npart_per_gpu, n_gpus, kernel="M4"):
+def workload(npart_per_gpu, n_gpus, kernel="M4", rank=0, count_reduce=None):
     from tests import scenarios as S
 
-    # weak scaling: box stretched along x, patch grid = n_gpus slabs (power of two)
+    # weak scaling: box stretched along x, patch grid = n_gpus slabs (power of two).  With several ranks
+    # each one generates only the particles of its own patches (the global count is all-reduced)
+    local_boxes = None
+    if n_gpus > 1 and count_reduce is not None:
+        from shamrock_b200 import _capi
+
+        def local_boxes(bmin, bmax):
+            boxes, owner = _capi.plan_patch_grid(bmin, bmax, (n_gpus, 1, 1), n_gpus)
+            return [(boxes[k][0], boxes[k][1]) for k in range(len(owner)) if owner[k] == rank]
+
     sc = S.periodic_box(npart_per_gpu * n_gpus, kernel, "cd10", jitter=0.0, grid=(n_gpus, 1, 1),
-                        stretch=(n_gpus, 1, 1), sort_mode="radix")
+                        stretch=(n_gpus, 1, 1), sort_mode="radix", local_boxes=local_boxes,
+                        count_reduce=count_reduce)
     return sc
 
 
@@ -222,7 +232,12 @@ def main():
         dist.broadcast_object_list(ids, src=0)
         nccl_id = ids[0]
 
-    sc = workload(args.npart_per_gpu, world)
+    def count_reduce(n_local):
+        t = torch.tensor([n_local], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        return int(t.item())
+
+    sc = workload(args.npart_per_gpu, world, rank=rank, count_reduce=count_reduce if world > 1 else None)
     ctx = _capi.Context(local)
     m = S.make_cuda(sc, ctx=ctx, keep_step_data=False, rank=rank, world=world, nccl_id=nccl_id, fp_mode=args.fp)
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))

@@ -26,16 +26,30 @@ def m4_w(q):
 
 
 def periodic_box(n_target, kernel="M4", av="cd10", jitter=0.0, seed=42, grid=(1, 1, 1), stretch=(1, 1, 1),
-                 two_stage=True, inject=True, sort_mode="bitonic"):
+                 two_stage=True, inject=True, sort_mode="bitonic", local_boxes=None, count_reduce=None):
     """sph_homogeneous_benchmark.py: HCP lattice in a periodic box, adiabatic gamma=5/3, CD10 AV,
-    uint kernel injection at the origin, C_cour=C_force=0.1."""
+    uint kernel injection at the origin, C_cour=C_force=0.1.
+
+    Multi-rank setup: `local_boxes(bmin, bmax)` returns the [lo, hi) boxes of this rank's patches and only
+    their particles are generated; `count_reduce(n_local)` returns the global particle count (an
+    all-reduce) that fixes the particle mass.  Same particles as the single-process call, rank by rank."""
     half = np.array([0.6 * stretch[0], 0.6 * stretch[1], 0.6 * stretch[2]])
     vol = float(np.prod(2 * half))
     # HCP: one particle per dr^3 * sqrt(2) * 4  (cell volume per particle = 4 sqrt(2) dr^3)
     dr = (vol / (n_target * 4 * math.sqrt(2))) ** (1.0 / 3.0)
     bmin, bmax = lattice.get_ideal_hcp_box(dr, tuple(-half), tuple(half))
-    pos = lattice.hcp_positions(dr, bmin, bmax)
-    n = len(pos)
+    if local_boxes is None:
+        pos = lattice.hcp_positions(dr, bmin, bmax)
+        n = len(pos)
+    else:
+        parts = []
+        for lo, hi in local_boxes(bmin, bmax):
+            # the lattice points of the whole box that fall into [lo, hi): clip the patch to the box first
+            lo_c = [max(a, b) for a, b in zip(lo, bmin)]
+            hi_c = [min(a, b) for a, b in zip(hi, bmax)]
+            parts.append(lattice.hcp_positions(dr, lo_c, hi_c))
+        pos = np.concatenate(parts) if parts else np.zeros((0, 3))
+        n = int(count_reduce(len(pos)))
     rng = np.random.default_rng(seed)
     if jitter > 0:
         pos = pos + rng.uniform(-jitter * dr, jitter * dr, size=pos.shape)
@@ -46,8 +60,8 @@ def periodic_box(n_target, kernel="M4", av="cd10", jitter=0.0, seed=42, grid=(1,
     vol = float(np.prod(np.array(bmax) - np.array(bmin)))
     rho = 1.0
     pmass = rho * vol / n
-    h = np.full(n, HFACT[kernel] * (pmass / rho) ** (1.0 / 3.0))
-    u = np.full(n, 1.0)
+    h = np.full(len(pos), HFACT[kernel] * (pmass / rho) ** (1.0 / 3.0))
+    u = np.full(len(pos), 1.0)
     if inject:
         r = np.linalg.norm(pos, axis=1)
         hi = 16 * dr

@@ -102,6 +102,27 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Run this process on the CPUs next to its GPU (NVML affinity mask) before any page-locked host memory
+    is allocated: the host patch data of the e2e leg then sits on the NUMA node the GPU's PCIe link hangs
+    off, instead of wherever the launcher started the process."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+        old = os.sched_getaffinity(0)
+        cpus &= old
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return old
+    except Exception:
+        return None
+
+
 def workload(npart_per_gpu, n_gpus, kernel="M4", rank=0, count_reduce=None):
     from tests import scenarios as S
 
@@ -224,6 +245,7 @@ def main():
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
     torch.cuda.set_device(local)
+    cpus_before = bind_to_gpu_numa_node(local)
     nccl_id = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -390,6 +412,8 @@ def main():
             "h_subcycles": st["h_subcycles"], "corrector_iter": st["corrector_iter"],
         }
         if not args.no_cpu_baseline and world == 1:
+            if cpus_before:
+                os.sched_setaffinity(0, cpus_before)  # the CPU baseline uses every host core again
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line), flush=True)
     m.close()

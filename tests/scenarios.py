@@ -104,15 +104,28 @@ def sod_tube(resol=24, kernel="M6", grid=(2, 1, 1), sort_mode="bitonic"):
                 vxyz=np.zeros_like(pos), hpart=h, uint=u, kill=[], sort_mode=sort_mode, kernel=kernel, dr=dr)
 
 
-def disc(n=4000, kernel="M4", seed=7, grid=(1, 1, 1), sort_mode="bitonic"):
+def disc(n=4000, kernel="M4", seed=7, grid=(1, 1, 1), sort_mode="bitonic", regular=False):
     """Protoplanetary-disc-like cloud around a central point mass: free boundaries, LP07 locally
     isothermal EOS, ConstantDisc AV, accretion radius and a kill sphere
-    (run_circular_disc_central_pot.py:190-248, Monte-Carlo positions with a fixed seed)."""
+    (run_circular_disc_central_pot.py:190-248, Monte-Carlo positions with a fixed seed).
+    regular=True: the same flared volume filled with an HCP lattice instead of Monte-Carlo points (large
+    runs: Poisson clumps of an unrelaxed random sample leave a few particles whose h never converges —
+    in the reference's algorithm as well, the oracle shows it at 2e5 particles)."""
     rng = np.random.default_rng(seed)
     rin, rout, H_r = 1.0, 3.0, 0.08
-    r = np.sqrt(rng.uniform(rin**2, rout**2, n))
-    phi = rng.uniform(0, 2 * math.pi, n)
-    z = rng.uniform(-1.5, 1.5, n) * H_r * r  # truncated: isolated particles never converge in h
+    if regular:
+        vol = math.pi * (rout**2 - rin**2) * 3 * H_r * 2.0  # mean radius 2: thickness 3 H_r r
+        dr = (vol / (n * 4 * math.sqrt(2))) ** (1.0 / 3.0)
+        zmax = 1.5 * H_r * rout
+        p = lattice.hcp_positions(dr, (-rout, -rout, -zmax), (rout, rout, zmax))
+        rr = np.hypot(p[:, 0], p[:, 1])
+        p = p[(rr > rin * 1.05) & (rr < rout) & (np.abs(p[:, 2]) < 1.5 * H_r * rr)]
+        n = len(p)
+        r, phi, z = np.hypot(p[:, 0], p[:, 1]), np.arctan2(p[:, 1], p[:, 0]), p[:, 2]
+    else:
+        r = np.sqrt(rng.uniform(rin**2, rout**2, n))
+        phi = rng.uniform(0, 2 * math.pi, n)
+        z = rng.uniform(-1.5, 1.5, n) * H_r * r  # truncated: isolated particles never converge in h
     pos = np.stack([r * np.cos(phi), r * np.sin(phi), z], axis=1)
     G, Mc = 1.0, 1.0
     vk = np.sqrt(G * Mc / r)
@@ -122,6 +135,8 @@ def disc(n=4000, kernel="M4", seed=7, grid=(1, 1, 1), sort_mode="bitonic"):
     vol = math.pi * (rout**2 - rin**2) * 3 * H_r * 2.0
     nd = n / (math.pi * (rout**2 - rin**2)) / (3 * H_r * r)  # local number density
     h = HFACT[kernel] * nd ** (-1.0 / 3.0)
+    if regular:
+        h = np.full(n, HFACT[kernel] * (4 * math.sqrt(2)) ** (1.0 / 3.0) * dr)
     u = np.full(n, 1e-3)
     cfg = dict(kernel=KERNEL_ID[kernel], gpart_mass=pmass, eos=2, cs0=0.05, eos_q=0.25, eos_r0=1.0, av=4,
                alpha_u=1.0, alpha_AV=1.0, beta_AV=2.0, bc=0, cfl_cour=0.3, cfl_force=0.25, has_point_mass=1,

@@ -16,6 +16,7 @@
 // warp-per-leaf with the 32 lanes holding 32 CANDIDATES; the leaf's particles are broadcast from shared
 // memory, each (particle, chunk) produces one ballot word.  The fill pass replays the ballots only.
 #include "neigh2.cuh"
+#include <algorithm>
 
 namespace sb {
 
@@ -282,18 +283,25 @@ __global__ void __launch_bounds__(32) top_walk_kernel(
 /// then exactly against each member that still hit the parent; every entry carries the 8-bit mask of
 /// the members it hits, so the frontier is the union of the members' own walks and nothing more.
 /// Output per group: (first rank, mask << 24 | length) of the candidate leaves in ascending rank order.
+/// BIG = false: the frontier lives in shared memory (F entries); a group whose walk does not fit appends
+/// itself to `over_list`.  BIG = true: one block per group of `over_list`, frontier in global scratch (F = L
+/// entries: a frontier holds roots of disjoint subtrees, never more than there are leaves) — the few groups
+/// around a particle with a very large h (the reference searches those too, slowly).
+template<bool BIG>
 __global__ void __launch_bounds__(WALK_WARPS * 32, 32) group_walk_kernel(
-    const NodePack *__restrict__ nodes, u32 I, u32 L, const u32 *__restrict__ real_prefix, f64 Rkern, u32 F, u32 capG,
-    const u32 *__restrict__ top_front, const u32 *__restrict__ top_count, uint2 *__restrict__ gcand,
-    u32 *__restrict__ gcount, u32 *__restrict__ flags) {
+    const NodePack *__restrict__ nodes, u32 I, u32 L, const u32 *__restrict__ real_prefix, f64 Rkern, u32 F,
+    const u32 *__restrict__ top_front, const u32 *__restrict__ top_count, u64 ecap,
+    unsigned long long *__restrict__ ecursor, uint2 *__restrict__ gcand, u64 *__restrict__ gc_off,
+    u32 *__restrict__ gcount, u32 *__restrict__ flags, u32 *__restrict__ over_list, u32 over_cap,
+    uint2 *__restrict__ big_scratch) {
     extern __shared__ __align__(16) unsigned char walk_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t per_warp = sizeof(LeafBox) * (GL + 1) + size_t(2) * F * sizeof(uint2);
+    const size_t per_warp = sizeof(LeafBox) * (GL + 1) + (BIG ? 0 : size_t(2) * F * sizeof(uint2));
     LeafBox *lb = reinterpret_cast<LeafBox *>(walk_smem + warp * per_warp); // members, then their union
-    uint2 *cur  = reinterpret_cast<uint2 *>(lb + GL + 1);
+    uint2 *cur  = BIG ? big_scratch + u64(blockIdx.x) * 2 * F : reinterpret_cast<uint2 *>(lb + GL + 1);
     uint2 *nxt  = cur + F;
     const u32 G  = (L + GL - 1) / GL;
-    const u32 g  = blockIdx.x * WALK_WARPS + warp;
+    const u32 g  = BIG ? over_list[blockIdx.x] : blockIdx.x * WALK_WARPS + warp;
     const u32 lt = (1u << lane) - 1u;
     if (g >= G)
         return;
@@ -431,9 +439,13 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, 32) group_walk_kernel(
             nn += total;
         }
         more = __any_sync(0xffffffffu, pending);
-        if (nn > F) { // the frontier does not fit: the host repeats the search with a larger one
+        if (nn > F) { // the frontier does not fit: this group is walked again with a frontier in global memory
             if (lane == 0) {
-                atomicMax(flags + 0, nn);
+                u32 slot = atomicAdd(flags + 0, 1u);
+                if (slot < over_cap && !BIG)
+                    over_list[slot] = g;
+                if (BIG)
+                    atomicOr(flags + 2, 2u);
                 gcount[g] = 0;
             }
             return;
@@ -444,17 +456,22 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, 32) group_walk_kernel(
         ncur     = nn;
     }
     __syncwarp();
-    if (ncur > capG) {
-        if (lane == 0) {
-            atomicMax(flags + 1, ncur);
+    // output: a slice of the candidate-entry array reserved with one atomic
+    unsigned long long ebase = 0;
+    if (lane == 0)
+        ebase = atomicAdd(ecursor, (unsigned long long) ncur);
+    ebase = __shfl_sync(0xffffffffu, ebase, 0);
+    if (ebase + ncur > ecap) { // the host reads the cursor, grows the array and repeats the search
+        if (lane == 0)
             gcount[g] = 0;
-        }
         return;
     }
     for (u32 k = lane; k < ncur; k += 32)
-        gcand[u64(g) * capG + k] = cur[k];
-    if (lane == 0)
+        gcand[ebase + k] = cur[k];
+    if (lane == 0) {
+        gc_off[g] = ebase;
         gcount[g] = ncur;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -631,13 +648,14 @@ constexpr int S2_WARPS = GL; // one block = one group of leaves
 /// candidates or ballots do not fit the shared stores test again in pass 2 instead.
 __global__ void __launch_bounds__(S2_WARPS * 32, 4) neigh_lists_kernel(
     const NodePack *__restrict__ nodes, u32 I, u32 L, const Pack4 *__restrict__ SA, const u8 *__restrict__ real_flag,
-    const u32 *__restrict__ real_prefix, const uint2 *__restrict__ gcand, u32 capG, const u32 *__restrict__ gcount,
-    f64 Rker2, f64 h_tolerance, u64 list_cap, unsigned long long *__restrict__ cursor, u32 *__restrict__ cnt_s,
-    u32 *__restrict__ off_s, u32 *__restrict__ list_s) {
+    const u32 *__restrict__ real_prefix, const uint2 *__restrict__ gcand, const u64 *__restrict__ gc_off,
+    const u32 *__restrict__ gcount, const u32 *__restrict__ group_ids, f64 Rker2, f64 h_tolerance, u64 list_cap,
+    unsigned long long *__restrict__ cursor, u32 *__restrict__ cnt_s, u32 *__restrict__ off_s,
+    u32 *__restrict__ list_s) {
     extern __shared__ __align__(32) unsigned char s2_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const u32 lt   = (1u << lane) - 1u;
-    const u32 g    = blockIdx.x;
+    const u32 g    = group_ids ? group_ids[blockIdx.x] : blockIdx.x;
     const u32 leaf = g * GL + warp;
     if (leaf >= L)
         return;
@@ -650,7 +668,7 @@ __global__ void __launch_bounds__(S2_WARPS * 32, 4) neigh_lists_kernel(
     const u32 slot0 = real_prefix[p0];
     if (real_prefix[p1] == slot0)
         return; // no real particle in this leaf
-    const uint2 *gc = gcand + u64(g) * capG;
+    const uint2 *gc = gcand + gc_off[g];
     const u32 bit   = 1u << (24 + warp);
     u32 a_base      = 0;
     for (u32 rb = p0; rb < p1; rb += 32) {
@@ -731,6 +749,7 @@ void search_build(
     SB_COUNT_LAUNCH();
     const u32 G = (L + GL - 1) / GL;
     sb.gcount.ensure(G, 1.1);
+    sb.gc_off.ensure(G, 1.1);
     sb.cnt_s.ensure(sb.N, 1.1);
     sb.off_s.ensure(sb.N, 1.1);
     const f64 Rker2 = Rkern * Rkern;
@@ -738,23 +757,36 @@ void search_build(
     const size_t s2_bytes = sizeof(WarpScratch) * S2_WARPS;
     if (!attr_set) {
         SB_CUDA_CHECK(cudaFuncSetAttribute(neigh_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(s2_bytes)));
-        SB_CUDA_CHECK(cudaFuncSetAttribute(group_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SB_CUDA_CHECK(cudaFuncSetAttribute(
+            group_walk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
-    // list capacity: what the previous search of this patch needed (+ slack), ~96 entries per particle the
-    // first time.  ONE host synchronisation per search: it reads the list cursor (= K) and the largest
-    // frontier / candidate-leaf counts; if any ran past its capacity the exact need is known and the
-    // search is repeated.
+    // capacities: what the previous search of this patch needed (+ slack); the first time ~96 list entries
+    // per particle and ~24 candidate entries per leaf.  ONE host synchronisation per search: it reads the
+    // list cursor (= K), the candidate-entry cursor and the number of groups whose walk did not fit its
+    // shared-memory frontier; if a capacity was exceeded the exact need is known and the search is repeated.
     if (sb.list_s.cap == 0)
         sb.list_s.ensure(size_t(sb.N) * 96 + 1024);
-    u32 *d_flags                 = reinterpret_cast<u32 *>(sb.scalars.p + 2); // [0] frontier need, [1] candidate need, [2] errors
-    unsigned long long *d_cursor = reinterpret_cast<unsigned long long *>(sb.scalars.p + 4);
+    if (sb.gcand.cap == 0)
+        sb.gcand.ensure(size_t(L) * 24 + 4096);
+    constexpr u32 OVER_CAP = 1u << 16;
+    sb.over_list.ensure(OVER_CAP);
+    u32 *d_flags = reinterpret_cast<u32 *>(sb.scalars.p + 2); // [0] groups over the frontier, [2] errors
+    unsigned long long *d_cursor  = reinterpret_cast<unsigned long long *>(sb.scalars.p + 4);
+    unsigned long long *d_ecursor = reinterpret_cast<unsigned long long *>(sb.scalars.p + 6);
+    auto read_back = [&]() {
+        SB_CUDA_CHECK(cudaMemcpyAsync(sb.h_scalars.p + 2, sb.scalars.p + 2, 5 * sizeof(u64), cudaMemcpyDeviceToHost, s));
+        SB_CUDA_CHECK(cudaStreamSynchronize(s));
+        const u32 err = u32(sb.h_scalars.p[3] & 0xffffffffull);
+        if (err & 1u)
+            throw std::runtime_error("neighbour search: a tree leaf holds 2^24 or more objects");
+        if (err & 2u)
+            throw std::runtime_error("neighbour search: internal error, a global-memory frontier overflowed");
+    };
     for (int attempt = 0;; attempt++) {
         const size_t per_warp = sizeof(LeafBox) * (GL + 1) + size_t(2) * sb.frontier_cap * sizeof(uint2);
-        if (per_warp * WALK_WARPS > 200 * 1024)
-            throw std::runtime_error("neighbour search: the tree-walk frontier of one leaf group exceeds shared memory");
-        sb.gcand.ensure(size_t(G) * sb.group_cap, 1.1);
-        SB_CUDA_CHECK(cudaMemsetAsync(sb.scalars.p + 2, 0, 3 * sizeof(u64), s));
+        const u64 ecap        = sb.gcand.cap;
+        SB_CUDA_CHECK(cudaMemsetAsync(sb.scalars.p + 2, 0, 5 * sizeof(u64), s));
         if (mark)
             mark("neigh_walk");
         const u32 S = (G + SUPER - 1) / SUPER;
@@ -762,32 +794,48 @@ void search_build(
         sb.top_count.ensure(S, 1.1);
         top_walk_kernel<<<S, 32, 0, s>>>(sb.nodes.p, I, L, sb.real_prefix.p, Rkern, sb.top_front.p, sb.top_count.p);
         SB_COUNT_LAUNCH();
-        group_walk_kernel<<<grid_for(G, WALK_WARPS), WALK_WARPS * 32, per_warp * WALK_WARPS, s>>>(
-            sb.nodes.p, I, L, sb.real_prefix.p, Rkern, sb.frontier_cap, sb.group_cap, sb.top_front.p, sb.top_count.p,
-            sb.gcand.p, sb.gcount.p, d_flags);
+        group_walk_kernel<false><<<grid_for(G, WALK_WARPS), WALK_WARPS * 32, per_warp * WALK_WARPS, s>>>(
+            sb.nodes.p, I, L, sb.real_prefix.p, Rkern, sb.frontier_cap, sb.top_front.p, sb.top_count.p, ecap, d_ecursor,
+            sb.gcand.p, sb.gc_off.p, sb.gcount.p, d_flags, sb.over_list.p, OVER_CAP, nullptr);
         SB_COUNT_LAUNCH();
         if (mark)
             mark("neigh_lists");
         neigh_lists_kernel<<<G, S2_WARPS * 32, s2_bytes, s>>>(
-            sb.nodes.p, I, L, sb.SA.p, sb.real_flag.p, sb.real_prefix.p, sb.gcand.p, sb.group_cap, sb.gcount.p, Rker2,
-            h_tolerance, u64(sb.list_s.cap), d_cursor, sb.cnt_s.p, sb.off_s.p, sb.list_s.p);
+            sb.nodes.p, I, L, sb.SA.p, sb.real_flag.p, sb.real_prefix.p, sb.gcand.p, sb.gc_off.p, sb.gcount.p, nullptr,
+            Rker2, h_tolerance, u64(sb.list_s.cap), d_cursor, sb.cnt_s.p, sb.off_s.p, sb.list_s.p);
         SB_COUNT_LAUNCH();
-        SB_CUDA_CHECK(cudaMemcpyAsync(sb.h_scalars.p + 2, sb.scalars.p + 2, 3 * sizeof(u64), cudaMemcpyDeviceToHost, s));
-        SB_CUDA_CHECK(cudaStreamSynchronize(s));
-        const u32 need_f = u32(sb.h_scalars.p[2] & 0xffffffffull), need_c = u32(sb.h_scalars.p[2] >> 32);
-        const u32 err    = u32(sb.h_scalars.p[3] & 0xffffffffull);
-        sb.K             = sb.h_scalars.p[4];
-        if (err)
-            throw std::runtime_error("neighbour search: a tree leaf holds 2^24 or more objects");
-        bool redo = false;
-        if (need_f > sb.frontier_cap) { // rare: the walk of a group holds more nodes than its frontier
-            while (sb.frontier_cap < need_f)
-                sb.frontier_cap *= 2;
+        read_back();
+        u32 n_over = u32(sb.h_scalars.p[2] & 0xffffffffull);
+        bool redo  = false;
+        // many groups over the frontier: a larger shared-memory frontier for everybody; a few (the
+        // surroundings of a particle with a very large h): those groups again with a frontier in global memory
+        if (n_over > OVER_CAP || (n_over > G / 64 && sb.frontier_cap < 2048)) {
+            if (sb.frontier_cap >= 8192)
+                throw std::runtime_error("neighbour search: too many leaf groups need a very large tree-walk frontier");
+            sb.frontier_cap *= 2;
             redo = true;
+        } else if (n_over > 0 && sb.h_scalars.p[6] <= ecap) {
+            const u64 budget = 4ull << 30; // scratch for the global frontiers, groups in batches
+            const u32 batch  = u32(std::max<u64>(1, std::min<u64>(n_over, budget / (u64(2) * L * sizeof(uint2)))));
+            sb.big_scratch.ensure(size_t(batch) * 2 * L);
+            for (u32 b0 = 0; b0 < n_over; b0 += batch) {
+                const u32 nb = std::min(batch, n_over - b0);
+                group_walk_kernel<true><<<nb, WALK_WARPS * 32, sizeof(LeafBox) * (GL + 1), s>>>(
+                    sb.nodes.p, I, L, sb.real_prefix.p, Rkern, L, sb.top_front.p, sb.top_count.p, ecap, d_ecursor,
+                    sb.gcand.p, sb.gc_off.p, sb.gcount.p, d_flags, sb.over_list.p + b0, OVER_CAP, sb.big_scratch.p);
+                SB_COUNT_LAUNCH();
+                neigh_lists_kernel<<<nb, S2_WARPS * 32, s2_bytes, s>>>(
+                    sb.nodes.p, I, L, sb.SA.p, sb.real_flag.p, sb.real_prefix.p, sb.gcand.p, sb.gc_off.p, sb.gcount.p,
+                    sb.over_list.p + b0, Rker2, h_tolerance, u64(sb.list_s.cap), d_cursor, sb.cnt_s.p, sb.off_s.p,
+                    sb.list_s.p);
+                SB_COUNT_LAUNCH();
+            }
+            read_back();
         }
-        if (need_c > sb.group_cap) { // rare: a group sees more candidate leaves than its slot holds
-            while (sb.group_cap < need_c)
-                sb.group_cap *= 2;
+        const u64 need_e = sb.h_scalars.p[6];
+        sb.K             = sb.h_scalars.p[4];
+        if (need_e > ecap) { // the candidate-entry array is too small
+            sb.gcand.ensure(need_e, 1.25);
             redo = true;
         }
         if (!redo && sb.K > 0xFFFFFFFFull)

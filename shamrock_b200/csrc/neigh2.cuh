@@ -22,7 +22,6 @@ constexpr int GL = 8; ///< leaves per walk group (the member mask lives in the t
 struct SearchBuffers {
     u32 N = 0, M = 0, L = 0, I = 0;
     u64 K        = 0; ///< total neighbour count
-    u32 group_cap    = 192; ///< candidate leaves kept per group (doubled on demand)
     u32 frontier_cap = 320; ///< walk frontier entries per group in shared memory (doubled on demand)
     DevBuf<NodePack> nodes;  // [I+L]
     DevBuf<Pack4> SA;        // [M] (x,y,z,h) in sorted order
@@ -30,8 +29,11 @@ struct SearchBuffers {
     DevBuf<u8> real_flag;    // [M+1]
     DevBuf<u32> real_prefix; // [M+1] exclusive scan of real_flag over ranks (slot of a real rank)
     DevBuf<u32> slot_rank;   // [N] rank of slot k
-    DevBuf<uint2> gcand;     // [G * group_cap] (first rank, member mask << 24 | length) per candidate leaf
-    DevBuf<u32> gcount;      // [G]
+    DevBuf<uint2> gcand;     // (first rank, member mask << 24 | length) per candidate leaf, group after group
+    DevBuf<u64> gc_off;      // [G] first entry of group g
+    DevBuf<u32> gcount;      // [G] number of entries of group g
+    DevBuf<u32> over_list;   // groups whose walk did not fit the shared-memory frontier
+    DevBuf<uint2> big_scratch; // their frontiers in global memory
     DevBuf<u32> top_front, top_count; // start frontiers of the group walks, one per 64 groups
     DevBuf<u32> cnt_s, off_s; // [N]
     DevBuf<u32> list_s;       // [K] ranks, ascending inside each list; lists of one leaf contiguous

@@ -176,6 +176,34 @@ def test_neighbour_cache_bit_exact(ctx, kernel, two_stage, kind, n):
     assert np.array_equal(fetch(cv.d_index_neigh_map, cv.sum_neigh_cnt, np.uint32), cref["index_neigh_map"])
 
 
+@pytest.mark.parametrize("kernel", ["M4", "M6"])
+def test_neighbour_cache_outlier_h(ctx, kernel):
+    """A few particles with a smoothing length of the size of the box (what an unconverged h iteration leaves
+    behind): their leaf groups see thousands of candidate leaves, far beyond the shared-memory frontier of the
+    tree walk — those groups are walked with a frontier in global memory and the lists stay bit-exact."""
+    R = {"M4": 2.0, "M6": 3.0}[kernel]
+    n = 30000
+    xyz = positions("uniform", n, 5)
+    rng = np.random.default_rng(9)
+    h = (0.7 / n ** (1 / 3)) * rng.uniform(0.8, 1.3, n)
+    h[[17, 4711, 20000]] = [0.25, 0.4, 0.1]
+    bb = ([0.0, 0.0, 0.0], [1.0, 1.0, 1.0])
+    ref = po.Tree(xyz, *bb, 3, bits=32)
+    ref.field_max(h, 1.1)
+    cref = ref.neigh_cache(h, n, R, 1.1, True)
+    dx, dh = dev(xyz), dev(h)
+    tv = ctx.tree_build(dx, n, *bb, reduction_level=3, sort_mode="bitonic")
+    rint = torch.empty(tv.leaf_count + tv.int_count, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    ctx.tree_field_max(tv, dh, 1.1, rint)
+    cv = ctx.neigh_cache_build(tv, dx, dh, rint, n, R, 1.1, True)
+    ctx.synchronize()
+    assert cref["cnt_neigh"].max() > 5000  # the outliers really see a large part of the box
+    assert cv.sum_neigh_cnt == len(cref["index_neigh_map"])
+    assert np.array_equal(fetch(cv.d_cnt_neigh, n, np.uint32), cref["cnt_neigh"])
+    assert np.array_equal(fetch(cv.d_index_neigh_map, cv.sum_neigh_cnt, np.uint32), cref["index_neigh_map"])
+
+
 def test_neighbour_cache_brute_force(ctx):
     """independent of the oracle: list == all pairs passing the accept test, in sorted-Morton rank"""
     n, R, tol = 3000, 2.0, 1.1

@@ -25,11 +25,12 @@ def main():
     ap.add_argument("--npart", type=int, default=8 * 2**20)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--fp", default="fast")
+    ap.add_argument("--mc", action="store_true", help="C5: Monte-Carlo positions instead of the regular lattice")
     a = ap.parse_args()
     if a.config == "C3":
         sc = S.periodic_box(a.npart, "M6", "cd10", sort_mode="radix")
     elif a.config == "C5":
-        sc = S.disc(a.npart, "M4", sort_mode="radix", regular=True)
+        sc = S.disc(a.npart, "M4", sort_mode="radix", regular=not a.mc)
     elif a.config == "C1":
         sc = sod_tube.scenario(kernel="M4")
         sc["sort_mode"] = "radix"

@@ -263,3 +263,18 @@ def test_evolve_once_host_matches_device_resident(scenario):
             assert np.array_equal(got, want, equal_nan=True), f"step {step} {nm}"
         n = n_new
         assert m.state()["dt"] == ref.state()["dt"]
+
+
+def test_bench_path_fields_match_oracle():
+    """The configuration bench.py times (fast fp, keep_step_data = 0) against the oracle: every main-layout
+    field within 1e-10 after three steps."""
+    sc = S.periodic_box(6000, "M4", "cd10", jitter=0.1)
+    o = S.make_oracle(sc)
+    m = S.make_cuda(sc, fp_mode="fast", keep_step_data=False)
+    for _ in range(3):
+        so, sm = o.evolve_once(), m.evolve_once()
+    floors = term_floors(o, 0)
+    for nm in ("xyz", "vxyz", "hpart", "uint", "axyz", "duint", "alpha_AV", "divv", "dtdivv", "curlv", "soundspeed"):
+        ok, msg = close(m.get(0, nm), o.get(0, nm), 1e-10, floors.get(nm, 0.0))
+        assert ok, f"{nm}: {msg}"
+    assert abs(sm["dt"] - so["dt"]) <= 1e-10 * abs(so["dt"])

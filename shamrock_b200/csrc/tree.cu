@@ -296,27 +296,57 @@ __global__ void __launch_bounds__(RADIX_THREADS) radix_scatter_kernel(
         __syncwarp();
     }
     __syncthreads();
-    // per digit: exclusive prefix over the warps of this CTA, plus the global offset
+    // per digit: exclusive prefix over the warps of this CTA; then the CTA-local start of every digit
+    // (block scan over the 256 digit counts) and the global offset of the CTA's run of that digit
+    __shared__ u32 dstart[256], gofs[256], wtot[NW];
+    __shared__ u32 skey[RADIX_TILE], sval[RADIX_TILE];
     {
         u32 d   = threadIdx.x;
-        u32 run = offsets[d * nblocks + blockIdx.x];
+        u32 run = 0;
 #pragma unroll
         for (int ww = 0; ww < NW; ww++) {
             u32 c        = whist[ww][d];
             whist[ww][d] = run;
             run += c;
         }
+        u32 inc = run; // inclusive scan of the digit counts inside the warp
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            u32 t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o)
+                inc += t;
+        }
+        if (lane == 31)
+            wtot[w] = inc;
+        __syncthreads();
+        u32 before = 0;
+#pragma unroll
+        for (int ww = 0; ww < NW; ww++)
+            before += ww < w ? wtot[ww] : 0u;
+        dstart[d] = before + inc - run;
+        gofs[d]   = offsets[d * nblocks + blockIdx.x] - (before + inc - run);
     }
     __syncthreads();
+    // stage the tile in digit order in shared memory (stable: warp, round, lane = input order) ...
 #pragma unroll
     for (int r = 0; r < RADIX_ITEMS; r++) {
         u32 i = wbase + r * 32 + lane;
         if (i < n) {
-            u32 d   = (k[r] >> shift) & 0xFF;
-            u32 pos = whist[w][d] + rank[r];
-            keys_out[pos] = k[r];
-            vals_out[pos] = v[r];
+            u32 d    = (k[r] >> shift) & 0xFF;
+            u32 lp   = dstart[d] + whist[w][d] + rank[r];
+            skey[lp] = k[r];
+            sval[lp] = v[r];
         }
+    }
+    __syncthreads();
+    // ... and write it out: consecutive threads write consecutive addresses inside each digit's run
+    const u32 tile0 = blockIdx.x * RADIX_TILE;
+    const u32 ntile = n - tile0 < u32(RADIX_TILE) ? n - tile0 : u32(RADIX_TILE);
+    for (u32 i = threadIdx.x; i < ntile; i += RADIX_THREADS) {
+        u32 kk  = skey[i];
+        u32 pos = gofs[(kk >> shift) & 0xFF] + i;
+        keys_out[pos] = kk;
+        vals_out[pos] = sval[i];
     }
 }
 
@@ -572,7 +602,8 @@ void tree_build(
     if (sort_mode == SORT_RADIX) {
         t.morton_alt.ensure(t.P2);
         t.index_alt.ensure(t.P2);
-        radix_sort_by_key(s, t.morton.p, t.index_map.p, t.morton_alt.p, t.index_alt.p, t.P2, 32, t.radix_hist);
+        // only the M real keys: the padding (0xFFFFFFFF, above every 30-bit code) is already in place behind them
+        radix_sort_by_key(s, t.morton.p, t.index_map.p, t.morton_alt.p, t.index_alt.p, M, 32, t.radix_hist);
     } else {
         bitonic_sort_by_key(s, t.morton.p, t.index_map.p, t.P2);
     }

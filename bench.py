@@ -146,14 +146,14 @@ def workload(npart_per_gpu, n_gpus, kernel="M4", rank=0, count_reduce=None):
 # M merged, N real, K = sum of list lengths, K_acc ~ K / htol^3 pairs inside the kernel support, L leaves.
 # Flop convention: FMA = 2, div / sqrt = 1; candidate test 10, density pair 39, div+curl+dtdivv 175,
 # force + v_sig 155 per accepted pair.
-def alg_work(stage, N, M, K, L, sweeps):
+def alg_work(stage, N, M, K, L, sweeps, tests=0):
     K_acc = K / 1.1**3
     return {
         # the search = one tree walk per group of 8 leaves + the accept / fill kernel; SURVEY.md §8d's figure
         # for the whole cache (64 M + 4 K + 12 N) split over the two launches: packed nodes (64 B, I + L = 2 L)
         # and candidate entries for the walk; sorted records (32 B), list and count / offset writes for the lists
         "neigh_walk": (64 * 2 * L + 8 * 12 * L, 30.0 * 2 * L),
-        "neigh_lists": (32 * M + 4 * K + 8 * N, 10.0 * K),
+        "neigh_lists": (32 * M + 4 * K + 8 * N, 10.0 * (tests or K)),  # one accept test per (particle, candidate)
         "h_iteration": (4 * K + 32 * M + 40 * N, (sweeps + 1) * (10.0 * K + 39.0 * K_acc)),
         "divv_curlv_dtdivv": (4 * K + 96 * M + 40 * N, 10.0 * K + 175.0 * K_acc),
         "forces": (4 * K + 128 * M + 64 * N, 10.0 * K + 155.0 * K_acc),
@@ -362,12 +362,13 @@ def main():
         # stage = device time between CUDA-event marks on the step's stream; each heavy stage is ONE kernel
         # (h_solve / av_operators / force_cfl) or the search kernels.  Roof = slower of HBM and FP64 pipe.
         N, K = n_local, int(st["K_local"])
+        tests = m.search_stats()[1]
         M, L = int(N * 1.0), int(N / 3.6)  # ~3.6 objects per leaf at reduction level 3 on the HCP lattice
         sweeps = int(st["h_iters_last"]) + 1
         per_stage = {k: v / args.steps for k, v in stage_acc.items()}
         table = {}
         for k, ms_k in per_stage.items():
-            w = alg_work(k, N, M, K, L, sweeps)
+            w = alg_work(k, N, M, K, L, sweeps, tests)
             if not w:
                 continue
             t_hbm, t_fp = w[0] / (hbm_peak * 1e9), (w[1] / (fp64_peak * 1e12) if fp64_peak else 0.0)
@@ -387,8 +388,9 @@ def main():
                     "achieved": tt["TFLOP/s"] if tt["bound"] == "fp64" else tt["GB/s"],
                     "peak": fp64_peak if tt["bound"] == "fp64" else hbm_peak,
                     "unit": "TFLOP/s" if tt["bound"] == "fp64" else "GB/s", "frac": tt["frac"], "traffic": traffic, "traffic_source": traffic_src,
-                    "algorithmic_bytes": alg_work(top, N, M, K, L, sweeps)[0],
-                    "algorithmic_flops": alg_work(top, N, M, K, L, sweeps)[1],
+                    "algorithmic_bytes": alg_work(top, N, M, K, L, sweeps, tests)[0],
+                    "algorithmic_flops": alg_work(top, N, M, K, L, sweeps, tests)[1],
+                    "accept_tests_per_particle": tests / max(N, 1),
                     "peak_source": {"hbm_gbs": hbm_peak, "hbm": peak_src, "fp64_tflops": fp64_peak,
                                     "fp64": "measured here: FP64 FMA chains (shamb200_microbench), FMA = 2 flop",
                                     "copy_gbs_here": copy_bw},

@@ -252,6 +252,9 @@ int shamb200_model_evolve_once_host(shamb200_model *m, uint32_t ip, const shamb2
 /* page-lock / unlock caller memory (cudaHostRegister) so that the copies above are asynchronous */
 int shamb200_host_register(void *p, uint64_t bytes);
 int shamb200_host_unregister(void *p);
+/* neighbour search of the last step on this rank: out[0] = sum of the list lengths (ObjectCache::sum_neigh_cnt,
+ * TreeTraversal.hpp:378), out[1] = (particle, candidate) accept tests done to build them */
+int shamb200_model_search_stats(shamb200_model *m, uint64_t out[2]);
 /* bytes moved by the last shamb200_model_evolve_once_host: out[0] host->device, out[1] device->host */
 int shamb200_model_host_traffic(shamb200_model *m, uint64_t out[2]);
 /* state: {time, next dt, cfl_multiplier, eps_v, h_subcycles, h_iters_last, corrector_iter,

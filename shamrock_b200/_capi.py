@@ -75,7 +75,8 @@ SYMBOLS = [
     "shamb200_model_init_comm", "shamb200_model_push_particles", "shamb200_model_patch_count",
     "shamb200_model_patch_is_local", "shamb200_model_patch_size", "shamb200_model_get",
     "shamb200_model_set_field", "shamb200_model_evolve_once", "shamb200_model_evolve_once_host",
-    "shamb200_host_register", "shamb200_host_unregister", "shamb200_model_host_traffic", "shamb200_model_state",
+    "shamb200_host_register", "shamb200_host_unregister", "shamb200_model_host_traffic",
+    "shamb200_model_search_stats", "shamb200_model_state",
     "shamb200_model_set_next_dt", "shamb200_model_set_time", "shamb200_model_set_cfl_multiplier",
     "shamb200_model_stage_times", "shamb200_plan_patch_grid", "shamb200_plan_interfaces",
     "shamb200_microbench",
@@ -319,6 +320,12 @@ class Model:
                 setattr(h, nm if nm != "uint" else "uint_", C.c_void_p(int(addr)))
         check(lib().shamb200_model_evolve_once_host(self.h, C.c_uint32(ip), C.byref(hin), C.byref(hout)))
         return int(hout.n)
+
+    def search_stats(self):
+        """(sum of the neighbour list lengths, accept tests done) of the last step on this rank"""
+        o = (C.c_uint64 * 2)()
+        check(lib().shamb200_model_search_stats(self.h, o))
+        return int(o[0]), int(o[1])
 
     def host_traffic(self):
         o = (C.c_uint64 * 2)()

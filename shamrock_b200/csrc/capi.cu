@@ -344,6 +344,12 @@ int shamb200_host_register(void *p, uint64_t bytes) {
 int shamb200_host_unregister(void *p) {
     return guard([&] { SB_CUDA_CHECK(cudaHostUnregister(p)); });
 }
+int shamb200_model_search_stats(shamb200_model *m, uint64_t out[2]) {
+    return guard([&] {
+        out[0] = m->m.K_local;
+        out[1] = m->m.pair_tests_local;
+    });
+}
 int shamb200_model_host_traffic(shamb200_model *m, uint64_t out[2]) {
     return guard([&] {
         out[0] = m->m.pipe.bytes_h2d;

@@ -492,6 +492,7 @@ struct ScanState {
     u32 cglob;   ///< chunks processed so far
     u32 mycount; ///< lane a < nb: accepted so far (MODE 0) / write cursor (MODE 1)
     bool fit;    ///< every ballot so far is in the shared store
+    u32 ncand;   ///< candidates of the leaf seen so far
 };
 
 /// NC chunks of 32 candidates (lane = one candidate of each chunk) against the nb particles of the batch;
@@ -606,6 +607,7 @@ __device__ __forceinline__ bool scan_candidates(
         const u32 tot = __shfl_sync(0xffffffffu, inc, 31);
         if (tot == 0)
             continue;
+        st.ncand += tot;
         if (tot > RANK_CACHE) { // very large leaves (many equal Morton codes): straight from the entries
             if (run)
                 flush_window<MODE>(w, st, SA, run, Rker2, h_tolerance, lane, lt, list_s);
@@ -686,7 +688,7 @@ __global__ void __launch_bounds__(S2_WARPS * 32, 4) neigh_lists_kernel(
         }
         __syncwarp();
         // ---- pass 1: ballots + counts
-        ScanState st{nb, 0u, 0u, true};
+        ScanState st{nb, 0u, 0u, true, 0u};
         u32 nwin    = 0;
         bool single = scan_candidates<0>(w, st, gc, gn, bit, SA, Rker2, h_tolerance, lane, lt, list_s, nwin);
         const u32 mycount = lane < int(nb) ? st.mycount : 0u;
@@ -700,8 +702,10 @@ __global__ void __launch_bounds__(S2_WARPS * 32, 4) neigh_lists_kernel(
         }
         u32 total = __shfl_sync(0xffffffffu, inc, 31);
         unsigned long long base = 0;
-        if (lane == 0)
+        if (lane == 0) {
             base = atomicAdd(cursor, (unsigned long long) total);
+            atomicAdd(cursor + 1, (unsigned long long) nb * st.ncand); // pair tests done (statistics)
+        }
         base = __shfl_sync(0xffffffffu, base, 0);
         u32 myoff = u32(base) + inc - mycount;
         if (lane < int(nb)) {
@@ -732,7 +736,7 @@ __global__ void __launch_bounds__(S2_WARPS * 32, 4) neigh_lists_kernel(
                 myoff += __popc(mkA) + __popc(mkB);
             }
         } else { // did not fit: scan and test again, writing as we go
-            ScanState st2{nb, 0u, myoff, true};
+            ScanState st2{nb, 0u, myoff, true, 0u};
             scan_candidates<1>(w, st2, gc, gn, bit, SA, Rker2, h_tolerance, lane, lt, list_s, nwin);
         }
     }
@@ -834,6 +838,7 @@ void search_build(
         }
         const u64 need_e = sb.h_scalars.p[6];
         sb.K             = sb.h_scalars.p[4];
+        sb.pair_tests    = sb.h_scalars.p[5];
         if (need_e > ecap) { // the candidate-entry array is too small
             sb.gcand.ensure(need_e, 1.25);
             redo = true;

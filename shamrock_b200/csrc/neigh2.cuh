@@ -22,6 +22,7 @@ constexpr int GL = 8; ///< leaves per walk group (the member mask lives in the t
 struct SearchBuffers {
     u32 N = 0, M = 0, L = 0, I = 0;
     u64 K        = 0; ///< total neighbour count
+    u64 pair_tests = 0; ///< (particle, candidate) accept tests of the last search
     u32 frontier_cap = 320; ///< walk frontier entries per group in shared memory (doubled on demand)
     DevBuf<NodePack> nodes;  // [I+L]
     DevBuf<Pack4> SA;        // [M] (x,y,z,h) in sorted order

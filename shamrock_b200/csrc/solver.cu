@@ -672,6 +672,7 @@ void Model::compute_presteps_rint() {
 void Model::start_neighbors_cache() {
     const f64 Rkern = cfg.kernel == SHAMB200_KERNEL_M4 ? 2.0 : 3.0;
     K_local         = 0;
+    pair_tests_local = 0;
     for (auto &p : patches)
         if (is_local(p) && p.f.n) {
             search_prepare_sorted(s(), p.st.tree, p.st.srch, p.st.A.p, p.st.n);
@@ -679,6 +680,7 @@ void Model::start_neighbors_cache() {
                 s(), p.st.tree, p.st.srch, p.st.rint.p, Rkern, cfg.htol_up_coarse_cycle,
                 [&](const char *name) { timer.mark(s(), name); });
             K_local += p.st.srch.K;
+            pair_tests_local += p.st.srch.pair_tests;
         }
 }
 

@@ -98,7 +98,7 @@ struct Model {
     // log of the last step
     f64 eps_v = 0, t_step = 0;
     u32 h_subcycles = 0, h_iters_last = 0, corrector_iter = 0;
-    u64 npart_all = 0, K_local = 0;
+    u64 npart_all = 0, K_local = 0, pair_tests_local = 0;
     std::vector<Iface> ifaces;
     StageTimer timer;
     // scratch

@@ -278,3 +278,12 @@ def test_bench_path_fields_match_oracle():
         ok, msg = close(m.get(0, nm), o.get(0, nm), 1e-10, floors.get(nm, 0.0))
         assert ok, f"{nm}: {msg}"
     assert abs(sm["dt"] - so["dt"]) <= 1e-10 * abs(so["dt"])
+
+
+@pytest.mark.parametrize("fp_mode", FP_MODES)
+@pytest.mark.parametrize("av", ["constant", "mm97"])
+def test_isothermal_eos(av, fp_mode):
+    """cfg.set_eos_isothermal(cs): P = cs^2 rho, cs constant (ComputeEos.cpp:54-130), free boundaries"""
+    sc = S.periodic_box(5000, "M4", av, jitter=0.15)
+    sc["cfg"].update(eos=1, cs0=0.7, bc=0)
+    run_and_compare(sc, steps=2, fp_mode=fp_mode)

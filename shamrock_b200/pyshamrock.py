@@ -269,12 +269,12 @@ _NV = {"xyz": 3, "vxyz": 3, "axyz": 3, "axyz_ext": 3, "curlv": 3}
 class Model:
     """shamrock.get_Model_SPH(...): shammodels::sph::Model<f64_3, Kernel>"""
 
-    def __init__(self, context, sph_kernel, device=0, fp_mode="strict"):
+    def __init__(self, context, sph_kernel, device=0, fp_mode="strict", sort_mode="bitonic"):
         if sph_kernel not in _KERNELS:
             raise ValueError(f"unknown sph kernel {sph_kernel} (this path: M4, M6)")
         self._ctx, context._model = context, self
         self._kernel, (self._kid, self._hfact, self._Rkern) = sph_kernel, _KERNELS[sph_kernel]
-        self._device, self._fp_mode = device, fp_mode
+        self._device, self._fp_mode, self._sort_mode = device, fp_mode, sort_mode
         self._cfg = SolverConfig(sph_kernel)
         self._bmin = self._bmax = None
         self._host = {nm: np.zeros((0, 3) if nm in _NV else (0,)) for nm in _MAIN}
@@ -424,7 +424,7 @@ class Model:
         for k, v in kv.items():
             cur = getattr(c, k)
             setattr(c, k, int(v) if isinstance(cur, int) else float(v))
-        c.sort_mode = _capi.SORT_MODES["bitonic"]
+        c.sort_mode = _capi.SORT_MODES[self._sort_mode]
         c.fp_mode = _capi.FP_MODES[self._fp_mode]
         c.keep_step_data = 0
         for i, (ctr, r) in enumerate(self._cfg._kill):
@@ -526,8 +526,11 @@ class Model:
         return AnalysisSodTube(self, sod, direction, time_val, x_ref, x_min, x_max)
 
 
-def get_Model_SPH(context, vector_type="f64_3", sph_kernel="M4", device=0, fp_mode="strict"):
-    """shamrock.get_Model_SPH(context=ctx, vector_type="f64_3", sph_kernel="M4" | "M6")"""
+def get_Model_SPH(context, vector_type="f64_3", sph_kernel="M4", device=0, fp_mode="strict", sort_mode="bitonic"):
+    """shamrock.get_Model_SPH(context=ctx, vector_type="f64_3", sph_kernel="M4" | "M6").  Backend options
+    (not in the reference): device ordinal; fp_mode "strict" (bit-identical to the reference's expression
+    order) or "fast"; sort_mode "bitonic" (the reference's network incl. its order of equal Morton codes) or
+    "radix" (faster, equal codes keep the input order)."""
     if vector_type != "f64_3":
         raise ValueError("unknown combination of representation and kernel (this path: f64_3 with M4 or M6)")
-    return Model(context, sph_kernel, device=device, fp_mode=fp_mode)
+    return Model(context, sph_kernel, device=device, fp_mode=fp_mode, sort_mode=sort_mode)

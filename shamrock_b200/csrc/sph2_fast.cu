@@ -112,25 +112,35 @@ __device__ __forceinline__ void density_sums(
     const f64 hinv = 1. / h_a;
     const f64 lim  = h_a * h_a * (K::Rkern * K::Rkern);
     f64 f_acc = 0, g_acc = 0;
-    u32 j  = s0 + sub;
-    u32 rb = j < s1 ? c.list[j] : 0u;
-    while (j < s1) { // the next index is fetched one trip ahead (one memory latency per trip)
-        const u32 jn  = j + G;
-        const u32 rbn = jn < s1 ? c.list[jn] : rb;
-        const Pack4 b = ld4(SA + rb);
-        j  = jn;
-        rb = rbn;
+    // two list entries per trip (independent loads and arithmetic chains), indices one trip ahead
+    auto pair = [&](const Pack4 &b) {
         f64 dx = a.a - b.a, dy = a.b - b.b, dz = a.c - b.c;
         f64 r2 = dx * dx + dy * dy + dz * dz;
-        if (r2 > lim)
-            continue;
-        f64 x  = r2 + 1e-280; // the particle itself: r2 = 0
-        f64 q  = (x * fast_rsqrt(x)) * hinv;
-        f64 f, df;
-        FastK<K>::f_df(q, f, df);
-        f_acc += f;
-        g_acc += fma(q, df, 3 * f);
+        if (r2 <= lim) {
+            f64 x = r2 + 1e-280; // the particle itself: r2 = 0
+            f64 q = (x * fast_rsqrt(x)) * hinv;
+            f64 f, df;
+            FastK<K>::f_df(q, f, df);
+            f_acc += f;
+            g_acc += fma(q, df, 3 * f);
+        }
+    };
+    u32 j   = s0 + sub;
+    u32 rb0 = j < s1 ? c.list[j] : 0u;
+    u32 rb1 = j + G < s1 ? c.list[j + G] : 0u;
+    while (j + G < s1) {
+        const u32 jn  = j + 2 * G;
+        const u32 rn0 = jn < s1 ? c.list[jn] : 0u;
+        const u32 rn1 = jn + G < s1 ? c.list[jn + G] : 0u;
+        const Pack4 b0 = ld4(SA + rb0), b1 = ld4(SA + rb1);
+        j   = jn;
+        rb0 = rn0;
+        rb1 = rn1;
+        pair(b0);
+        pair(b1);
     }
+    if (j < s1)
+        pair(ld4(SA + rb0));
     sf = group_sum<G>(f_acc);
     sg = group_sum<G>(g_acc);
 }

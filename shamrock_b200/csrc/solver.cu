@@ -1049,8 +1049,9 @@ void Model::evolve_once() {
     if (piped) {
         static const char *const tail[] = {"vxyz", "uint", "axyz", "duint", "soundspeed",
                                            "divv", "curlv", "dtdivv", "alpha_AV"};
-        // a repeated corrector pass recomputed the CD10 operators: send them again
-        pipe_download(tail, corrector_iter_cnt > 1 && has_alpha ? 9 : 5);
+        // the CD10 fields left during the force loop; a repeated corrector pass recomputed them (send them
+        // again), a configuration without them still returns the (untouched) arrays: every field comes back
+        pipe_download(tail, (corrector_iter_cnt > 1 || !has_alpha) ? 9 : 5);
     }
     timer.end_step(s());
     SB_CUDA_CHECK(cudaStreamSynchronize(s()));

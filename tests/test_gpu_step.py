@@ -254,10 +254,8 @@ def test_evolve_once_host_matches_device_resident(scenario):
         assert n_new == ref.patch_size(0)
         up, down = m.host_traffic()
         assert up == sum(n * dict(_capi.HOST_FIELDS)[nm] * 8 for nm in in_names)
-        assert down == n_new * (22 if has_alpha else 16) * 8  # fields the step does not produce stay put
+        assert down >= n_new * 22 * 8  # all twelve fields come back (the CD10 ones twice if the corrector reran)
         for nm in ALL_FIELDS:
-            if not has_alpha and nm in ("alpha_AV", "divv", "dtdivv", "curlv", "soundspeed") and scenario != "disc":
-                continue
             got = host[nm].numpy()[: n_new * dict(_capi.HOST_FIELDS)[nm]]
             want = ref.get(0, nm).reshape(-1)
             assert np.array_equal(got, want, equal_nan=True), f"step {step} {nm}"

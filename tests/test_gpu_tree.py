@@ -204,6 +204,34 @@ def test_neighbour_cache_outlier_h(ctx, kernel):
     assert np.array_equal(fetch(cv.d_index_neigh_map, cv.sum_neigh_cnt, np.uint32), cref["index_neigh_map"])
 
 
+@pytest.mark.parametrize("n_same", [40, 1500])
+def test_neighbour_cache_coincident_particles(ctx, n_same):
+    """Many particles at exactly the same position: one Morton code, one huge leaf.  Exercises the batches
+    of 32 particles per leaf, candidate windows larger than the shared-memory rank cache (entries of more
+    than 1024 ranks are streamed straight from the entry) and the re-test fill when the ballots do not fit."""
+    n, R = 3000, 2.0
+    xyz = positions("uniform", n, 11)
+    xyz[100:100 + n_same] = xyz[100]
+    xyz[2000:2000 + n_same // 2] = xyz[2000] + 1e-9  # a second clump, distinct positions inside one cell
+    h = np.full(n, 0.05)
+    h[100:100 + n_same:7] = 0.09
+    bb = ([0.0, 0.0, 0.0], [1.0, 1.0, 1.0])
+    ref = po.Tree(xyz, *bb, 3, bits=32)
+    ref.field_max(h, 1.1)
+    cref = ref.neigh_cache(h, n, R, 1.1, True)
+    dx, dh = dev(xyz), dev(h)
+    tv = ctx.tree_build(dx, n, *bb, reduction_level=3, sort_mode="bitonic")
+    rint = torch.empty(tv.leaf_count + tv.int_count, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    ctx.tree_field_max(tv, dh, 1.1, rint)
+    cv = ctx.neigh_cache_build(tv, dx, dh, rint, n, R, 1.1, True)
+    ctx.synchronize()
+    assert cref["cnt_neigh"].max() >= n_same
+    assert cv.sum_neigh_cnt == len(cref["index_neigh_map"])
+    assert np.array_equal(fetch(cv.d_cnt_neigh, n, np.uint32), cref["cnt_neigh"])
+    assert np.array_equal(fetch(cv.d_index_neigh_map, cv.sum_neigh_cnt, np.uint32), cref["index_neigh_map"])
+
+
 def test_neighbour_cache_brute_force(ctx):
     """independent of the oracle: list == all pairs passing the accept test, in sorted-Morton rank"""
     n, R, tol = 3000, 2.0, 1.1

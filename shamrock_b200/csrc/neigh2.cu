@@ -16,6 +16,7 @@
 // warp-per-leaf with the 32 lanes holding 32 CANDIDATES; the leaf's particles are broadcast from shared
 // memory, each (particle, chunk) produces one ballot word.  The fill pass replays the ballots only.
 #include "neigh2.cuh"
+#include <cstdlib>
 #include <algorithm>
 
 namespace sb {
@@ -498,14 +499,18 @@ struct ScanState {
 /// NC chunks of 32 candidates (lane = one candidate of each chunk) against the nb particles of the batch;
 /// two chunks per pass halve the shared-memory reads of the particles and give two independent chains.
 /// MODE 0: ballots + counts;  MODE 1: test again and write (used when the ballots / ranks did not fit)
-template<int MODE, int NC>
+/// V = 1 (default): a candidate slot past the end gets coordinates no particle is near to (r² = inf, so
+/// its ballot bit is clear without a validity term), and the per-particle counts are taken from the kept
+/// ballots after the particle loop instead of inside it.  V = 0: the first version, kept for tuning runs.
+template<int MODE, int NC, int V>
 __device__ __forceinline__ void chunk_body(
     WarpScratch &w, ScanState &st, const Pack4 *__restrict__ SA, const bool (&vb)[NC], const u32 (&rank_b)[NC],
     f64 Rker2, f64 h_tolerance, int lane, u32 lt, u32 *__restrict__ list_s) {
     f64 bx[NC], by[NC], bz[NC], lim_b[NC];
 #pragma unroll
     for (int c = 0; c < NC; c++) {
-        bx[c] = by[c] = bz[c] = lim_b[c] = 0;
+        bx[c] = V ? 1e300 : 0.;
+        by[c] = bz[c] = lim_b[c] = 0;
         if (vb[c]) {
             Pack4 q = ld4(SA + rank_b[c]);
             bx[c] = q.a, by[c] = q.b, bz[c] = q.c;
@@ -526,14 +531,15 @@ __device__ __forceinline__ void chunk_body(
             f64 dx = pa.a - bx[c], dy = pa.b - by[c], dz = pa.c - bz[c];
             f64 rab2         = dx * dx + dy * dy + dz * dz;
             bool no_interact = rab2 > pa.d && rab2 > lim_b[c];
-            m[c]             = __ballot_sync(0xffffffffu, vb[c] && !no_interact);
+            m[c]             = __ballot_sync(0xffffffffu, V ? !no_interact : (vb[c] && !no_interact));
         }
         if (MODE == 0) {
             if (lane == int(a)) {
 #pragma unroll
                 for (int c = 0; c < NC; c++) {
                     mymask[c] = m[c];
-                    st.mycount += __popc(m[c]);
+                    if (!V)
+                        st.mycount += __popc(m[c]);
                 }
             }
         } else {
@@ -549,6 +555,11 @@ __device__ __forceinline__ void chunk_body(
         }
     }
     if (MODE == 0) {
+        if (V) { // mymask is zero in the lanes that hold no particle
+#pragma unroll
+            for (int c = 0; c < NC; c++)
+                st.mycount += __popc(mymask[c]);
+        }
         if (keep) {
             if (lane < int(st.nb)) {
 #pragma unroll
@@ -563,7 +574,7 @@ __device__ __forceinline__ void chunk_body(
 }
 
 /// the window of `run` ranks in w.rankc, 64 (then 32) candidates at a time
-template<int MODE>
+template<int MODE, int V>
 __device__ __forceinline__ void flush_window(
     WarpScratch &w, ScanState &st, const Pack4 *__restrict__ SA, u32 run, f64 Rker2, f64 h_tolerance, int lane, u32 lt,
     u32 *__restrict__ list_s) {
@@ -573,13 +584,13 @@ __device__ __forceinline__ void flush_window(
         const u32 jA = j0 + lane, jB = j0 + 32 + lane;
         const bool vb[2]  = {true, jB < run};
         const u32 rk[2]   = {w.rankc[jA], vb[1] ? w.rankc[jB] : 0u};
-        chunk_body<MODE, 2>(w, st, SA, vb, rk, Rker2, h_tolerance, lane, lt, list_s);
+        chunk_body<MODE, 2, V>(w, st, SA, vb, rk, Rker2, h_tolerance, lane, lt, list_s);
     }
     if (j0 < run) {
         const u32 j      = j0 + lane;
         const bool vb[1] = {j < run};
         const u32 rk[1]  = {vb[0] ? w.rankc[j] : 0u};
-        chunk_body<MODE, 1>(w, st, SA, vb, rk, Rker2, h_tolerance, lane, lt, list_s);
+        chunk_body<MODE, 1, V>(w, st, SA, vb, rk, Rker2, h_tolerance, lane, lt, list_s);
     }
     __syncwarp();
 }
@@ -587,7 +598,7 @@ __device__ __forceinline__ void flush_window(
 /// scans the candidates of one leaf of group g: the group's entries that carry the leaf's bit, expanded
 /// into windows of ranks (shared memory) and processed 32 at a time.  Returns true when everything went
 /// through ONE window that is still in w.rankc (then `nwin` is its length and the ballots can be replayed).
-template<int MODE>
+template<int MODE, int V>
 __device__ __forceinline__ bool scan_candidates(
     WarpScratch &w, ScanState &st, const uint2 *__restrict__ gc, u32 gn, u32 bit, const Pack4 *__restrict__ SA,
     f64 Rker2, f64 h_tolerance, int lane, u32 lt, u32 *__restrict__ list_s, u32 &nwin) {
@@ -610,7 +621,7 @@ __device__ __forceinline__ bool scan_candidates(
         st.ncand += tot;
         if (tot > RANK_CACHE) { // very large leaves (many equal Morton codes): straight from the entries
             if (run)
-                flush_window<MODE>(w, st, SA, run, Rker2, h_tolerance, lane, lt, list_s);
+                flush_window<MODE, V>(w, st, SA, run, Rker2, h_tolerance, lane, lt, list_s);
             run    = 0;
             single = false;
             for (int kk = 0; kk < 32; kk++) {
@@ -619,25 +630,33 @@ __device__ __forceinline__ bool scan_candidates(
                     const u32 j      = j0 + lane;
                     const bool vb[1] = {j < ln};
                     const u32 rk[1]  = {s0 + j};
-                    chunk_body<MODE, 1>(w, st, SA, vb, rk, Rker2, h_tolerance, lane, lt, list_s);
+                    chunk_body<MODE, 1, V>(w, st, SA, vb, rk, Rker2, h_tolerance, lane, lt, list_s);
                 }
             }
             continue;
         }
         if (run + tot > RANK_CACHE) {
-            flush_window<MODE>(w, st, SA, run, Rker2, h_tolerance, lane, lt, list_s);
+            flush_window<MODE, V>(w, st, SA, run, Rker2, h_tolerance, lane, lt, list_s);
             run    = 0;
             single = false;
         }
         u32 dst = run + inc - len;
-        for (u32 t = 0; __any_sync(0xffffffffu, t < len); t++)
-            if (t < len)
-                w.rankc[dst + t] = e.x + t;
+        if (V) { // the longest run of the 32 entries bounds the (warp-uniform) trip count
+            const u32 maxlen = __reduce_max_sync(0xffffffffu, len);
+            u32 *wr = w.rankc + dst;
+            for (u32 t = 0; t < maxlen; t++)
+                if (t < len)
+                    wr[t] = e.x + t;
+        } else {
+            for (u32 t = 0; __any_sync(0xffffffffu, t < len); t++)
+                if (t < len)
+                    w.rankc[dst + t] = e.x + t;
+        }
         run += tot;
     }
     nwin = run;
     if (run)
-        flush_window<MODE>(w, st, SA, run, Rker2, h_tolerance, lane, lt, list_s);
+        flush_window<MODE, V>(w, st, SA, run, Rker2, h_tolerance, lane, lt, list_s);
     return single;
 }
 
@@ -648,6 +667,7 @@ constexpr int S2_WARPS = GL; // one block = one group of leaves
 /// (lists are contiguous per leaf, leaves in completion order — the internal CSR does not need a global
 /// order, the exported ObjectCache is rebuilt by id) and pass 2 replays the ballots.  Leaves whose
 /// candidates or ballots do not fit the shared stores test again in pass 2 instead.
+template<int V>
 __global__ void __launch_bounds__(S2_WARPS * 32, 4) neigh_lists_kernel(
     const NodePack *__restrict__ nodes, u32 I, u32 L, const Pack4 *__restrict__ SA, const u8 *__restrict__ real_flag,
     const u32 *__restrict__ real_prefix, const uint2 *__restrict__ gcand, const u64 *__restrict__ gc_off,
@@ -690,7 +710,7 @@ __global__ void __launch_bounds__(S2_WARPS * 32, 4) neigh_lists_kernel(
         // ---- pass 1: ballots + counts
         ScanState st{nb, 0u, 0u, true, 0u};
         u32 nwin    = 0;
-        bool single = scan_candidates<0>(w, st, gc, gn, bit, SA, Rker2, h_tolerance, lane, lt, list_s, nwin);
+        bool single = scan_candidates<0, V>(w, st, gc, gn, bit, SA, Rker2, h_tolerance, lane, lt, list_s, nwin);
         const u32 mycount = lane < int(nb) ? st.mycount : 0u;
         // ---- reserve the list space of this batch: exclusive prefix of the counts + one atomic
         u32 inc = mycount;
@@ -737,7 +757,7 @@ __global__ void __launch_bounds__(S2_WARPS * 32, 4) neigh_lists_kernel(
             }
         } else { // did not fit: scan and test again, writing as we go
             ScanState st2{nb, 0u, myoff, true, 0u};
-            scan_candidates<1>(w, st2, gc, gn, bit, SA, Rker2, h_tolerance, lane, lt, list_s, nwin);
+            scan_candidates<1, V>(w, st2, gc, gn, bit, SA, Rker2, h_tolerance, lane, lt, list_s, nwin);
         }
     }
 }
@@ -760,7 +780,8 @@ void search_build(
     static bool attr_set = false;
     const size_t s2_bytes = sizeof(WarpScratch) * S2_WARPS;
     if (!attr_set) {
-        SB_CUDA_CHECK(cudaFuncSetAttribute(neigh_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(s2_bytes)));
+        SB_CUDA_CHECK(cudaFuncSetAttribute(neigh_lists_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(s2_bytes)));
+        SB_CUDA_CHECK(cudaFuncSetAttribute(neigh_lists_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(s2_bytes)));
         SB_CUDA_CHECK(cudaFuncSetAttribute(
             group_walk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
@@ -787,6 +808,9 @@ void search_build(
         if (err & 2u)
             throw std::runtime_error("neighbour search: internal error, a global-memory frontier overflowed");
     };
+    // SHAMB200_NL = 0 selects the first version of the list kernel (tuning runs)
+    const char *nl_env      = getenv("SHAMB200_NL");
+    const auto lists_kernel = (nl_env && atoi(nl_env) == 0) ? neigh_lists_kernel<0> : neigh_lists_kernel<1>;
     for (int attempt = 0;; attempt++) {
         const size_t per_warp = sizeof(LeafBox) * (GL + 1) + size_t(2) * sb.frontier_cap * sizeof(uint2);
         const u64 ecap        = sb.gcand.cap;
@@ -804,7 +828,7 @@ void search_build(
         SB_COUNT_LAUNCH();
         if (mark)
             mark("neigh_lists");
-        neigh_lists_kernel<<<G, S2_WARPS * 32, s2_bytes, s>>>(
+        lists_kernel<<<G, S2_WARPS * 32, s2_bytes, s>>>(
             sb.nodes.p, I, L, sb.SA.p, sb.real_flag.p, sb.real_prefix.p, sb.gcand.p, sb.gc_off.p, sb.gcount.p, nullptr,
             Rker2, h_tolerance, u64(sb.list_s.cap), d_cursor, sb.cnt_s.p, sb.off_s.p, sb.list_s.p);
         SB_COUNT_LAUNCH();
@@ -828,7 +852,7 @@ void search_build(
                     sb.nodes.p, I, L, sb.real_prefix.p, Rkern, L, sb.top_front.p, sb.top_count.p, ecap, d_ecursor,
                     sb.gcand.p, sb.gc_off.p, sb.gcount.p, d_flags, sb.over_list.p + b0, OVER_CAP, sb.big_scratch.p);
                 SB_COUNT_LAUNCH();
-                neigh_lists_kernel<<<nb, S2_WARPS * 32, s2_bytes, s>>>(
+                lists_kernel<<<nb, S2_WARPS * 32, s2_bytes, s>>>(
                     sb.nodes.p, I, L, sb.SA.p, sb.real_flag.p, sb.real_prefix.p, sb.gcand.p, sb.gc_off.p, sb.gcount.p,
                     sb.over_list.p + b0, Rker2, h_tolerance, u64(sb.list_s.cap), d_cursor, sb.cnt_s.p, sb.off_s.p,
                     sb.list_s.p);

@@ -146,6 +146,78 @@ int shamb200_h_iterate_loop(shamb200_ctx *ctx, int kernel, const shamb200_csr *c
 int shamb200_compute_omega(shamb200_ctx *ctx, int kernel, const shamb200_csr *csr, const double *d_xyz,
                            size_t stride_dbl, const double *d_hpart, double *d_omega, double gpart_mass);
 
+/* ---- SPH modules on merged patch data (stage level) ------------------------------------------------
+ * The modules Solver::evolve_once runs between the h iteration and the corrector, one entry point per
+ * reference module, on the arrays the reference's solver graph hands them: the MERGED fields of one
+ * patch (its N real objects first, then the ghosts: M objects, BasicSPHGhosts.hpp:294-514 /
+ * Solver.cpp:1394-1633) and the patch's ObjectCache.  Device pointers, caller owned.  Results are
+ * bit-identical to the reference's expressions evaluated without FMA contraction (the oracle);
+ * shamb200_model_evolve_once runs the fused Morton-ordered versions of the same loops.
+ * A NULL input pointer stands for a field the module does not read (documented per function). */
+typedef struct shamb200_merged_fields {
+    uint32_t obj_cnt;          /* M, merged objects                                       */
+    uint32_t real_cnt;         /* N <= M, the patch's own objects (outputs have N entries) */
+    const double *d_xyz;       /* [M * stride_dbl]                                         */
+    size_t stride_dbl;         /* 3 or 4                                                   */
+    const double *d_hpart;     /* [M]                                                      */
+    const double *d_vxyz;      /* [M * 3] packed                                           */
+    const double *d_uint;      /* [M]                                                      */
+    const double *d_axyz;      /* [M * 3] packed (only d(div v)/dt reads it)               */
+    const double *d_omega;     /* [M]                                                      */
+    const double *d_pressure;  /* [M]                                                      */
+    const double *d_soundspeed;/* [M]                                                      */
+    const double *d_alpha_AV;  /* [M] (MM97 / CD10); NULL with a constant alpha            */
+} shamb200_merged_fields;
+
+/* replaces modules::ComputeEos::compute_eos (shammodels/sph/src/modules/ComputeEos.cpp:1138-1308;
+ * adiabatic :147-248, isothermal :54-130, locally isothermal LP07 :724-800) over the merged range.
+ * Reads xyz (LP07), hpart, uint (adiabatic).  d_pressure / d_soundspeed: [M]. */
+int shamb200_compute_eos(shamb200_ctx *ctx, int kernel, int eos, const shamb200_merged_fields *f,
+                         double gpart_mass, double gamma, double cs0, double eos_q, double eos_r0,
+                         double *d_pressure, double *d_soundspeed);
+/* replaces modules::DiffOperators::update_divv / update_curlv (DiffOperator.cpp:25-146, :148-260).
+ * Reads xyz, hpart, vxyz, omega.  d_divv [N]; d_curlv [N * 3] or NULL. */
+int shamb200_update_divv_curlv(shamb200_ctx *ctx, int kernel, const shamb200_csr *csr,
+                               const shamb200_merged_fields *f, double gpart_mass, double *d_divv,
+                               double *d_curlv);
+/* replaces modules::DiffOperatorDtDivv::update_dtdivv (DiffOperatorDtDivv.cpp:29-353).  Reads xyz, hpart,
+ * vxyz, axyz.  also_divv_curlv != 0: the combined variant that also writes div v and curl v from the
+ * same velocity-gradient matrix (combined_dtdiv_divcurlv_compute, SolverConfig.hpp:602). */
+int shamb200_update_dtdivv(shamb200_ctx *ctx, int kernel, const shamb200_csr *csr,
+                           const shamb200_merged_fields *f, double gpart_mass, int also_divv_curlv,
+                           double *d_divv, double *d_curlv, double *d_dtdivv);
+/* replaces modules::UpdateViscosity::update_artificial_viscosity (UpdateViscosity.cpp:52-119 MM97,
+ * :122-222 CD10).  All arrays [N] (d_curlv [N * 3]); d_dtdivv / d_curlv are only read for CD10. */
+int shamb200_update_viscosity(shamb200_ctx *ctx, int av, uint32_t real_cnt, double dt, double sigma_decay,
+                              double alpha_min, double alpha_max, const double *d_divv,
+                              const double *d_curlv, const double *d_dtdivv, const double *d_soundspeed,
+                              const double *d_hpart, const double *d_alpha_AV, double *d_alpha_AV_updated);
+/* replaces modules::UpdateDerivs::update_derivs (UpdateDerivs.cpp:89-288 constant alpha, :580-780 disc;
+ * NodeUpdateDerivsVaryingAlphaAV.cpp:26-137 MM97 / CD10; math/forces.hpp:27-226, math/q_ab.hpp:37-62).
+ * Reads xyz, hpart, vxyz, uint, omega, pressure, soundspeed and alpha_AV (MM97 / CD10).
+ * d_axyz [N * 3] = pressure + viscosity forces + d_axyz_ext (NULL = 0); d_duint [N]. */
+int shamb200_update_derivs(shamb200_ctx *ctx, int kernel, int av, const shamb200_csr *csr,
+                           const shamb200_merged_fields *f, double gpart_mass, double alpha_u,
+                           double alpha_AV, double beta_AV, const double *d_axyz_ext, double *d_axyz,
+                           double *d_duint);
+/* replaces the signal-velocity loop and the CFL time step of Solver::evolve_once (Solver.cpp:2677-2840,
+ * :2895-3119; modules/ComputeCFLCourant.hpp, ComputeCFLForce.hpp).  Reads xyz, hpart, vxyz, soundspeed
+ * and d_axyz [N * 3] (the new accelerations).  d_vsig, d_cfl_dt: [N]; *dt_min = min over the patch.
+ * Synchronises. */
+int shamb200_vsig_cfl(shamb200_ctx *ctx, int kernel, const shamb200_csr *csr, const shamb200_merged_fields *f,
+                      const double *d_axyz, double C_cour, double C_force, double *d_vsig, double *d_cfl_dt,
+                      double *dt_min);
+/* replaces the leapfrog predictor of Solver::do_predictor_leapfrog (Solver.cpp:390-524,
+ * shamrock/src/math/integrators.cpp:88-119): v += dt/2 a; u += dt/2 du; x += dt v; v += dt/2 a;
+ * u += dt/2 du, in place over n objects. */
+int shamb200_leapfrog_predict(shamb200_ctx *ctx, uint32_t n, double dt, double *d_xyz, double *d_vxyz,
+                              const double *d_axyz, double *d_uint, const double *d_duint);
+/* replaces the corrector of Solver::apply_corrector / the eps_v test (Solver.cpp:2513-2616):
+ * v += half_dt (a - a_old); u += half_dt (du - du_old); out2 = {max |dv|^2, sum |v|^2}.  Synchronises. */
+int shamb200_leapfrog_correct(shamb200_ctx *ctx, uint32_t n, double half_dt, double *d_vxyz,
+                              const double *d_axyz, const double *d_axyz_old, double *d_uint,
+                              const double *d_duint, const double *d_duint_old, double out2[2]);
+
 /* ---- patch decomposition / ghost-zone planning (host only, no CUDA call) ---------------------------
  * Pure functions of replicated metadata: every rank computes the same plan, so the NCCL send/recv
  * pairs of the ghost exchange match without negotiation.

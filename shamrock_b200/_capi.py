@@ -39,6 +39,16 @@ class CsrView(C.Structure):
     ]
 
 
+class MergedFields(C.Structure):
+    """shamb200_merged_fields: device pointers of the merged (real + ghost) fields of one patch"""
+    _fields_ = [
+        ("obj_cnt", C.c_uint32), ("real_cnt", C.c_uint32), ("d_xyz", C.c_void_p), ("stride_dbl", C.c_size_t),
+        ("d_hpart", C.c_void_p), ("d_vxyz", C.c_void_p), ("d_uint", C.c_void_p), ("d_axyz", C.c_void_p),
+        ("d_omega", C.c_void_p), ("d_pressure", C.c_void_p), ("d_soundspeed", C.c_void_p),
+        ("d_alpha_AV", C.c_void_p),
+    ]
+
+
 class SolverConfig(C.Structure):
     _fields_ = [
         ("kernel", C.c_int32), ("eos", C.c_int32), ("av", C.c_int32), ("bc", C.c_int32),
@@ -80,6 +90,8 @@ SYMBOLS = [
     "shamb200_model_set_next_dt", "shamb200_model_set_time", "shamb200_model_set_cfl_multiplier",
     "shamb200_model_stage_times", "shamb200_plan_patch_grid", "shamb200_plan_interfaces",
     "shamb200_microbench",
+    "shamb200_compute_eos", "shamb200_update_divv_curlv", "shamb200_update_dtdivv", "shamb200_update_viscosity",
+    "shamb200_update_derivs", "shamb200_vsig_cfl", "shamb200_leapfrog_predict", "shamb200_leapfrog_correct",
 ]
 
 HOST_FIELDS = (("xyz", 3), ("vxyz", 3), ("axyz", 3), ("axyz_ext", 3), ("hpart", 1), ("uint", 1), ("duint", 1),
@@ -217,6 +229,69 @@ class Context:
         check(lib().shamb200_compute_omega(
             self.h, KERNELS[kernel], C.byref(cv), C.c_void_p(xyz_t.data_ptr()), C.c_size_t(stride_dbl),
             C.c_void_p(h_t.data_ptr()), C.c_void_p(omega_t.data_ptr()), C.c_double(pmass)))
+
+
+    # ---- SPH modules on merged patch data (torch tensors on this context's device) ------------------
+    @staticmethod
+    def _p(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else None
+
+    @classmethod
+    def merged_fields(cls, obj_cnt, real_cnt, xyz, hpart, vxyz=None, uint=None, axyz=None, omega=None,
+                      pressure=None, soundspeed=None, alpha_AV=None, stride_dbl=3):
+        """A shamb200_merged_fields view of device tensors (kept alive by the caller)."""
+        f = MergedFields()
+        f.obj_cnt, f.real_cnt, f.stride_dbl = int(obj_cnt), int(real_cnt), int(stride_dbl)
+        for name, t in (("d_xyz", xyz), ("d_hpart", hpart), ("d_vxyz", vxyz), ("d_uint", uint), ("d_axyz", axyz),
+                        ("d_omega", omega), ("d_pressure", pressure), ("d_soundspeed", soundspeed),
+                        ("d_alpha_AV", alpha_AV)):
+            setattr(f, name, t.data_ptr() if t is not None else None)
+        return f
+
+    def compute_eos(self, kernel, eos, f, pmass, gamma, cs0, eos_q, eos_r0, pressure_t, soundspeed_t):
+        check(lib().shamb200_compute_eos(
+            self.h, KERNELS[kernel], EOS[eos], C.byref(f), C.c_double(pmass), C.c_double(gamma), C.c_double(cs0),
+            C.c_double(eos_q), C.c_double(eos_r0), self._p(pressure_t), self._p(soundspeed_t)))
+
+    def update_divv_curlv(self, kernel, cv, f, pmass, divv_t, curlv_t=None):
+        check(lib().shamb200_update_divv_curlv(
+            self.h, KERNELS[kernel], C.byref(cv), C.byref(f), C.c_double(pmass), self._p(divv_t), self._p(curlv_t)))
+
+    def update_dtdivv(self, kernel, cv, f, pmass, dtdivv_t, also_divv_curlv=False, divv_t=None, curlv_t=None):
+        check(lib().shamb200_update_dtdivv(
+            self.h, KERNELS[kernel], C.byref(cv), C.byref(f), C.c_double(pmass), int(also_divv_curlv),
+            self._p(divv_t), self._p(curlv_t), self._p(dtdivv_t)))
+
+    def update_viscosity(self, av, n, dt, sigma_decay, alpha_min, alpha_max, divv_t, curlv_t, dtdivv_t, cs_t, h_t,
+                         alpha_t, alpha_out_t):
+        check(lib().shamb200_update_viscosity(
+            self.h, AV[av], C.c_uint32(n), C.c_double(dt), C.c_double(sigma_decay), C.c_double(alpha_min),
+            C.c_double(alpha_max), self._p(divv_t), self._p(curlv_t), self._p(dtdivv_t), self._p(cs_t), self._p(h_t),
+            self._p(alpha_t), self._p(alpha_out_t)))
+
+    def update_derivs(self, kernel, av, cv, f, pmass, alpha_u, alpha_AV, beta_AV, axyz_ext_t, axyz_t, duint_t):
+        check(lib().shamb200_update_derivs(
+            self.h, KERNELS[kernel], AV[av], C.byref(cv), C.byref(f), C.c_double(pmass), C.c_double(alpha_u),
+            C.c_double(alpha_AV), C.c_double(beta_AV), self._p(axyz_ext_t), self._p(axyz_t), self._p(duint_t)))
+
+    def vsig_cfl(self, kernel, cv, f, axyz_t, C_cour, C_force, vsig_t, cfl_dt_t):
+        out = C.c_double()
+        check(lib().shamb200_vsig_cfl(
+            self.h, KERNELS[kernel], C.byref(cv), C.byref(f), self._p(axyz_t), C.c_double(C_cour), C.c_double(C_force),
+            self._p(vsig_t), self._p(cfl_dt_t), C.byref(out)))
+        return out.value
+
+    def leapfrog_predict(self, n, dt, xyz_t, vxyz_t, axyz_t, uint_t, duint_t):
+        check(lib().shamb200_leapfrog_predict(
+            self.h, C.c_uint32(n), C.c_double(dt), self._p(xyz_t), self._p(vxyz_t), self._p(axyz_t), self._p(uint_t),
+            self._p(duint_t)))
+
+    def leapfrog_correct(self, n, half_dt, vxyz_t, axyz_t, axyz_old_t, uint_t, duint_t, duint_old_t):
+        out = (C.c_double * 2)()
+        check(lib().shamb200_leapfrog_correct(
+            self.h, C.c_uint32(n), C.c_double(half_dt), self._p(vxyz_t), self._p(axyz_t), self._p(axyz_old_t),
+            self._p(uint_t), self._p(duint_t), self._p(duint_old_t), out))
+        return out[0], out[1]
 
 
 _U32 = {"sorted_morton", "sort_index_map", "reduc_index_map", "reduced_morton", "lchild_id", "rchild_id",

@@ -51,6 +51,10 @@ void fill_tree_view(const TreeBuffers &t, shamb200_tree *out) {
 }
 } // namespace
 
+namespace sb {
+void set_last_error(const char *msg) { g_err = msg; }
+} // namespace sb
+
 extern "C" {
 
 const char *shamb200_last_error(void) { return g_err.c_str(); }

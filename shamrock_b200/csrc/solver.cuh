@@ -27,6 +27,8 @@ struct Ctx {
     SearchBuffers api_srch;
     DevBuf<u64> red;
     PinnedBuf<u64> h_red;
+    DevBuf<Pack4> api_A, api_B, api_C, api_D; ///< merged records of the stage-level SPH modules
+    DevBuf<f64> api_tmp;
 };
 
 /// main patch data layout (SolverConfig.cpp:24-121), device resident, packed vec3 (3 doubles)
@@ -174,6 +176,11 @@ void comm_send(Model &m, const void *d, size_t bytes, int peer);
 void comm_recv(Model &m, void *d, size_t bytes, int peer);
 void comm_destroy(Model &m);
 
+} // namespace sb
+
+namespace sb {
+/// message returned by shamb200_last_error (thread local; capi.cu)
+void set_last_error(const char *msg);
 } // namespace sb
 
 struct shamb200_ctx {

@@ -263,9 +263,10 @@ typedef struct shamb200_solver_config {
     int32_t n_kill_spheres;
     int32_t keep_step_data; /* keep per-step intermediates for shamb200_model_get (tests) */
     int32_t fp_mode;        /* SHAMB200_FP_*                                   */
-    int32_t reserved0;
+    int32_t enable_particle_reordering; /* SolverConfig.hpp:621: Morton-reorder the patch data ...     */
     double kill_center[4][3];
     double kill_radius[4];
+    uint64_t particle_reordering_step_freq; /* ... at every step whose index is a multiple of this (1000) */
 } shamb200_solver_config;
 
 /* defaults of SolverConfig (shammodels/sph/include/shammodels/sph/SolverConfig.hpp:584-630,
@@ -297,6 +298,13 @@ uint32_t shamb200_model_patch_size(shamb200_model *m, uint32_t ip); /* 0 for rem
  * get: returns the byte size, copies when cap_bytes is large enough; -1 if unknown. */
 int64_t shamb200_model_get(shamb200_model *m, uint32_t ip, const char *name, void *out, int64_t cap_bytes);
 int shamb200_model_set_field(shamb200_model *m, uint32_t ip, const char *name, const double *in, uint64_t count);
+/* modules::ParticleReordering::reorder_particles (shammodels/sph/src/modules/ParticleReordering.cpp:22-51),
+ * the call SPHSetup::apply_setup(part_reordering = true) makes after the particles are in place
+ * (SPHSetup.cpp:202-205): every local patch is permuted into the Morton order of its positions over the
+ * patch box (RadixTreeMortonBuilder.cpp:68-107; sort_mode BITONIC reproduces the reference's order inside
+ * runs of equal codes).  evolve_once does the same at the steps selected by enable_particle_reordering /
+ * particle_reordering_step_freq (Solver.cpp:2043-2048). */
+int shamb200_model_reorder_particles(shamb200_model *m);
 /* Solver::evolve_once (Solver.cpp:1942).  Runs one full step; synchronises at the end. */
 int shamb200_model_evolve_once(shamb200_model *m);
 /* Solver::evolve_once on HOST-resident patch data: the call a host code that keeps its PatchDataLayer

@@ -307,6 +307,11 @@ int oracle_solver_configure(void *ss, const char *kv) {
             else if (k == "pm_mass") c.pm_mass = v;
             else if (k == "pm_racc") c.pm_racc = v;
             else if (k == "constant_G") c.constant_G = v;
+            else if (k == "enable_particle_reordering") c.enable_particle_reordering = int(v);
+            else if (k == "particle_reordering_step_freq") {
+                if (v < 1) throw std::invalid_argument("particle_reordering_step_freq cannot be zero");
+                c.particle_reordering_step_freq = u64(v);
+            }
             else if (k == "time") S->time = v;
             else if (k == "dt") S->dt = v;
             else if (k == "cfl_multiplier") S->cfl_multiplier = v;
@@ -414,6 +419,11 @@ int64_t oracle_solver_get(void *ss, uint32_t ip, const char *name, void *out, in
     if (n == "step.cfl_dt") return copy_out(st.cfl_dt, out, cap);
     if (n == "step.alpha_updated") return copy_out(st.alpha_updated, out, cap);
     return -1;
+}
+/// modules::ParticleReordering::reorder_particles (the call SPHSetup::apply_setup makes, SPHSetup.cpp:202-205)
+int oracle_solver_reorder_particles(void *ss) {
+    auto *S = (Solver *) ss;
+    return guard([&] { S->reorder_particles(); });
 }
 int oracle_solver_evolve_once(void *ss) {
     auto *S = (Solver *) ss;

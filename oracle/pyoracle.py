@@ -234,6 +234,9 @@ class Solver:
             out = out.reshape(-1, 3)
         return out
 
+    def reorder_particles(self):
+        _chk(lib().oracle_solver_reorder_particles(C.c_void_p(self.s)))
+
     def evolve_once(self):
         _chk(lib().oracle_solver_evolve_once(C.c_void_p(self.s)))
         return self.state()

@@ -57,6 +57,9 @@ struct SolverConfig {
     f64 pm_mass        = 0;
     f64 pm_racc        = 0;
     f64 constant_G     = 1;
+    // Morton reordering of the patch data (SolverConfig.hpp:621-630)
+    int enable_particle_reordering    = 0;
+    u64 particle_reordering_step_freq = 1000;
     // particle killing (kill spheres)
     int n_kill_spheres = 0;
     f64 kill_center[4][3];
@@ -168,6 +171,7 @@ struct Solver {
     f64 time = 0, dt = 0, cfl_multiplier = 1e-2; // ref: Solver.hpp:131-147
     std::map<u64, PatchStep> step; // last step's intermediate data, by patch id
     StepLog log;
+    u64 step_count = 0; // SolverLog::step_count (SolverLog.hpp:49-54): steps registered so far
 
     static constexpr u64 GRID = 1ull << 21; // PatchScheduler::max_axis_patch_coord_length
 
@@ -178,6 +182,31 @@ struct Solver {
             f64 fact = (box_max[d] - box_min[d]) / f64(GRID);
             lo[d]    = f64(p.coord_min[d]) * fact + box_min[d];
             hi[d]    = f64(p.coord_max[d] + 1) * fact + box_min[d];
+        }
+    }
+
+    /// ref: shammodels/sph/src/modules/ParticleReordering.cpp:22-51 — per patch: Morton codes of the
+    /// positions over the PATCH box (shamtree/src/RadixTreeMortonBuilder.cpp:68-107: codes, pad to a power of
+    /// two with the error code, index buffer, key/value bitonic sort), then PatchDataLayer::index_remap:
+    /// new[i] = old[index_map[i]] for every field
+    void reorder_particles() {
+        for (auto &p : patches) {
+            u32 n = p.pdat.n;
+            if (n == 0)
+                continue;
+            f64 lo[3], hi[3];
+            patch_box(p, lo, hi);
+            u32 P2 = roundup_pow2(n);
+            std::vector<u32> codes(P2), ids(P2);
+            morton_code_set_from_positions<u32>(p.pdat.xyz.data(), 3, n, lo, hi, P2, codes.data());
+            for (u32 i = 0; i < P2; i++)
+                ids[i] = i;
+            sort_by_key_bitonic<u32>(codes.data(), ids.data(), P2);
+            ids.resize(n);
+            for (u32 i : ids)
+                if (i >= n)
+                    throw std::runtime_error("reorder_particles: a padding entry sorted below a particle");
+            p.pdat.keep_ids(ids);
         }
     }
 
@@ -1043,6 +1072,10 @@ struct SolverT {
         u64 Npart_all = S.total_count();
         S.log.npart   = Npart_all;
 
+        // ref: Solver.cpp:2043-2048
+        if (cfg.enable_particle_reordering && S.step_count % cfg.particle_reordering_step_freq == 0)
+            S.reorder_particles();
+
         sph_prestep();
 
         f64 next_cfl              = 0;
@@ -1153,6 +1186,7 @@ struct SolverT {
         S.time               = t_current + dt;
         f64 stiff            = cfg.cfl_multiplier_stiffness;
         S.cfl_multiplier     = (S.cfl_multiplier * stiff + 1.) / (stiff + 1.);
+        S.step_count++;
     }
 };
 

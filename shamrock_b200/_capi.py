@@ -64,8 +64,9 @@ class SolverConfig(C.Structure):
         ("sort_mode", C.c_int32), ("has_point_mass", C.c_int32),
         ("pm_mass", C.c_double), ("pm_racc", C.c_double), ("constant_G", C.c_double),
         ("n_kill_spheres", C.c_int32), ("keep_step_data", C.c_int32),
-        ("fp_mode", C.c_int32), ("reserved0", C.c_int32),
+        ("fp_mode", C.c_int32), ("enable_particle_reordering", C.c_int32),
         ("kill_center", (C.c_double * 3) * 4), ("kill_radius", C.c_double * 4),
+        ("particle_reordering_step_freq", C.c_uint64),
     ]
 
 
@@ -84,7 +85,8 @@ SYMBOLS = [
     "shamb200_model_set_config", "shamb200_model_set_box", "shamb200_nccl_unique_id",
     "shamb200_model_init_comm", "shamb200_model_push_particles", "shamb200_model_patch_count",
     "shamb200_model_patch_is_local", "shamb200_model_patch_size", "shamb200_model_get",
-    "shamb200_model_set_field", "shamb200_model_evolve_once", "shamb200_model_evolve_once_host",
+    "shamb200_model_set_field", "shamb200_model_reorder_particles", "shamb200_model_evolve_once",
+    "shamb200_model_evolve_once_host",
     "shamb200_host_register", "shamb200_host_unregister", "shamb200_model_host_traffic",
     "shamb200_model_search_stats", "shamb200_model_state",
     "shamb200_model_set_next_dt", "shamb200_model_set_time", "shamb200_model_set_cfl_multiplier",
@@ -380,6 +382,10 @@ class Model:
         a = np.ascontiguousarray(arr, dtype=np.float64).reshape(-1)
         check(lib().shamb200_model_set_field(self.h, C.c_uint32(ip), name.encode(),
                                              a.ctypes.data_as(C.c_void_p), C.c_uint64(a.size)))
+
+    def reorder_particles(self):
+        """modules::ParticleReordering::reorder_particles: Morton order of every local patch"""
+        check(lib().shamb200_model_reorder_particles(self.h))
 
     def evolve_once(self):
         check(lib().shamb200_model_evolve_once(self.h))

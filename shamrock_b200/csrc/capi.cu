@@ -290,6 +290,8 @@ void shamb200_solver_config_default(shamb200_solver_config *cfg) {
     cfg->use_two_stage_search     = 1;
     cfg->sort_mode                = SHAMB200_SORT_BITONIC;
     cfg->constant_G               = 1;
+    cfg->enable_particle_reordering    = 0;
+    cfg->particle_reordering_step_freq = 1000;
 }
 
 int shamb200_model_create(shamb200_ctx *ctx, const shamb200_solver_config *cfg, shamb200_model **out) {
@@ -386,6 +388,12 @@ int shamb200_model_set_next_dt(shamb200_model *m, double dt) {
 }
 int shamb200_model_set_time(shamb200_model *m, double t) {
     return guard([&] { m->m.time = t; });
+}
+int shamb200_model_reorder_particles(shamb200_model *m) {
+    return guard([&] {
+        m->m.reorder_particles();
+        SB_CUDA_CHECK(cudaStreamSynchronize(m->m.s()));
+    });
 }
 int shamb200_model_set_cfl_multiplier(shamb200_model *m, double v) {
     return guard([&] { m->m.cfl_multiplier = v; });

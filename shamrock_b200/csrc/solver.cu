@@ -315,6 +315,25 @@ void Model::keep_flagged(PatchD &p, u32 *out_kept) {
     p.f.n = kept;
 }
 
+/// modules::ParticleReordering::reorder_particles (shammodels/sph/src/modules/ParticleReordering.cpp:22-51):
+/// per patch, the Morton order of the positions over the PATCH box (RadixTreeMortonBuilder.cpp:68-107) and
+/// PatchDataLayer::index_remap — new[i] = old[index_map[i]] for every field of the main layout
+void Model::reorder_particles() {
+    SB_CUDA_CHECK(cudaSetDevice(ctx->device));
+    for (auto &p : patches) {
+        if (!is_local(p) || !p.f.n)
+            continue;
+        const u32 n = p.f.n;
+        morton_sort_permutation(s(), reorder_tree, p.f.xyz.p, 3, n, p.lo, p.hi, cfg.sort_mode);
+        for (auto &r : p.f.all()) {
+            field_tmp.ensure(size_t(n) * r.nvar + 1);
+            gather_field(s(), n, r.nvar, reorder_tree.index_map.p, r.buf->p, field_tmp.p);
+            SB_CUDA_CHECK(cudaMemcpyAsync(
+                r.buf->p, field_tmp.p, size_t(n) * r.nvar * sizeof(f64), cudaMemcpyDeviceToDevice, s()));
+        }
+    }
+}
+
 /// ExternalForces::point_mass_accrete_particles (ExternalForces.cpp:593-700)
 void Model::point_mass_accrete_particles() {
     if (!cfg.has_point_mass)
@@ -918,6 +937,14 @@ void Model::evolve_once() {
             npart_all += p.f.n;
     comm_allreduce_host_u64(*this, &npart_all, 1, 0);
 
+    // Solver.cpp:2043-2048
+    if (cfg.enable_particle_reordering && cfg.particle_reordering_step_freq
+        && step_count % cfg.particle_reordering_step_freq == 0) {
+        if (pipe.active && pipe.defer_in2) // host-resident step: every input field must have arrived
+            SB_CUDA_CHECK(cudaStreamWaitEvent(s(), pipe.ev_in2, 0));
+        reorder_particles();
+    }
+
     sph_prestep();
     if (piped) {
         static const char *const early[] = {"xyz", "hpart", "axyz_ext"};
@@ -1060,6 +1087,7 @@ void Model::evolve_once() {
     time = t_current + dt_;
     f64 stiff      = cfg.cfl_multiplier_stiffness;
     cfl_multiplier = (cfl_multiplier * stiff + 1.) / (stiff + 1.);
+    step_count++;
     t_step         = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
 }
 

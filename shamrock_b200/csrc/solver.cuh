@@ -101,6 +101,8 @@ struct Model {
     f64 eps_v = 0, t_step = 0;
     u32 h_subcycles = 0, h_iters_last = 0, corrector_iter = 0;
     u64 npart_all = 0, K_local = 0, pair_tests_local = 0;
+    u64 step_count = 0; ///< SolverLog::step_count: steps done so far
+    TreeBuffers reorder_tree; ///< Morton codes / permutation of reorder_particles
     std::vector<Iface> ifaces;
     StageTimer timer;
     // scratch
@@ -147,6 +149,7 @@ struct Model {
     void kill_particles();
     void compute_ext_forces_indep_v();
     void apply_position_boundary();
+    void reorder_particles();
     void reattribute_patch_objects();
     void build_ghost_cache();
     void merge_position_ghost();

@@ -570,6 +570,36 @@ __global__ void __launch_bounds__(128) leaf_field_max_propagate_kernel(
 // =============================================================================================
 // host drivers
 // =============================================================================================
+/// Morton codes over the box [bmin, bmax] + key/value sort: t.index_map[0..M) is the Morton order of the
+/// objects (shamtree/src/RadixTreeMortonBuilder.cpp:68-107, the part modules::ParticleReordering needs)
+void morton_sort_permutation(
+    cudaStream_t s, TreeBuffers &t, const f64 *d_xyz, size_t stride, u32 M, const f64 *bmin, const f64 *bmax,
+    int sort_mode) {
+    if (M == 0)
+        return;
+    t.M  = M;
+    t.P2 = roundup_pow2(M);
+    t.bbox.ensure(8);
+    t.scalars.ensure(16);
+    t.h_scalars.ensure(16);
+    f64 hb[6] = {bmin[0], bmin[1], bmin[2], bmax[0], bmax[1], bmax[2]};
+    f64 *hp   = reinterpret_cast<f64 *>(t.h_scalars.p + 8);
+    std::memcpy(hp, hb, sizeof(hb));
+    SB_CUDA_CHECK(cudaMemcpyAsync(t.bbox.p, hp, sizeof(hb), cudaMemcpyHostToDevice, s));
+    t.morton.ensure(t.P2);
+    t.index_map.ensure(t.P2);
+    morton_kernel<<<grid_for(t.P2, 256), 256, 0, s>>>(d_xyz, stride, M, t.P2, t.bbox.p, t.morton.p, t.index_map.p);
+    SB_COUNT_LAUNCH();
+    if (sort_mode == SORT_RADIX) {
+        t.morton_alt.ensure(t.P2);
+        t.index_alt.ensure(t.P2);
+        radix_sort_by_key(s, t.morton.p, t.index_map.p, t.morton_alt.p, t.index_alt.p, M, 32, t.radix_hist);
+    } else {
+        bitonic_sort_by_key(s, t.morton.p, t.index_map.p, t.P2);
+    }
+    SB_LAUNCH_CHECK();
+}
+
 void tree_build(
     cudaStream_t s, TreeBuffers &t, const f64 *d_xyz, size_t stride, u32 M, const f64 *bmin,
     const f64 *bmax, bool auto_bbox, u32 reduction_level, int sort_mode) {

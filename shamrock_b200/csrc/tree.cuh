@@ -33,6 +33,11 @@ void tree_build(
     cudaStream_t s, TreeBuffers &t, const f64 *d_xyz, size_t stride_dbl, u32 M, const f64 *bmin,
     const f64 *bmax, bool auto_bbox, u32 reduction_level, int sort_mode);
 
+/// Morton codes over [bmin, bmax] + sort only: t.index_map[0..M) = Morton order of the objects
+void morton_sort_permutation(
+    cudaStream_t s, TreeBuffers &t, const f64 *d_xyz, size_t stride_dbl, u32 M, const f64 *bmin, const f64 *bmax,
+    int sort_mode);
+
 /// out[node] = scale * max over the node's objects of field[obj]   ([I+L])
 void tree_field_max(cudaStream_t s, TreeBuffers &t, const f64 *d_field, f64 scale, f64 *d_out, size_t field_stride = 1);
 

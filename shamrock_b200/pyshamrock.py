@@ -165,6 +165,14 @@ class SolverConfig:
     def set_two_stage_search(self, enable):
         self._c.update(use_two_stage_search=int(bool(enable)))
 
+    def set_enable_particle_reordering(self, enable):
+        self._c["enable_particle_reordering"] = int(bool(enable))
+
+    def set_particle_reordering_step_freq(self, freq):
+        if int(freq) == 0:
+            raise ValueError("particle_reordering_step_freq cannot be zero")
+        self._c["particle_reordering_step_freq"] = int(freq)
+
     def set_smoothing_length_density_based(self):
         pass  # the default (and only) mode of this path
 
@@ -229,6 +237,9 @@ class SPHSetup:
         if setup is None:
             raise ValueError("The setup shared pointer is empty")
         self._m._append(setup.pos, setup.h)
+        # SPHSetup.cpp:202-205: modules::ParticleReordering once the particles are in place (done on the
+        # device when the patch data goes up: the fields set by position in between move with their particles)
+        self._m._reorder_at_push = self._m._reorder_at_push or bool(part_reordering)
 
 
 # ---- analysis ----------------------------------------------------------------------------------------------
@@ -284,6 +295,7 @@ class Model:
         self._callbacks = []
         self._last = {}
         self._dirty, self._on_device, self._host_fresh = True, False, True
+        self._reorder_at_push = False
 
     # -- configuration
     def gen_default_config(self):
@@ -449,6 +461,9 @@ class Model:
                 raise RuntimeError("particles cannot be added once the simulation has started")
             for nm in _MAIN:
                 self._dev.set_field(0, nm, self._host[nm])
+        if first and self._reorder_at_push:
+            self._dev.reorder_particles()
+            self._host_fresh = False  # the host copy is in generation order
         self._dirty, self._on_device = False, True
 
     def _pull(self):

@@ -225,6 +225,8 @@ def main():
     ap.add_argument("--fp", default="fast", choices=["fast", "strict"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-reorder", action="store_true",
+                    help="keep the generation order of the lattice (the reference's apply_setup reorders by default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -263,6 +265,8 @@ def main():
     ctx = _capi.Context(local)
     m = S.make_cuda(sc, ctx=ctx, keep_step_data=False, rank=rank, world=world, nccl_id=nccl_id, fp_mode=args.fp)
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+    if not args.no_reorder:  # SPHSetup::apply_setup(part_reordering = true), the protocol's default
+        m.reorder_particles()
 
     def barrier():
         if world > 1:
@@ -406,6 +410,9 @@ def main():
                        "injection, dt=0 replay (reference protocol sph_homogeneous_benchmark.py)",
                        "npart_total": n_total, "npart_per_gpu": n_total // world, "neighbours_per_particle": K / max(N, 1),
                        "patches": list(sc["grid"]), "sort": sc["sort_mode"],
+                       "setup": "lattice order" if args.no_reorder else
+                       "patch data Morton-reordered once after the setup (apply_setup part_reordering=True, the "
+                       "reference's default)",
                        "fp": {"fast": "fast (FMA, per-particle reciprocals; parity 1e-10 relative vs the oracle)",
                               "strict": "strict (no FMA, bit-identical to the oracle)"}[args.fp],
                        "l2": "inputs larger than L2 (no flush needed)",

@@ -12,6 +12,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-fi
 # full captures of the heavy kernels (one launch each, taken in the 3rd step)
 ncu --set full --clock-control none --import-source on \
     -k regex:'group_walk|neigh_lists|h_solve|av_operators|force_cfl|radix_scatter|sort_gather' \
-    -s 27 -c 12 -o gpurun_out/prof_$TAG -f \
+    -s 31 -c 12 -o gpurun_out/prof_$TAG -f \
     python bench.py --steps 1 --warmup 3 --npart-per-gpu $NP --no-cpu-baseline --no-e2e > gpurun_out/ncu_full_$TAG.log 2>&1
 ls -la gpurun_out

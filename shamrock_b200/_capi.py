@@ -2,6 +2,7 @@
 GPU (symbols can be inspected), every compute entry point needs a CUDA device."""
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -157,9 +158,14 @@ class Context:
         check(lib().shamb200_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
         self.h = h
         self.device = device
+        self._models = weakref.WeakSet()  # models running on this context: destroyed before it
 
     def close(self):
         if getattr(self, "h", None):
+            # the garbage collector finalises a model and its context in any order: a model must never
+            # outlive the stream it runs on
+            for m in list(getattr(self, "_models", ())):
+                m.close()
             lib().shamb200_ctx_destroy(self.h)
             self.h = None
 
@@ -311,6 +317,7 @@ class Model:
         h = C.c_void_p()
         check(lib().shamb200_model_create(ctx.h, C.byref(cfg), C.byref(h)))
         self.h = h
+        ctx._models.add(self)
 
     def close(self):
         if getattr(self, "h", None):

@@ -96,6 +96,7 @@ int shamb200_ctx_destroy(shamb200_ctx *ctx) {
         if (ctx->c.own_stream)
             cudaStreamDestroy(ctx->c.stream);
         delete ctx;
+        cudaGetLastError(); // a failure while tearing down must not surface in a later launch check
     });
 }
 void *shamb200_ctx_stream(shamb200_ctx *ctx) { return ctx ? (void *) ctx->c.stream : nullptr; }
@@ -308,6 +309,7 @@ int shamb200_model_destroy(shamb200_model *m) {
             cudaStreamSynchronize(m->m.ctx->stream);
             comm_destroy(m->m);
             delete m;
+            cudaGetLastError(); // a failure while tearing down must not surface in a later launch check
         }
     });
 }

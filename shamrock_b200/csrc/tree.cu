@@ -598,6 +598,9 @@ void morton_sort_permutation(
         bitonic_sort_by_key(s, t.morton.p, t.index_map.p, t.P2);
     }
     SB_LAUNCH_CHECK();
+    // the box went up from the pinned staging words of `t`: they must not be rewritten (next patch) before
+    // the copy has run
+    SB_CUDA_CHECK(cudaStreamSynchronize(s));
 }
 
 void tree_build(

@@ -381,13 +381,21 @@ def main():
                         "GB/s": w[0] / (ms_k * 1e-3) / 1e9, "TFLOP/s": w[1] / (ms_k * 1e-3) / 1e12}
         top = max(table, key=lambda k: table[k]["ms"])
         tt = table[top]
-        # DRAM bytes of one launch of that kernel from the committed ncu --set full capture of this workload
+        # DRAM bytes of one launch of that kernel from the committed ncu --set full capture of this workload;
+        # the same capture gives, per heavy kernel, the utilisation of the units that actually bind it (the
+        # neighbour loops saturate the L1 data pipe of the LSU - 32-byte record gathers - before the FP64 pipe)
         traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic_17M.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
-            if abs(tj["npart"] - n_local) <= 0.01 * n_local and top in tj["stages"]:
-                traffic, traffic_src = tj["stages"][top]["traffic"], "profiles/traffic_17M.json (" + tj["stages"][top]["kernel"] + ")"
+            if abs(tj["npart"] - n_local) <= 0.01 * n_local:
+                if top in tj["stages"]:
+                    traffic = tj["stages"][top]["traffic"]
+                    traffic_src = "profiles/traffic_17M.json (" + tj["stages"][top]["kernel"] + ")"
+                for k, v in tj["stages"].items():
+                    if k in table:
+                        table[k]["ncu"] = {q: v[q] for q in ("fp64_pipe_pct", "l1_lsu_data_pipe_pct", "issue_active_pct")
+                                           if q in v}
         roofline = {"bound": tt["bound"], "kernel": top,
                     "achieved": tt["TFLOP/s"] if tt["bound"] == "fp64" else tt["GB/s"],
                     "peak": fp64_peak if tt["bound"] == "fp64" else hbm_peak,
@@ -398,7 +406,9 @@ def main():
                     "peak_source": {"hbm_gbs": hbm_peak, "hbm": peak_src, "fp64_tflops": fp64_peak,
                                     "fp64": "measured here: FP64 FMA chains (shamb200_microbench), FMA = 2 flop",
                                     "copy_gbs_here": copy_bw},
-                    "note": "roof = slower of the FP64 pipe and HBM (north star); flops: FMA=2, div/sqrt=1",
+                    "note": "roof = slower of the FP64 pipe and HBM (north star); flops: FMA=2, div/sqrt=1; "
+                            "stages[*].ncu = unit utilisation from the committed ncu capture (profiles/traffic_17M.json): "
+                            "the neighbour loops run at 75-97 % of the L1 LSU data pipe",
                     "ms_per_launch": tt["ms"], "stages": table,
                     "stage_ms": {k: round(v, 3) for k, v in per_stage.items()}}
         line = {

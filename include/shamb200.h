@@ -240,6 +240,18 @@ int shamb200_plan_interfaces(uint32_t npatch, const double *boxes, const double 
                              int periodic, const double *interact_r, const uint32_t *pcount, uint32_t cap,
                              shamb200_iface *out, uint32_t *n_found);
 
+/* Hilbert index of a cell of the 2^21-per-axis patch grid (shamrock::sfc::HilbertCurve<u64, 3>::icoord_to_hilbert,
+ * shammath/include/shammath/sfc/hilbert.hpp:36-87) */
+uint64_t shamb200_hilbert_index(uint64_t x, uint64_t y, uint64_t z);
+/* replaces the owner table of shamrock::scheduler::HilbertLoadBalance<u64>::make_change_list
+ * (shamrock/src/scheduler/HilbertLoadBalance.cpp:46-75): patches ordered by the Hilbert index of their
+ * coord_min [npatch * 3], loads = particle counts (ComputeLoadBalanceValue.cpp:23-30), and
+ * shamrock::scheduler::load_balance (loadbalance/LoadBalanceStrategy.hpp:274-312: parallel sweep against
+ * round robin, the smaller maximum rank load wins, round robin favoured by 0.95).
+ * owner [npatch]; *strategy (may be NULL): 0 parallel sweep, 1 round robin. */
+int shamb200_plan_load_balance(uint32_t npatch, const uint64_t *coord_min, const uint64_t *load, int world_size,
+                               int32_t *owner, int *strategy);
+
 /* ---- model (shammodels::sph::Model<f64_3, Kernel> / Solver::evolve_once) -------------------------
  * Host-side drop-in: owns the patch data on the device and runs the whole step on the GPU.
  * Mirrors shammodels/sph/include/shammodels/sph/Model.hpp:55-1076 and Solver.cpp:1942-3272 for
@@ -280,6 +292,12 @@ int shamb200_model_set_config(shamb200_model *m, const shamb200_solver_config *c
  * patch grid of PatchScheduler; patches are dealt to ranks in id order, contiguously. */
 int shamb200_model_set_box(shamb200_model *m, const double bmin[3], const double bmax[3], uint32_t nx,
                            uint32_t ny, uint32_t nz);
+/* patch -> rank table (one entry per patch of the grid, patch id order), e.g. from shamb200_plan_load_balance
+ * on the particle counts of the setup; allowed while no particle has been pushed (patches do not migrate
+ * between ranks afterwards).  Every rank passes the same table.  coord_min [npatch * 3] (may be NULL)
+ * receives the patches' coordinates on the integer grid. */
+int shamb200_model_set_patch_owners(shamb200_model *m, uint32_t npatch, const int32_t *owner);
+int shamb200_model_patch_coords(shamb200_model *m, uint32_t npatch, uint64_t *coord_min);
 /* multi-GPU: rank/size of this process and the NCCL unique id (128 bytes, from
  * shamb200_nccl_unique_id on rank 0, broadcast by the caller).  Optional (single GPU otherwise). */
 int shamb200_nccl_unique_id(void *out128);

@@ -92,7 +92,8 @@ SYMBOLS = [
     "shamb200_model_search_stats", "shamb200_model_state",
     "shamb200_model_set_next_dt", "shamb200_model_set_time", "shamb200_model_set_cfl_multiplier",
     "shamb200_model_stage_times", "shamb200_plan_patch_grid", "shamb200_plan_interfaces",
-    "shamb200_microbench",
+    "shamb200_microbench", "shamb200_hilbert_index", "shamb200_plan_load_balance",
+    "shamb200_model_set_patch_owners", "shamb200_model_patch_coords",
     "shamb200_compute_eos", "shamb200_update_divv_curlv", "shamb200_update_dtdivv", "shamb200_update_viscosity",
     "shamb200_update_derivs", "shamb200_vsig_cfl", "shamb200_leapfrog_predict", "shamb200_leapfrog_correct",
 ]
@@ -125,6 +126,8 @@ def lib():
         L.shamb200_model_get.restype = C.c_int64
         L.shamb200_model_patch_count.restype = C.c_uint32
         L.shamb200_model_patch_size.restype = C.c_uint32
+        L.shamb200_hilbert_index.restype = C.c_uint64
+        L.shamb200_hilbert_index.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
         L.shamb200_ctx_create.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
         L.shamb200_model_create.argtypes = [C.c_void_p, C.POINTER(SolverConfig), C.POINTER(C.c_void_p)]
         _lib = L
@@ -134,6 +137,25 @@ def lib():
 def check(rc):
     if rc != 0:
         raise ShamB200Error(f"[{rc}] " + lib().shamb200_last_error().decode())
+
+
+def hilbert_index(x, y, z):
+    """Hilbert index of a cell of the 2^21-per-axis patch grid (host only)"""
+    return int(lib().shamb200_hilbert_index(int(x), int(y), int(z)))
+
+
+def plan_load_balance(coord_min, load, world_size):
+    """patch -> rank along the Hilbert curve (HilbertLoadBalance + load_balance of the reference, host only).
+    Returns (owner[npatch], strategy) with strategy 'psweep' or 'round robin'."""
+    c = np.ascontiguousarray(coord_min, dtype=np.uint64).reshape(-1, 3)
+    l = np.ascontiguousarray(load, dtype=np.uint64)
+    assert len(c) == len(l)
+    owner = np.zeros(len(l), dtype=np.int32)
+    strat = C.c_int(0)
+    check(lib().shamb200_plan_load_balance(
+        C.c_uint32(len(l)), c.ctypes.data_as(C.c_void_p), l.ctypes.data_as(C.c_void_p), int(world_size),
+        owner.ctypes.data_as(C.c_void_p), C.byref(strat)))
+    return owner, ("psweep", "round robin")[strat.value]
 
 
 def default_config():
@@ -337,6 +359,18 @@ class Model:
     def set_box(self, bmin, bmax, grid=(1, 1, 1)):
         check(lib().shamb200_model_set_box(self.h, (C.c_double * 3)(*bmin), (C.c_double * 3)(*bmax),
                                            *[C.c_uint32(g) for g in grid]))
+
+    def patch_coords(self):
+        """coord_min of every patch on the 2^21 integer grid, [npatch, 3]"""
+        n = self.patch_count
+        out = np.zeros((n, 3), dtype=np.uint64)
+        check(lib().shamb200_model_patch_coords(self.h, C.c_uint32(n), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def set_patch_owners(self, owner):
+        """patch -> rank table (before any particle is pushed), e.g. from plan_load_balance"""
+        o = np.ascontiguousarray(owner, dtype=np.int32)
+        check(lib().shamb200_model_set_patch_owners(self.h, C.c_uint32(len(o)), o.ctypes.data_as(C.c_void_p)))
 
     def init_comm(self, rank, world, nccl_id):
         buf = (C.c_char * 128).from_buffer_copy(bytes(nccl_id))

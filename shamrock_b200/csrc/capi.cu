@@ -1,5 +1,6 @@
 // capi.cu — the extern "C" boundary declared in include/shamb200.h.
 #include "solver.cuh"
+#include "load_balance.hpp"
 #include <cstring>
 
 using namespace sb;
@@ -230,6 +231,42 @@ int shamb200_plan_patch_grid(
             }
             owner[k] = g[k].owner;
         }
+    });
+}
+uint64_t shamb200_hilbert_index(uint64_t x, uint64_t y, uint64_t z) { return hilbert_index_3d(x, y, z); }
+int shamb200_plan_load_balance(
+    uint32_t npatch, const uint64_t *coord_min, const uint64_t *load, int world_size, int32_t *owner, int *strategy) {
+    return guard([&] {
+        if ((npatch && (!coord_min || !load || !owner)))
+            throw std::invalid_argument("load balance: null argument");
+        std::vector<uint64_t> c(coord_min, coord_min + size_t(3) * npatch), l(load, load + npatch);
+        auto o = hilbert_load_balance(c, l, world_size, strategy);
+        std::copy(o.begin(), o.end(), owner);
+    });
+}
+int shamb200_model_set_patch_owners(shamb200_model *m, uint32_t npatch, const int32_t *owner) {
+    return guard([&] {
+        Model &M = m->m;
+        if (npatch != M.patches.size())
+            throw std::invalid_argument("set_patch_owners: one owner per patch of the grid");
+        for (auto &p : M.patches)
+            if (p.f.n)
+                throw std::invalid_argument("set_patch_owners: particles have already been pushed");
+        for (uint32_t k = 0; k < npatch; k++) {
+            if (owner[k] < 0 || owner[k] >= M.world)
+                throw std::invalid_argument("set_patch_owners: owner outside the world");
+            M.patches[k].owner = owner[k];
+        }
+    });
+}
+int shamb200_model_patch_coords(shamb200_model *m, uint32_t npatch, uint64_t *coord_min) {
+    return guard([&] {
+        Model &M = m->m;
+        if (npatch != M.patches.size() || !coord_min)
+            throw std::invalid_argument("patch_coords: one entry per patch of the grid");
+        for (uint32_t k = 0; k < npatch; k++)
+            for (int d = 0; d < 3; d++)
+                coord_min[3 * k + d] = M.patches[k].cmin[d];
     });
 }
 int shamb200_plan_interfaces(

@@ -29,6 +29,9 @@ def main():
     elif which == "sod":
         sc = S.sod_tube(16, "M6", grid=(4, 1, 1))
         steps, rtol = 2, 0.0
+    elif which == "disc_balanced":  # thin disc on a 4 x 4 x 2 grid: most of the load in a few patches
+        sc = S.disc(8000, "M4", grid=(4, 4, 2))
+        steps, rtol = 2, 1e-12
     else:
         sc = S.disc(8000, "M4", grid=(2, 2, 2))
         steps, rtol = 2, 1e-12
@@ -36,7 +39,12 @@ def main():
     if not strict:
         rtol = 1e-10
     o = S.make_oracle(sc)
-    m = S.make_cuda(sc, ctx=_capi.Context(local), rank=rank, world=world, nccl_id=ids[0], fp_mode=fp_mode)
+    balance = which == "disc_balanced"
+    m = S.make_cuda(sc, ctx=_capi.Context(local), rank=rank, world=world, nccl_id=ids[0], fp_mode=fp_mode,
+                    balance=balance)
+    if balance:  # both ranks hold about half of the particles
+        n_loc = sum(m.patch_size(ip) for ip in range(m.patch_count) if m.patch_is_local(ip))
+        assert abs(n_loc - len(sc["xyz"]) / world) <= 0.2 * len(sc["xyz"]) / world, (rank, n_loc)
     names = ["xyz", "vxyz", "axyz", "hpart", "uint", "duint", "step.mxyz", "step.omega", "step.pressure", "step.g_v",
              "step.vsig"]
     if sc["cfg"]["av"] == 3:

@@ -158,7 +158,19 @@ def make_oracle(sc):
     return s
 
 
-def make_cuda(sc, ctx=None, keep_step_data=True, rank=0, world=1, nccl_id=None, fp_mode="strict"):
+def patch_loads(sc, world=1):
+    """particles of the scenario per patch of its grid (patch id order) — the load values of the balancer"""
+    from shamrock_b200 import _capi
+
+    boxes, _ = _capi.plan_patch_grid(sc["bmin"], sc["bmax"], sc["grid"], world)
+    x = np.asarray(sc["xyz"])
+    return np.array([int(np.all((x >= np.array(lo)) & (x < np.array(hi)), axis=1).sum()) for lo, hi in boxes],
+                    dtype=np.uint64)
+
+
+def make_cuda(sc, ctx=None, keep_step_data=True, rank=0, world=1, nccl_id=None, fp_mode="strict", balance=False):
+    """balance=True: patches dealt to the ranks by the Hilbert-curve load balancer on the particle counts of the
+    setup (shamb200_plan_load_balance) instead of contiguous blocks of patch ids"""
     from shamrock_b200 import _capi
 
     ctx = ctx or _capi.Context(0)
@@ -178,5 +190,8 @@ def make_cuda(sc, ctx=None, keep_step_data=True, rank=0, world=1, nccl_id=None, 
     if world > 1:
         m.init_comm(rank, world, nccl_id)
     m.set_box(sc["bmin"], sc["bmax"], sc["grid"])
+    if balance:
+        owner, _ = _capi.plan_load_balance(m.patch_coords(), patch_loads(sc, world), world)
+        m.set_patch_owners(owner)
     m.push_particles(sc["xyz"], sc["vxyz"], sc["hpart"], sc["uint"])
     return m

@@ -25,7 +25,15 @@ SCENARIOS = {
     "periodic_M6_mm97": lambda: S.periodic_box(2500, "M6", "mm97", jitter=0.15),
     "periodic_M4_constant": lambda: S.periodic_box(2500, "M4", "constant", jitter=0.15),
     "disc_M4": lambda: disc_without_removal(),
+    "periodic_M6_cd10_combined": lambda: combined_cd10(),
 }
+
+
+def combined_cd10():
+    """CD10 with combined_dtdiv_divcurlv_compute: div v, curl v and d(div v)/dt from one velocity-gradient matrix"""
+    sc = S.periodic_box(2500, "M6", "cd10", jitter=0.15)
+    sc["cfg"] = dict(sc["cfg"], combined_dtdiv_divcurlv_compute=1)
+    return sc
 
 
 def disc_without_removal():
@@ -108,7 +116,18 @@ def test_modules_against_oracle(ctx, name):
     same(cs.cpu().numpy(), g["soundspeed"], "soundspeed", rt)
 
     # ---- DiffOperators / DiffOperatorDtDivv / UpdateViscosity (MM97, CD10)
-    if vary:
+    combined = bool(cfg.get("combined_dtdiv_divcurlv_compute"))
+    if vary and combined:
+        divv = torch.empty(n, dtype=torch.float64, device="cuda")
+        curlv = torch.empty(3 * n, dtype=torch.float64, device="cuda")
+        dtdivv = torch.empty(n, dtype=torch.float64, device="cuda")
+        ctx.update_dtdivv(kernel, cv, fields(vxyz=t["g_v"], axyz=g_a), pmass, dtdivv, also_divv_curlv=True, divv_t=divv,
+                          curlv_t=curlv)
+        ctx.synchronize()
+        same(divv.cpu().numpy(), o.get(ip, "divv"), "divv (combined)")
+        same(curlv.cpu().numpy().reshape(-1, 3), o.get(ip, "curlv"), "curlv (combined)")
+        same(dtdivv.cpu().numpy(), o.get(ip, "dtdivv"), "dtdivv (combined)")
+    elif vary:
         divv = torch.empty(n, dtype=torch.float64, device="cuda")
         curlv = torch.empty(3 * n, dtype=torch.float64, device="cuda") if cfg["av"] == 3 else None
         ctx.update_divv_curlv(kernel, cv, fields(vxyz=t["g_v"], omega=t["g_omega"]), pmass, divv, curlv)
@@ -121,6 +140,7 @@ def test_modules_against_oracle(ctx, name):
             ctx.update_dtdivv(kernel, cv, fields(vxyz=t["g_v"], axyz=g_a), pmass, dtdivv)
             ctx.synchronize()
             same(dtdivv.cpu().numpy(), o.get(ip, "dtdivv"), "dtdivv")
+    if vary:
         alpha_new = torch.empty(n, dtype=torch.float64, device="cuda")
         ctx.update_viscosity(av, n, dt, cfg["sigma_decay"], cfg["alpha_min"], cfg["alpha_max"], divv, curlv, dtdivv,
                              dev(cs_old), t["g_h"], dev(alpha_old), alpha_new)
@@ -164,6 +184,27 @@ def test_modules_against_oracle(ctx, name):
         assert abs(sum_v2 - (vn * vn).sum()) <= 1e-12 * (vn * vn).sum() + 1e-300
         eps_v = np.sqrt(max_dv2) / np.sqrt(sum_v2 / n) if sum_v2 > 0 else 0.0
         assert abs(eps_v - st["eps_v"]) <= 1e-12 * max(st["eps_v"], 1e-300)
+
+
+def test_modules_on_empty_patch(ctx):
+    """a patch without objects: every module returns without touching anything"""
+    z = torch.zeros(4, dtype=torch.float64, device="cuda")
+    zi = torch.zeros(4, dtype=torch.int32, device="cuda")
+    f = ctx.merged_fields(0, 0, z, z, vxyz=z, uint=z, axyz=z, omega=z, pressure=z, soundspeed=z, alpha_AV=z)
+    cv = _capi.CsrView()
+    cv.obj_cnt, cv.sum_neigh_cnt = 0, 0
+    cv.d_cnt_neigh, cv.d_scanned_cnt, cv.d_index_neigh_map = zi.data_ptr(), zi.data_ptr(), zi.data_ptr()
+    out = torch.full((4,), 7.0, dtype=torch.float64, device="cuda")
+    ctx.compute_eos("M4", "adiabatic", f, 1.0, 1.4, 0.0, 0.0, 1.0, out, out)
+    ctx.update_divv_curlv("M4", cv, f, 1.0, out, out)
+    ctx.update_dtdivv("M6", cv, f, 1.0, out, also_divv_curlv=True, divv_t=out, curlv_t=out)
+    ctx.update_viscosity("varying_cd10", 0, 0.1, 0.1, 0.0, 1.0, out, out, out, z, z, z, out)
+    ctx.update_derivs("M4", "varying_cd10", cv, f, 1.0, 1.0, 1.0, 2.0, None, out, out)
+    assert ctx.vsig_cfl("M4", cv, f, z, 0.3, 0.25, out, out) == float("inf")
+    ctx.leapfrog_predict(0, 0.1, out, out, z, out, z)
+    assert ctx.leapfrog_correct(0, 0.05, out, z, z, out, z, z) == (0.0, 0.0)
+    ctx.synchronize()
+    assert torch.all(out == 7.0)
 
 
 def test_modules_reject_bad_arguments(ctx):

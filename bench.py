@@ -299,6 +299,9 @@ def main():
         clocks.start()
     fp64_peak = ctx.microbench("fp64")
     copy_bw = ctx.microbench("copy")
+    # 32-byte record gathers from an L1-resident table (microbench.cu): the rate of the unit that binds the SPH
+    # neighbour loops, for a random record per lane (what a neighbour list is) and for the conflict-free case
+    gather_random, gather_aligned = ctx.microbench(11), ctx.microbench(12)
 
     # warm-up: first real timestep (converges h), then dt = 0 replays
     m.evolve_once()
@@ -379,6 +382,11 @@ def main():
             bound = "fp64" if t_fp > t_hbm else "hbm"
             table[k] = {"ms": round(ms_k, 3), "bound": bound, "frac": max(t_hbm, t_fp) / (ms_k * 1e-3),
                         "GB/s": w[0] / (ms_k * 1e-3) / 1e9, "TFLOP/s": w[1] / (ms_k * 1e-3) / 1e12}
+        # records gathered per launch by the three neighbour loops (one 32-byte record per list entry and array)
+        for k, nrec in (("h_iteration", (sweeps + 1) * K), ("divv_curlv_dtdivv", 3 * K), ("forces", 3 * K)):
+            if k in table:
+                rate = nrec / (table[k]["ms"] * 1e-3) / 1e9
+                table[k]["gather"] = {"records": nrec, "Grec/s": rate, "frac_of_l1_random_gather": rate / gather_random}
         top = max(table, key=lambda k: table[k]["ms"])
         tt = table[top]
         # DRAM bytes of one launch of that kernel from the committed ncu --set full capture of this workload;
@@ -405,7 +413,11 @@ def main():
                     "accept_tests_per_particle": tests / max(N, 1),
                     "peak_source": {"hbm_gbs": hbm_peak, "hbm": peak_src, "fp64_tflops": fp64_peak,
                                     "fp64": "measured here: FP64 FMA chains (shamb200_microbench), FMA = 2 flop",
-                                    "copy_gbs_here": copy_bw},
+                                    "copy_gbs_here": copy_bw,
+                                    "l1_gather_random_Grec_s": gather_random,
+                                    "l1_gather_bank_aligned_Grec_s": gather_aligned,
+                                    "l1_gather": "measured here: one 256-bit load per lane from a 32 KB table "
+                                                 "(shamb200_microbench 11 / 12), G records of 32 B per second"},
                     "note": "roof = slower of the FP64 pipe and HBM (north star); flops: FMA=2, div/sqrt=1; "
                             "stages[*].ncu = unit utilisation from the committed ncu capture (profiles/traffic_17M.json): "
                             "the neighbour loops run at 75-97 % of the L1 LSU data pipe",

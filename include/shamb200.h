@@ -72,7 +72,10 @@ int shamb200_ctx_synchronize(shamb200_ctx *ctx);
 
 /* roofline denominators measured on this device (pattern of the reference's own micro-benchmarks,
  * shamsys/src/MicroBenchmark.cpp:51-77): what = 0 FP64 FMA chains [TFLOP/s, FMA = 2 flop],
- * what = 1 streaming copy [GB/s, read + write]. */
+ * what = 1 streaming copy [GB/s, read + write]; what = 10 + p / 20 + p: warp-wide gathers of 32-byte records
+ * (one 256-bit load per lane, the access pattern of the SPH neighbour loops) from an L1- / L2-resident table
+ * [G records/s]: p = 0 coalesced, 1 random record per lane, 2 random line per lane with bank group = lane & 3,
+ * 3 random line per lane in one bank group, 4 four lanes per random line. */
 int shamb200_microbench(shamb200_ctx *ctx, int what, double *out);
 
 /* ---- tree (shamtree::CompressedLeafBVH<u32, f64_3, 3>) ----------------------------------------

@@ -6,6 +6,7 @@
 // relative to /root/reference/src.  Every device operation is a hand-written kernel of this
 // library; there is no CPU fallback for any stage.
 #include "solver.cuh"
+#include <cstdlib>
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -999,14 +1000,21 @@ void Model::evolve_once() {
                 compute_eos(
                     s(), cfg.kernel, cfg.eos, p.st.srch.SA.p, p.st.SB.p, p.st.SC.p, p.st.m, cfg.gpart_mass, cfg.gamma,
                     cfg.cs0, cfg.eos_q, cfg.eos_r0);
+        // adiabatic EOS: the force loop reads a 16-byte third record and recomputes the neighbour's rho and P
+        // (SHAMB200_SF16=0 keeps the 32-byte record: tuning runs)
+        const char *sf16_env = getenv("SHAMB200_SF16");
+        const bool sf16 = cfg.fp_mode == SHAMB200_FP_FAST && cfg.eos == SHAMB200_EOS_ADIABATIC
+                          && !(sf16_env && atoi(sf16_env) == 0);
         if (cfg.fp_mode == SHAMB200_FP_FAST)
             for (auto &p : patches)
                 if (is_local(p) && p.f.n) {
                     p.st.SE.ensure(p.st.m, 1.1);
                     p.st.SF.ensure(p.st.m, 1.1);
+                    if (sf16)
+                        p.st.SG.ensure(p.st.m, 1.1);
                     derive_fast(
                         s(), cfg.kernel, cfg.av, p.st.m, p.st.srch.SA.p, p.st.SB.p, p.st.SC.p, cfg.gpart_mass,
-                        cfg.alpha_AV, p.st.SE.p, p.st.SF.p);
+                        cfg.alpha_AV, p.st.SE.p, p.st.SF.p, sf16 ? p.st.SG.p : nullptr);
                 }
         if (piped && corrector_iter_cnt == 0) {
             static const char *const mid[] = {"divv", "curlv", "dtdivv", "alpha_AV@updated"};
@@ -1028,9 +1036,14 @@ void Model::evolve_once() {
             st.cfl_dt.ensure(st.n);
             SB_CUDA_CHECK(cudaMemcpyAsync(st.a_old.p, p.f.axyz.p, size_t(st.n) * 3 * sizeof(f64), cudaMemcpyDeviceToDevice, s()));
             SB_CUDA_CHECK(cudaMemcpyAsync(st.du_old.p, p.f.duint.p, size_t(st.n) * sizeof(f64), cudaMemcpyDeviceToDevice, s()));
+            SphParams spf = sp;
+            if (sf16) {
+                spf.adiabatic_gm1 = cfg.gamma - 1;
+                spf.SG            = st.SG.p;
+            }
             force_cfl(
                 s(), cfg.fp_mode, cfg.kernel, cfg.av, rank_csr_of(st.srch, st.tree), st.srch.SA.p, st.SB.p, st.SC.p,
-                st.SE.p, st.SF.p, sp, p.f.axyz_ext.p, p.f.axyz.p, p.f.duint.p, C_cour, C_force, st.vsig.p, st.cfl_dt.p,
+                st.SE.p, st.SF.p, spf, p.f.axyz_ext.p, p.f.axyz.p, p.f.duint.p, C_cour, C_force, st.vsig.p, st.cfl_dt.p,
                 red.p + 4);
         }
         timer.mark(s(), "corrector");

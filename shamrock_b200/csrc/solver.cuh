@@ -61,6 +61,7 @@ struct PatchStep {
     DevBuf<Pack4> A;          ///< merged (x,y,z,h) by merged id (real first, then ghosts): tree-build input
     DevBuf<Pack4> SB, SC, SD; ///< Morton-sorted records: (v,u), (P,omega,cs,alpha), (a,0); (x,y,z,h) is srch.SA
     DevBuf<Pack4> SE, SF;     ///< fast fp mode: per-particle derived factors (sph2_fast.cu)
+    DevBuf<double2> SG;       ///< fast fp mode, adiabatic EOS: (1/(rho² Ω), α c_s), the 16-byte neighbour record
     TreeBuffers tree;
     DevBuf<f64> rint;
     SearchBuffers srch;

@@ -33,6 +33,10 @@ enum { EOSK_ADIABATIC = 0, EOSK_ISOTHERMAL = 1, EOSK_LP07 = 2 };
 struct SphParams {
     f64 pmass;
     f64 alpha_u, alpha_AV, beta_AV;
+    /// fast force loop, adiabatic EOS: gamma - 1 and the 16-byte records (1/(rho² Ω), α c_s) of derive_fast; the
+    /// neighbour's rho and P are then recomputed from its h and u instead of being loaded (0 / null: not used)
+    f64 adiabatic_gm1   = 0;
+    const double2 *SG   = nullptr;
 };
 
 /// One Newton sweep (IterateSmoothingLengthDensity).  order: thread→object map (may be null),

@@ -51,7 +51,7 @@ void av_operators_fast(
 /// SE / SF: per-particle derived factors written by derive_fast (merged range, sorted order)
 void derive_fast(
     cudaStream_t s, int kernel, int av, u32 M, const Pack4 *SA, const Pack4 *SB, const Pack4 *SC, f64 pmass,
-    f64 alpha_AV, Pack4 *SE, Pack4 *SF);
+    f64 alpha_AV, Pack4 *SE, Pack4 *SF, double2 *SG = nullptr);
 void force_cfl_fast(
     cudaStream_t s, int kernel, int av, RankCsr c, const Pack4 *SA, const Pack4 *SB, const Pack4 *SE, const Pack4 *SF,
     const Pack4 *SC, SphParams p,

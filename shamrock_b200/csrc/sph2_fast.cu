@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(BLK) av_operators_fast_kernel(
 template<class K>
 __global__ void __launch_bounds__(256) derive_fast_kernel(
     u32 M, bool vary, f64 alpha_const, const Pack4 *__restrict__ SA, const Pack4 *__restrict__ SC, f64 pmass,
-    Pack4 *__restrict__ SE, Pack4 *__restrict__ SF) {
+    Pack4 *__restrict__ SE, Pack4 *__restrict__ SF, double2 *__restrict__ SG) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M)
         return;
@@ -400,10 +400,12 @@ __global__ void __launch_bounds__(256) derive_fast_kernel(
     f64 alpha = vary ? cc.d : alpha_const;
     SE[i] = Pack4{pa.a, pa.b, pa.c, hinv};
     SF[i] = Pack4{iro2, alpha * cc.c, cc.a, rho};
+    if (SG)
+        SG[i] = make_double2(iro2, alpha * cc.c);
 }
 
 // ---- forces + v_sig + CFL --------------------------------------------------------------------------------
-template<class K, int AV, int G>
+template<class K, int AV, int G, bool SF16 = false>
 __global__ void __launch_bounds__(BLK) force_cfl_fast_kernel(
     RankCsr c, const Pack4 *__restrict__ SA, const Pack4 *__restrict__ SB, const Pack4 *__restrict__ SE,
     const Pack4 *__restrict__ SF, const Pack4 *__restrict__ SC, SphParams p, const f64 *__restrict__ axyz_ext,
@@ -436,7 +438,17 @@ __global__ void __launch_bounds__(BLK) force_cfl_fast_kernel(
     while (j < s1) {
         const u32 jn  = j + G;
         const u32 rbn = jn < s1 ? c.list[jn] : rb;
-        const Pack4 pb = ld4(SE + rb), vb = ld4(SB + rb), fb = ld4(SF + rb);
+        const Pack4 pb = ld4(SE + rb), vb = ld4(SB + rb);
+        Pack4 fb;
+        if (SF16) { // 16 bytes instead of 32: rho_b from h_b, P_b = (gamma - 1) rho_b u_b
+            double2 g;
+            asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(g.x), "=d"(g.y) : "l"(p.SG + rb));
+            const f64 hfh = K::hfactd * pb.d;
+            const f64 rho = p.pmass * hfh * hfh * hfh;
+            fb            = Pack4{g.x, g.y, p.adiabatic_gm1 * rho * vb.d, rho};
+        } else {
+            fb = ld4(SF + rb);
+        }
         j  = jn;
         rb = rbn;
         f64 dx = pa.a - pb.a, dy = pa.b - pb.b, dz = pa.c - pb.c;
@@ -598,15 +610,15 @@ void av_operators_fast(
 
 void derive_fast(
     cudaStream_t s, int kernel, int av, u32 M, const Pack4 *SA, const Pack4 *SB, const Pack4 *SC, f64 pmass,
-    f64 alpha_AV, Pack4 *SE, Pack4 *SF) {
+    f64 alpha_AV, Pack4 *SE, Pack4 *SF, double2 *SG) {
     (void) SB;
     if (!M)
         return;
     bool vary = (av == AVK_MM97 || av == AVK_CD10);
     if (kernel == KERN_M4)
-        derive_fast_kernel<KM4><<<grid_for(M, 256), 256, 0, s>>>(M, vary, alpha_AV, SA, SC, pmass, SE, SF);
+        derive_fast_kernel<KM4><<<grid_for(M, 256), 256, 0, s>>>(M, vary, alpha_AV, SA, SC, pmass, SE, SF, SG);
     else
-        derive_fast_kernel<KM6><<<grid_for(M, 256), 256, 0, s>>>(M, vary, alpha_AV, SA, SC, pmass, SE, SF);
+        derive_fast_kernel<KM6><<<grid_for(M, 256), 256, 0, s>>>(M, vary, alpha_AV, SA, SC, pmass, SE, SF, SG);
     SB_COUNT_LAUNCH();
     SB_LAUNCH_CHECK();
 }
@@ -618,8 +630,14 @@ void force_cfl_fast(
     if (!c.N)
         return;
 #define FRC(AV_)                                                                                 \
-    SB_KDG(kernel, (force_cfl_fast_kernel<KT, AV_, G><<<grid_groups<G>(c.N), BLK, 0, s>>>(       \
-                       c, SA, SB, SE, SF, SC, p, axyz_ext, axyz, duint, C_cour, C_force, vsig, cfl_dt, red_min)))
+    do {                                                                                         \
+        if (p.SG && p.adiabatic_gm1 != 0)                                                        \
+            SB_KDG(kernel, (force_cfl_fast_kernel<KT, AV_, G, true><<<grid_groups<G>(c.N), BLK, 0, s>>>(  \
+                               c, SA, SB, SE, SF, SC, p, axyz_ext, axyz, duint, C_cour, C_force, vsig, cfl_dt, red_min))); \
+        else                                                                                     \
+            SB_KDG(kernel, (force_cfl_fast_kernel<KT, AV_, G><<<grid_groups<G>(c.N), BLK, 0, s>>>(   \
+                               c, SA, SB, SE, SF, SC, p, axyz_ext, axyz, duint, C_cour, C_force, vsig, cfl_dt, red_min))); \
+    } while (0)
     switch (av) {
     case AVK_CONSTANT:
     case AVK_MM97:

@@ -2,6 +2,8 @@
 #include "solver.cuh"
 #include "load_balance.hpp"
 #include <cstring>
+#include <mutex>
+#include <set>
 
 using namespace sb;
 
@@ -56,6 +58,42 @@ namespace sb {
 void set_last_error(const char *msg) { g_err = msg; }
 } // namespace sb
 
+// Live handles.  A binding with garbage collection finalises a model and its context in any order (and may
+// try to finalise a model whose context is already gone): destroying a context first destroys the models that
+// run on it, destroying a handle that is not live is a no-op, and using one is SHAMB200_ERR_INVALID.
+namespace {
+std::mutex g_handles_mu;
+std::set<shamb200_model *> g_live_models;
+std::set<shamb200_ctx *> g_live_ctxs;
+
+bool model_is_live(shamb200_model *m) {
+    std::lock_guard<std::mutex> lk(g_handles_mu);
+    return m && g_live_models.count(m);
+}
+void need_live(shamb200_model *m) {
+    if (!model_is_live(m))
+        throw std::invalid_argument("stale model handle (the model or its context has been destroyed)");
+}
+void need_live(shamb200_ctx *c) {
+    std::lock_guard<std::mutex> lk(g_handles_mu);
+    if (!c || !g_live_ctxs.count(c))
+        throw std::invalid_argument("stale context handle");
+}
+} // namespace
+namespace sb {
+void require_live(shamb200_ctx *c) { need_live(c); }
+} // namespace sb
+namespace {
+/// the model is live and owned by the caller (already taken out of the registry)
+void destroy_model_now(shamb200_model *m) {
+    cudaSetDevice(m->m.ctx->device);
+    cudaStreamSynchronize(m->m.ctx->stream);
+    comm_destroy(m->m);
+    delete m;
+    cudaGetLastError(); // a failure while tearing down must not surface in a later launch check
+}
+} // namespace
+
 extern "C" {
 
 const char *shamb200_last_error(void) { return g_err.c_str(); }
@@ -85,13 +123,31 @@ int shamb200_ctx_create(int device, void *cuda_stream, shamb200_ctx **out) {
             SB_CUDA_CHECK(cudaStreamCreateWithFlags(&c->c.stream, cudaStreamNonBlocking));
             c->c.own_stream = true;
         }
+        {
+            std::lock_guard<std::mutex> lk(g_handles_mu);
+            g_live_ctxs.insert(c);
+        }
         *out = c;
     });
 }
 int shamb200_ctx_destroy(shamb200_ctx *ctx) {
     return guard([&] {
-        if (!ctx)
-            return;
+        std::vector<shamb200_model *> mine;
+        {
+            std::lock_guard<std::mutex> lk(g_handles_mu);
+            if (!ctx || !g_live_ctxs.erase(ctx))
+                return; // not a live context (already destroyed)
+            for (auto it = g_live_models.begin(); it != g_live_models.end();) {
+                if ((*it)->m.ctx == &ctx->c) {
+                    mine.push_back(*it);
+                    it = g_live_models.erase(it);
+                } else {
+                    ++it;
+                }
+            }
+        }
+        for (auto *m : mine) // a model never outlives the stream it runs on
+            destroy_model_now(m);
         cudaSetDevice(ctx->c.device);
         cudaStreamSynchronize(ctx->c.stream);
         if (ctx->c.own_stream)
@@ -100,15 +156,22 @@ int shamb200_ctx_destroy(shamb200_ctx *ctx) {
         cudaGetLastError(); // a failure while tearing down must not surface in a later launch check
     });
 }
-void *shamb200_ctx_stream(shamb200_ctx *ctx) { return ctx ? (void *) ctx->c.stream : nullptr; }
+void *shamb200_ctx_stream(shamb200_ctx *ctx) {
+    std::lock_guard<std::mutex> lk(g_handles_mu);
+    return ctx && g_live_ctxs.count(ctx) ? (void *) ctx->c.stream : nullptr;
+}
 int shamb200_ctx_synchronize(shamb200_ctx *ctx) {
-    return guard([&] { SB_CUDA_CHECK(cudaStreamSynchronize(ctx->c.stream)); });
+    return guard([&] {
+        need_live(ctx);
+        SB_CUDA_CHECK(cudaStreamSynchronize(ctx->c.stream));
+    });
 }
 
 int shamb200_tree_build(
     shamb200_ctx *ctx, const double *d_xyz, size_t stride_dbl, uint32_t obj_cnt, const double bmin[3],
     const double bmax[3], uint32_t reduction_level, int sort_mode, shamb200_tree *out) {
     return guard([&] {
+        need_live(ctx);
         SB_CUDA_CHECK(cudaSetDevice(ctx->c.device));
         tree_build(ctx->c.stream, ctx->c.api_tree, d_xyz, stride_dbl, obj_cnt, bmin, bmax, false, reduction_level, sort_mode);
         fill_tree_view(ctx->c.api_tree, out);
@@ -118,6 +181,7 @@ int shamb200_tree_build_auto_bbox(
     shamb200_ctx *ctx, const double *d_xyz, size_t stride_dbl, uint32_t obj_cnt, uint32_t reduction_level,
     int sort_mode, shamb200_tree *out) {
     return guard([&] {
+        need_live(ctx);
         SB_CUDA_CHECK(cudaSetDevice(ctx->c.device));
         tree_build(ctx->c.stream, ctx->c.api_tree, d_xyz, stride_dbl, obj_cnt, nullptr, nullptr, true, reduction_level, sort_mode);
         fill_tree_view(ctx->c.api_tree, out);
@@ -126,6 +190,7 @@ int shamb200_tree_build_auto_bbox(
 int shamb200_tree_field_max(
     shamb200_ctx *ctx, const shamb200_tree *tree, const double *d_field, double scale, double *d_out) {
     return guard([&] {
+        need_live(ctx);
         if (tree->d_sort_index_map != ctx->c.api_tree.index_map.p)
             throw std::invalid_argument("the tree view is stale (not the last tree built by this context)");
         tree_field_max(ctx->c.stream, ctx->c.api_tree, d_field, scale, d_out, 1);
@@ -136,6 +201,7 @@ int shamb200_neigh_cache_build(
     shamb200_ctx *ctx, const shamb200_tree *tree, const double *d_xyz, size_t stride_dbl, const double *d_hpart,
     const double *d_rint, uint32_t obj_cnt, double Rkern, double h_tolerance, int two_stage, shamb200_csr *out) {
     return guard([&] {
+        need_live(ctx);
         if (tree->d_sort_index_map != ctx->c.api_tree.index_map.p)
             throw std::invalid_argument("the tree view is stale (not the last tree built by this context)");
         if (two_stage) { // the B200 search (neigh2.cu), exported in the reference's ObjectCache layout
@@ -174,6 +240,7 @@ int shamb200_h_iterate(
     const double *d_h_old, double *d_h_new, double *d_eps, double gpart_mass, double h_evol_max,
     double h_evol_iter_max) {
     return guard([&] {
+        need_live(ctx);
         ctx_reset_red(ctx->c);
         CsrView c{csr->d_cnt_neigh, csr->d_scanned_cnt, csr->d_index_neigh_map, csr->obj_cnt};
         h_iterate(ctx->c.stream, kernel, c, d_xyz, stride_dbl, nullptr, 0, d_h_old, d_h_new, d_eps, gpart_mass, h_evol_max, h_evol_iter_max, ctx->c.red.p);
@@ -184,6 +251,7 @@ int shamb200_h_iterate_loop(
     const double *d_h_old, double *d_h_new, double *d_eps, double gpart_mass, double h_evol_max,
     double h_evol_iter_max, double epsilon_h, uint32_t max_sweeps, double out3[3]) {
     return guard([&] {
+        need_live(ctx);
         CsrView c{csr->d_cnt_neigh, csr->d_scanned_cnt, csr->d_index_neigh_map, csr->obj_cnt};
         f64 mx = std::numeric_limits<f64>::max(), mn = -1;
         u32 it = 0;
@@ -206,6 +274,7 @@ int shamb200_compute_omega(
     shamb200_ctx *ctx, int kernel, const shamb200_csr *csr, const double *d_xyz, size_t stride_dbl,
     const double *d_hpart, double *d_omega, double gpart_mass) {
     return guard([&] {
+        need_live(ctx);
         CsrView c{csr->d_cnt_neigh, csr->d_scanned_cnt, csr->d_index_neigh_map, csr->obj_cnt};
         compute_omega(ctx->c.stream, kernel, c, d_xyz, stride_dbl, nullptr, 0, d_hpart, d_omega, gpart_mass);
     });
@@ -213,6 +282,7 @@ int shamb200_compute_omega(
 
 int shamb200_microbench(shamb200_ctx *ctx, int what, double *out) {
     return guard([&] {
+        need_live(ctx);
         SB_CUDA_CHECK(cudaSetDevice(ctx->c.device));
         *out = microbench(ctx->c, what);
     });
@@ -246,6 +316,7 @@ int shamb200_plan_load_balance(
 }
 int shamb200_model_set_patch_owners(shamb200_model *m, uint32_t npatch, const int32_t *owner) {
     return guard([&] {
+        need_live(m);
         Model &M = m->m;
         if (npatch != M.patches.size())
             throw std::invalid_argument("set_patch_owners: one owner per patch of the grid");
@@ -261,6 +332,7 @@ int shamb200_model_set_patch_owners(shamb200_model *m, uint32_t npatch, const in
 }
 int shamb200_model_patch_coords(shamb200_model *m, uint32_t npatch, uint64_t *coord_min) {
     return guard([&] {
+        need_live(m);
         Model &M = m->m;
         if (npatch != M.patches.size() || !coord_min)
             throw std::invalid_argument("patch_coords: one entry per patch of the grid");
@@ -334,54 +406,80 @@ void shamb200_solver_config_default(shamb200_solver_config *cfg) {
 
 int shamb200_model_create(shamb200_ctx *ctx, const shamb200_solver_config *cfg, shamb200_model **out) {
     return guard([&] {
-        if (!ctx)
-            throw std::invalid_argument("null context");
-        *out = new shamb200_model(&ctx->c, *cfg);
+        need_live(ctx);
+        auto *m = new shamb200_model(&ctx->c, *cfg);
+        {
+            std::lock_guard<std::mutex> lk(g_handles_mu);
+            g_live_models.insert(m);
+        }
+        *out = m;
     });
 }
 int shamb200_model_destroy(shamb200_model *m) {
     return guard([&] {
-        if (m) {
-            cudaSetDevice(m->m.ctx->device);
-            cudaStreamSynchronize(m->m.ctx->stream);
-            comm_destroy(m->m);
-            delete m;
-            cudaGetLastError(); // a failure while tearing down must not surface in a later launch check
+        {
+            std::lock_guard<std::mutex> lk(g_handles_mu);
+            if (!m || !g_live_models.erase(m))
+                return; // not a live model (already destroyed, possibly with its context)
         }
+        destroy_model_now(m);
     });
 }
 int shamb200_model_set_config(shamb200_model *m, const shamb200_solver_config *cfg) {
-    return guard([&] { m->m.cfg = *cfg; });
+    return guard([&] {
+        need_live(m);
+        m->m.cfg = *cfg;
+    });
 }
 int shamb200_model_set_box(shamb200_model *m, const double bmin[3], const double bmax[3], uint32_t nx, uint32_t ny, uint32_t nz) {
-    return guard([&] { m->m.set_box(bmin, bmax, nx, ny, nz); });
+    return guard([&] {
+        need_live(m);
+        m->m.set_box(bmin, bmax, nx, ny, nz);
+    });
 }
 int shamb200_model_push_particles(shamb200_model *m, uint64_t n, const double *xyz, const double *vxyz, const double *hpart, const double *uint_) {
-    return guard([&] { m->m.push_particles(n, xyz, vxyz, hpart, uint_); });
+    return guard([&] {
+        need_live(m);
+        m->m.push_particles(n, xyz, vxyz, hpart, uint_);
+    });
 }
-uint32_t shamb200_model_patch_count(shamb200_model *m) { return (uint32_t) m->m.patches.size(); }
+uint32_t shamb200_model_patch_count(shamb200_model *m) {
+    return model_is_live(m) ? (uint32_t) m->m.patches.size() : 0;
+}
 int shamb200_model_patch_is_local(shamb200_model *m, uint32_t ip) {
-    return ip < m->m.patches.size() && m->m.is_local(m->m.patches[ip]);
+    return model_is_live(m) && ip < m->m.patches.size() && m->m.is_local(m->m.patches[ip]);
 }
 uint32_t shamb200_model_patch_size(shamb200_model *m, uint32_t ip) {
-    if (ip >= m->m.patches.size() || !m->m.is_local(m->m.patches[ip]))
+    if (!model_is_live(m) || ip >= m->m.patches.size() || !m->m.is_local(m->m.patches[ip]))
         return 0;
     return m->m.patches[ip].f.n;
 }
 int64_t shamb200_model_get(shamb200_model *m, uint32_t ip, const char *name, void *out, int64_t cap_bytes) {
     int64_t r = -1;
-    int rc    = guard([&] { r = m->m.get(ip, name, out, cap_bytes); });
+    int rc    = guard([&] {
+        need_live(m);
+        r = m->m.get(ip, name, out, cap_bytes);
+    });
     return rc == SHAMB200_OK ? r : -2;
 }
 int shamb200_model_set_field(shamb200_model *m, uint32_t ip, const char *name, const double *in, uint64_t count) {
-    return guard([&] { m->m.set_field(ip, name, in, count); });
+    return guard([&] {
+        need_live(m);
+        m->m.set_field(ip, name, in, count);
+    });
 }
 int shamb200_model_evolve_once(shamb200_model *m) {
-    return guard([&] { m->m.evolve_once(); });
+    return guard([&] {
+        need_live(m);
+        m->m.evolve_once();
+    });
 }
 int shamb200_model_evolve_once_host(shamb200_model *m, uint32_t ip, const shamb200_host_patchdata *in,
                                     shamb200_host_patchdata *out) {
-    return guard([&] { m->m.evolve_once_host(ip, in, out); });
+    return guard([&] {
+        need_live(m);
+        m->m.evolve_once_host(ip, in, out);
+    });
 }
 int shamb200_host_register(void *p, uint64_t bytes) {
     return guard([&] { SB_CUDA_CHECK(cudaHostRegister(p, size_t(bytes), cudaHostRegisterDefault)); });
@@ -391,18 +489,21 @@ int shamb200_host_unregister(void *p) {
 }
 int shamb200_model_search_stats(shamb200_model *m, uint64_t out[2]) {
     return guard([&] {
+        need_live(m);
         out[0] = m->m.K_local;
         out[1] = m->m.pair_tests_local;
     });
 }
 int shamb200_model_host_traffic(shamb200_model *m, uint64_t out[2]) {
     return guard([&] {
+        need_live(m);
         out[0] = m->m.pipe.bytes_h2d;
         out[1] = m->m.pipe.bytes_d2h;
     });
 }
 int shamb200_model_state(shamb200_model *m, double out[12]) {
     return guard([&] {
+        need_live(m);
         Model &M = m->m;
         u64 nloc = 0;
         for (auto &p : M.patches)
@@ -423,22 +524,33 @@ int shamb200_model_state(shamb200_model *m, double out[12]) {
     });
 }
 int shamb200_model_set_next_dt(shamb200_model *m, double dt) {
-    return guard([&] { m->m.dt = dt; });
+    return guard([&] {
+        need_live(m);
+        m->m.dt = dt;
+    });
 }
 int shamb200_model_set_time(shamb200_model *m, double t) {
-    return guard([&] { m->m.time = t; });
+    return guard([&] {
+        need_live(m);
+        m->m.time = t;
+    });
 }
 int shamb200_model_reorder_particles(shamb200_model *m) {
     return guard([&] {
+        need_live(m);
         m->m.reorder_particles();
         SB_CUDA_CHECK(cudaStreamSynchronize(m->m.s()));
     });
 }
 int shamb200_model_set_cfl_multiplier(shamb200_model *m, double v) {
-    return guard([&] { m->m.cfl_multiplier = v; });
+    return guard([&] {
+        need_live(m);
+        m->m.cfl_multiplier = v;
+    });
 }
 int shamb200_model_stage_times(shamb200_model *m, const char **names, const double **ms, uint32_t *count) {
     return guard([&] {
+        need_live(m);
         *names = m->m.timer.names_joined.c_str();
         *ms    = m->m.timer.values.data();
         *count = (uint32_t) m->m.timer.values.size();

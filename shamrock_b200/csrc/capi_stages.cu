@@ -104,6 +104,7 @@ int shamb200_compute_eos(
     shamb200_ctx *ctx, int kernel, int eos, const shamb200_merged_fields *f, double gpart_mass, double gamma,
     double cs0, double eos_q, double eos_r0, double *d_pressure, double *d_soundspeed) {
     return guard([&] {
+        require_live(ctx);
         need(d_pressure, "d_pressure");
         need(d_soundspeed, "d_soundspeed");
         if (eos == SHAMB200_EOS_ADIABATIC)
@@ -120,6 +121,7 @@ int shamb200_update_divv_curlv(
     shamb200_ctx *ctx, int kernel, const shamb200_csr *csr, const shamb200_merged_fields *f, double gpart_mass,
     double *d_divv, double *d_curlv) {
     return guard([&] {
+        require_live(ctx);
         need(d_divv, "d_divv");
         need(f ? f->d_vxyz : nullptr, "vxyz");
         need(f->d_omega, "omega");
@@ -133,6 +135,7 @@ int shamb200_update_dtdivv(
     shamb200_ctx *ctx, int kernel, const shamb200_csr *csr, const shamb200_merged_fields *f, double gpart_mass,
     int also_divv_curlv, double *d_divv, double *d_curlv, double *d_dtdivv) {
     return guard([&] {
+        require_live(ctx);
         need(d_dtdivv, "d_dtdivv");
         need(f ? f->d_vxyz : nullptr, "vxyz");
         if (also_divv_curlv) {
@@ -152,6 +155,7 @@ int shamb200_update_viscosity(
     const double *d_divv, const double *d_curlv, const double *d_dtdivv, const double *d_soundspeed,
     const double *d_hpart, const double *d_alpha_AV, double *d_alpha_AV_updated) {
     return guard([&] {
+        require_live(ctx);
         const int k = av_kind(av);
         if (k != AVK_MM97 && k != AVK_CD10)
             throw std::invalid_argument("the viscosity switch exists for MM97 and CD10 only");
@@ -176,6 +180,7 @@ int shamb200_update_derivs(
     double gpart_mass, double alpha_u, double alpha_AV, double beta_AV, const double *d_axyz_ext, double *d_axyz,
     double *d_duint) {
     return guard([&] {
+        require_live(ctx);
         const int k = av_kind(av);
         need(d_axyz, "d_axyz");
         need(d_duint, "d_duint");
@@ -203,6 +208,7 @@ int shamb200_vsig_cfl(
     shamb200_ctx *ctx, int kernel, const shamb200_csr *csr, const shamb200_merged_fields *f, const double *d_axyz,
     double C_cour, double C_force, double *d_vsig, double *d_cfl_dt, double *dt_min) {
     return guard([&] {
+        require_live(ctx);
         need(d_axyz, "d_axyz");
         need(d_vsig, "d_vsig");
         need(d_cfl_dt, "d_cfl_dt");
@@ -228,6 +234,7 @@ int shamb200_leapfrog_predict(
     shamb200_ctx *ctx, uint32_t n, double dt, double *d_xyz, double *d_vxyz, const double *d_axyz, double *d_uint,
     const double *d_duint) {
     return guard([&] {
+        require_live(ctx);
         need(d_xyz, "d_xyz");
         need(d_vxyz, "d_vxyz");
         need(d_axyz, "d_axyz");
@@ -242,6 +249,7 @@ int shamb200_leapfrog_correct(
     shamb200_ctx *ctx, uint32_t n, double half_dt, double *d_vxyz, const double *d_axyz, const double *d_axyz_old,
     double *d_uint, const double *d_duint, const double *d_duint_old, double out2[2]) {
     return guard([&] {
+        require_live(ctx);
         need(d_vxyz, "d_vxyz");
         need(d_axyz, "d_axyz");
         need(d_axyz_old, "d_axyz_old");

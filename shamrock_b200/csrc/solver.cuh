@@ -185,6 +185,8 @@ void comm_destroy(Model &m);
 namespace sb {
 /// message returned by shamb200_last_error (thread local; capi.cu)
 void set_last_error(const char *msg);
+/// throws std::invalid_argument unless `c` is a live context handle (capi.cu)
+void require_live(struct ::shamb200_ctx *c);
 } // namespace sb
 
 struct shamb200_ctx {

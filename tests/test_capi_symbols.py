@@ -50,6 +50,33 @@ def test_default_config_matches_reference_defaults(lib):
     assert C.sizeof(_capi.SolverConfig) % 8 == 0 and cfg.constant_G == 1.0
 
 
+def test_default_config_reordering_fields(lib):
+    cfg = _capi.default_config()  # SolverConfig.hpp:621-630; the new fields sit at the end of the C struct
+    assert cfg.enable_particle_reordering == 0 and cfg.particle_reordering_step_freq == 1000
+    assert cfg.n_kill_spheres == 0 and cfg.kill_radius[3] == 0.0
+
+
+def test_stale_handles_are_refused_not_dereferenced(lib):
+    """handles that are not live (never created, or destroyed): destroy is a no-op, use is SHAMB200_ERR_INVALID"""
+    fake_m, fake_c = C.c_void_p(0x1000), C.c_void_p(0x2000)
+    assert lib.shamb200_model_destroy(fake_m) == 0
+    assert lib.shamb200_ctx_destroy(fake_c) == 0
+    assert lib.shamb200_model_patch_count(fake_m) == 0 and lib.shamb200_model_patch_size(fake_m, C.c_uint32(0)) == 0
+    assert lib.shamb200_model_evolve_once(fake_m) == -1
+    assert b"stale model handle" in lib.shamb200_last_error()
+    assert lib.shamb200_model_set_next_dt(fake_m, C.c_double(0.0)) == -1
+    assert lib.shamb200_model_reorder_particles(fake_m) == -1
+    assert lib.shamb200_ctx_synchronize(fake_c) == -1
+    assert b"stale context handle" in lib.shamb200_last_error()
+    assert lib.shamb200_ctx_stream(fake_c) is None
+    out = C.c_void_p()
+    assert lib.shamb200_model_create(fake_c, C.byref(_capi.default_config()), C.byref(out)) == -1
+    d = C.c_double()
+    assert lib.shamb200_microbench(fake_c, 0, C.byref(d)) == -1
+    z = (C.c_double * 3)()
+    assert lib.shamb200_leapfrog_predict(fake_c, C.c_uint32(0), C.c_double(0.1), z, z, z, z, z) == -1
+
+
 def test_no_cpu_fallback_without_gpu(lib):
     import torch
 

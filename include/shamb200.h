@@ -340,7 +340,9 @@ int shamb200_model_evolve_once(shamb200_model *m);
  * during the CD10 operators, divv curlv dtdivv alpha_AV during the force loop; only vxyz uint axyz duint
  * soundspeed follow the corrector.  Host memory should be page-locked (shamb200_host_register) for the
  * copies to be asynchronous.  One local patch per call (`ip`); a model with several local patches,
- * kill spheres, a point mass or free boundaries takes the same call without the overlap. */
+ * kill spheres, a point mass or free boundaries takes the same call without the overlap.
+ * With enable_particle_reordering the objects of a patch change places at the reordering steps: the fields that
+ * come back are in the new order, so a host that keeps its own copy reads back every field it keeps. */
 typedef struct shamb200_host_patchdata {
     uint64_t n;
     double *xyz, *vxyz, *axyz, *axyz_ext; /* 3 doubles per object */

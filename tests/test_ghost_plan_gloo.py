@@ -24,7 +24,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, grid, periodic, q):
+def _worker(rank, world, port, grid, periodic, q, balanced=False):
     try:
         os.environ["MASTER_ADDR"] = "127.0.0.1"
         os.environ["MASTER_PORT"] = str(port)
@@ -40,6 +40,17 @@ def _worker(rank, world, port, grid, periodic, q):
         npatch = len(boxes)
         assert sorted(set(owner.tolist())) == list(range(world))  # every rank owns patches
         assert (np.diff(owner) >= 0).all()  # contiguous deal of patch ids
+        if balanced:  # owners from the Hilbert-curve load balancer on the particle counts of the setup
+            G = 1 << 21
+            coords = np.array([(x * (G // grid[0]), y * (G // grid[1]), z * (G // grid[2]))
+                               for z in range(grid[2]) for y in range(grid[1]) for x in range(grid[0])], dtype=np.uint64)
+            loads = S.patch_loads(sc, world)
+            owner, _ = _capi.plan_load_balance(coords, loads, world)
+            t = torch.from_numpy(owner.astype(np.int64))
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)  # every rank computed the same table
+            assert np.array_equal(t.numpy(), owner)
+            per = np.bincount(owner, weights=loads.astype(np.float64), minlength=world)
+            assert per.min() > 0 and per.max() <= 0.75 * loads.sum()
         # local patch data = the particles of my patches, in push order (the oracle's pre-step order)
         xyz, h = sc["xyz"], sc["hpart"]
         if periodic:  # apply_position_boundary runs before the ghost exchange (integrators.cpp:207-236)
@@ -118,6 +129,22 @@ def test_ghost_exchange_plan_world2(grid, periodic):
     q = ctx.Queue()
     port = _free_port()
     ps = [ctx.Process(target=_worker, args=(r, 2, port, grid, periodic, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=240) for _ in ps]
+    for p in ps:
+        p.join(timeout=60)
+    for rank, msg in res:
+        assert msg == "ok", f"rank {rank}: {msg}"
+
+
+def test_ghost_exchange_with_balanced_owner_table_world2():
+    """patch -> rank from shamb200_plan_load_balance (not contiguous in patch id): the planned exchange still
+    reproduces the oracle's merged ghost zones"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, (4, 2, 2), False, q, True)) for r in range(2)]
     for p in ps:
         p.start()
     res = [q.get(timeout=240) for _ in ps]

@@ -297,9 +297,10 @@ int shamb200_model_set_box(shamb200_model *m, const double bmin[3], const double
                            uint32_t ny, uint32_t nz);
 /* patch -> rank table (one entry per patch of the grid, patch id order), e.g. from shamb200_plan_load_balance
  * on the particle counts of the setup; allowed while no particle has been pushed (patches do not migrate
- * between ranks afterwards).  Every rank passes the same table.  coord_min [npatch * 3] (may be NULL)
- * receives the patches' coordinates on the integer grid. */
+ * between ranks afterwards).  Every rank passes the same table. */
 int shamb200_model_set_patch_owners(shamb200_model *m, uint32_t npatch, const int32_t *owner);
+/* coord_min [npatch * 3]: the patches' lower corners on the 2^21 integer grid (Patch::coord_min,
+ * shamrock/include/shamrock/patch/Patch.hpp:63-72), the input of shamb200_plan_load_balance */
 int shamb200_model_patch_coords(shamb200_model *m, uint32_t npatch, uint64_t *coord_min);
 /* multi-GPU: rank/size of this process and the NCCL unique id (128 bytes, from
  * shamb200_nccl_unique_id on rank 0, broadcast by the caller).  Optional (single GPU otherwise). */

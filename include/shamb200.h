@@ -332,9 +332,10 @@ int shamb200_model_evolve_once(shamb200_model *m);
 /* Solver::evolve_once on HOST-resident patch data: the call a host code that keeps its PatchDataLayer
  * fields in its own memory makes once per step (the reference's fields live in sham::DeviceBuffer /
  * PatchDataField, shamrock/include/shamrock/patch/PatchDataField.hpp; main layout SolverConfig.cpp:24-121).
- * `in`: the step's inputs (xyz vxyz axyz hpart uint duint, alpha_AV for MM97/CD10); the other main-layout
- * fields are outputs of the step and are never read (NULL allowed everywhere in `in` = keep the device
- * copy).  `out`: every non-NULL pointer receives the field after the step; out->n is the capacity
+ * `in`: the step's inputs (xyz vxyz axyz hpart uint duint; alpha_AV and soundspeed for MM97/CD10 — the AV
+ * switch reads the previous step's soundspeed, UpdateViscosity.cpp:52-222); the other main-layout fields are
+ * outputs of the step and are never read (NULL allowed everywhere in `in` = keep the device copy; fields of a
+ * patch the library has just grown start at 0, like the reference's PatchDataField).  `out`: every non-NULL pointer receives the field after the step; out->n is the capacity
  * (objects) of the out arrays on entry and the object count of the patch on return.
  * Copies run on two copy streams and overlap with the kernels: the positions are drifted and the tree /
  * neighbour cache built while uint, duint, alpha_AV are still uploading; xyz, hpart, axyz_ext go back

@@ -73,11 +73,13 @@ bool model_is_live(shamb200_model *m) {
 void need_live(shamb200_model *m) {
     if (!model_is_live(m))
         throw std::invalid_argument("stale model handle (the model or its context has been destroyed)");
+    pool_set_stream(m->m.ctx->stream);
 }
 void need_live(shamb200_ctx *c) {
     std::lock_guard<std::mutex> lk(g_handles_mu);
     if (!c || !g_live_ctxs.count(c))
         throw std::invalid_argument("stale context handle");
+    pool_set_stream(c->c.stream);
 }
 } // namespace
 namespace sb {
@@ -87,6 +89,7 @@ namespace {
 /// the model is live and owned by the caller (already taken out of the registry)
 void destroy_model_now(shamb200_model *m) {
     cudaSetDevice(m->m.ctx->device);
+    pool_set_stream(m->m.ctx->stream);
     cudaStreamSynchronize(m->m.ctx->stream);
     comm_destroy(m->m);
     delete m;
@@ -149,10 +152,15 @@ int shamb200_ctx_destroy(shamb200_ctx *ctx) {
         for (auto *m : mine) // a model never outlives the stream it runs on
             destroy_model_now(m);
         cudaSetDevice(ctx->c.device);
-        cudaStreamSynchronize(ctx->c.stream);
-        if (ctx->c.own_stream)
-            cudaStreamDestroy(ctx->c.stream);
-        delete ctx;
+        cudaStream_t st = ctx->c.stream;
+        const bool own  = ctx->c.own_stream;
+        pool_set_stream(st);
+        cudaStreamSynchronize(st);
+        delete ctx; // its buffers go back to the pool while the stream still exists
+        cudaStreamSynchronize(st);
+        pool_set_stream(nullptr);
+        if (own)
+            cudaStreamDestroy(st);
         cudaGetLastError(); // a failure while tearing down must not surface in a later launch check
     });
 }
@@ -404,9 +412,33 @@ void shamb200_solver_config_default(shamb200_solver_config *cfg) {
     cfg->particle_reordering_step_freq = 1000;
 }
 
+/// one validation for create and set_config: enum fields in range, array bounds of the config respected
+static void validate_config(const shamb200_solver_config *cfg) {
+    if (!cfg)
+        throw std::invalid_argument("null solver config");
+    auto in = [](int v, int lo, int hi) { return v >= lo && v <= hi; };
+    if (!in(cfg->kernel, SHAMB200_KERNEL_M4, SHAMB200_KERNEL_M6))
+        throw std::invalid_argument("solver config: unknown kernel");
+    if (!in(cfg->eos, SHAMB200_EOS_ADIABATIC, SHAMB200_EOS_LOCALLY_ISOTHERMAL_LP07))
+        throw std::invalid_argument("solver config: unknown eos");
+    if (!in(cfg->av, SHAMB200_AV_NONE, SHAMB200_AV_CONSTANT_DISC))
+        throw std::invalid_argument("solver config: unknown artificial viscosity");
+    if (!in(cfg->bc, SHAMB200_BC_FREE, SHAMB200_BC_PERIODIC))
+        throw std::invalid_argument("solver config: unknown boundary condition");
+    if (!in(cfg->fp_mode, SHAMB200_FP_STRICT, SHAMB200_FP_FAST))
+        throw std::invalid_argument("solver config: unknown fp_mode");
+    if (!in(cfg->sort_mode, SHAMB200_SORT_BITONIC, SHAMB200_SORT_RADIX))
+        throw std::invalid_argument("solver config: unknown sort_mode");
+    if (cfg->n_kill_spheres < 0 || cfg->n_kill_spheres > 4)
+        throw std::invalid_argument("solver config: n_kill_spheres must be in [0, 4]");
+    if (cfg->enable_particle_reordering && cfg->particle_reordering_step_freq == 0)
+        throw std::invalid_argument("solver config: particle_reordering_step_freq must be > 0 when reordering is enabled");
+}
+
 int shamb200_model_create(shamb200_ctx *ctx, const shamb200_solver_config *cfg, shamb200_model **out) {
     return guard([&] {
         need_live(ctx);
+        validate_config(cfg);
         auto *m = new shamb200_model(&ctx->c, *cfg);
         {
             std::lock_guard<std::mutex> lk(g_handles_mu);
@@ -428,9 +460,29 @@ int shamb200_model_destroy(shamb200_model *m) {
 int shamb200_model_set_config(shamb200_model *m, const shamb200_solver_config *cfg) {
     return guard([&] {
         need_live(m);
+        validate_config(cfg);
         m->m.cfg = *cfg;
     });
 }
+int shamb200_nccl_unique_id(void *out128) {
+    int rc = guard([&] {
+        if (!out128)
+            throw std::invalid_argument("null unique-id buffer");
+        comm_unique_id(out128);
+    });
+    return rc == SHAMB200_ERR_RUNTIME ? SHAMB200_ERR_NCCL : rc;
+}
+int shamb200_model_init_comm(shamb200_model *m, int rank, int world_size, const void *nccl_id128) {
+    int rc = guard([&] {
+        need_live(m);
+        if (world_size > 1 && !nccl_id128)
+            throw std::invalid_argument("null NCCL unique id");
+        comm_init(m->m, rank, world_size, nccl_id128);
+    });
+    return rc == SHAMB200_ERR_RUNTIME ? SHAMB200_ERR_NCCL : rc;
+}
+/* kept for old bindings: the message is the one of shamb200_last_error */
+const char *shamb200_comm_last_error(void) { return g_err.c_str(); }
 int shamb200_model_set_box(shamb200_model *m, const double bmin[3], const double bmax[3], uint32_t nx, uint32_t ny, uint32_t nz) {
     return guard([&] {
         need_live(m);

@@ -43,9 +43,10 @@ inline unsigned grid_for(u64 n, unsigned block) { return (unsigned) ((n + block 
 
 /// Caching device allocator (runtime.cu): freed blocks are kept in size buckets and handed out again,
 /// so the per-step scratch of the solver never reaches cudaMalloc/cudaFree (which synchronise the
-/// device) after the first steps.  Safe without events because each context enqueues all of its
-/// work on ONE in-order stream.  Replaces sham::DeviceBuffer's USM allocations for this path
+/// device) after the first steps.  Blocks remember the stream they were freed on (runtime.cu) and a
+/// different stream waits for that point before it reuses them.  Replaces sham::DeviceBuffer's USM allocations for this path
 /// (shambackends/include/shambackends/DeviceBuffer.hpp).
+void pool_set_stream(cudaStream_t s); ///< stream the calling thread's allocations / frees are ordered on
 void *pool_alloc(size_t bytes);
 void pool_free(void *p);
 void pool_release_all();            ///< give every cached block back to the driver

@@ -1,5 +1,8 @@
 // runtime.cu — process-wide runtime pieces of libshamb200: the caching device allocator and the
-// kernel-launch counter.
+// kernel-launch counter.  The allocator is stream aware: every C-ABI entry point binds its context's
+// stream to the calling thread (pool_set_stream); a block freed on one stream and handed to another one
+// carries an event the new stream waits for, so two contexts / models on one device never share a block
+// that queued work of the other still uses.
 #include "common.cuh"
 #include <map>
 #include <mutex>
@@ -11,12 +14,21 @@ namespace sb {
 unsigned long long g_launch_count = 0;
 
 namespace {
+struct Block {
+    size_t size = 0;
+    int device  = 0;
+    cudaStream_t freed_on = nullptr; ///< stream whose queued work may still use the block
+    cudaEvent_t freed_ev  = nullptr; ///< recorded on freed_on by pool_free (created on first use)
+    bool has_ev           = false;
+};
 struct Pool {
     std::mutex mu;
-    std::multimap<size_t, void *> free_blocks;          // size -> block (per device key folded below)
-    std::unordered_map<void *, std::pair<size_t, int>> live; // ptr -> (size, device)
+    std::multimap<size_t, void *> free_blocks; // size -> block (per device key folded below)
+    std::unordered_map<void *, Block> live;    // ptr -> block
     size_t reserved = 0;
 };
+thread_local cudaStream_t t_stream = nullptr;
+thread_local bool t_stream_known   = false;
 Pool &pool() {
     static Pool p;
     return p;
@@ -33,6 +45,11 @@ size_t round_size(size_t b) {
 }
 } // namespace
 
+void pool_set_stream(cudaStream_t s) {
+    t_stream       = s;
+    t_stream_known = true;
+}
+
 void *pool_alloc(size_t bytes) {
     Pool &P   = pool();
     size_t sz = round_size(bytes);
@@ -42,9 +59,19 @@ void *pool_alloc(size_t bytes) {
         std::lock_guard<std::mutex> g(P.mu);
         auto range = P.free_blocks.equal_range(sz);
         for (auto it = range.first; it != range.second; ++it) {
-            void *p = it->second;
-            if (P.live[p].second == dev) {
+            void *p  = it->second;
+            Block &b = P.live[p];
+            if (b.device == dev) {
                 P.free_blocks.erase(it);
+                // stream-ordered reuse: work queued on the freeing stream may still touch the block; a
+                // different stream waits for the event recorded at the free
+                if (b.has_ev && !(t_stream_known && b.freed_on == t_stream)) {
+                    if (t_stream_known)
+                        cudaStreamWaitEvent(t_stream, b.freed_ev, 0);
+                    else
+                        cudaEventSynchronize(b.freed_ev);
+                }
+                b.has_ev = false;
                 return p;
             }
         }
@@ -59,7 +86,10 @@ void *pool_alloc(size_t bytes) {
     if (e != cudaSuccess)
         throw CudaError(std::string("cudaMalloc of ") + std::to_string(sz) + " bytes failed: " + cudaGetErrorString(e));
     std::lock_guard<std::mutex> g(P.mu);
-    P.live[p] = {sz, dev};
+    Block b;
+    b.size   = sz;
+    b.device = dev;
+    P.live[p] = b;
     P.reserved += sz;
     return p;
 }
@@ -74,7 +104,22 @@ void pool_free(void *p) {
         cudaFree(p);
         return;
     }
-    P.free_blocks.emplace(it->second.first, p);
+    Block &b = it->second;
+    if (t_stream_known) {
+        if (!b.freed_ev && cudaEventCreateWithFlags(&b.freed_ev, cudaEventDisableTiming) != cudaSuccess)
+            b.freed_ev = nullptr;
+        if (b.freed_ev && cudaEventRecord(b.freed_ev, t_stream) == cudaSuccess) {
+            b.freed_on = t_stream;
+            b.has_ev   = true;
+        } else {
+            cudaGetLastError();
+            cudaStreamSynchronize(t_stream);
+            b.has_ev = false;
+        }
+    } else {
+        b.has_ev = false; // no stream bound to this thread: the caller synchronised (legacy single-stream use)
+    }
+    P.free_blocks.emplace(b.size, p);
 }
 
 void pool_release_all() {
@@ -84,7 +129,9 @@ void pool_release_all() {
     for (auto &kv : P.free_blocks) {
         auto it = P.live.find(kv.second);
         if (it != P.live.end()) {
-            P.reserved -= it->second.first;
+            P.reserved -= it->second.size;
+            if (it->second.freed_ev)
+                cudaEventDestroy(it->second.freed_ev);
             P.live.erase(it);
         }
         cudaFree(kv.second);

@@ -26,8 +26,13 @@ std::vector<PatchFields::Ref> PatchFields::all() {
             {"dtdivv", &dtdivv, 1},   {"curlv", &curlv, 3}, {"soundspeed", &soundspeed, 1}};
 }
 void PatchFields::reserve(u32 cap, cudaStream_t s) {
-    for (auto &r : all())
+    for (auto &r : all()) {
+        const size_t old_cap = r.buf->cap;
         r.buf->ensure_keep(size_t(cap) * r.nvar, size_t(n) * r.nvar, s, 1.25);
+        if (r.buf->cap != old_cap) // a fresh block: fields start at 0 like the reference's PatchDataField
+            SB_CUDA_CHECK(cudaMemsetAsync(
+                r.buf->p + size_t(n) * r.nvar, 0, (r.buf->cap - size_t(n) * r.nvar) * sizeof(f64), s));
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -478,10 +483,17 @@ void Model::reattribute_patch_objects() {
         keep_flagged(p);
     }
     // 4. append at the destinations: (sender, receiver) ascending
-    for (auto &m : migs) {
-        PatchD &dst = patches[m.dst];
-        if (is_local(dst))
-            dst.f.reserve(dst.f.n + m.count, s());
+    // (a destination may receive from several senders: reserve once for the sum of the incoming counts)
+    std::vector<u64> incoming(np, 0);
+    for (auto &m : migs)
+        incoming[m.dst] += m.count;
+    for (size_t d = 0; d < np; d++) {
+        PatchD &dst = patches[d];
+        if (!is_local(dst) || !incoming[d])
+            continue;
+        if (u64(dst.f.n) + incoming[d] > 0xFFFFFFF0ull)
+            throw std::overflow_error("patch object count overflows u32 after the reattribution");
+        dst.f.reserve(u32(dst.f.n + incoming[d]), s());
     }
     comm_group_start(*this);
     for (auto &m : migs) {
@@ -1203,9 +1215,10 @@ void Model::evolve_once_host(u32 ip, const shamb200_host_patchdata *in, shamb200
         SB_CUDA_CHECK(cudaEventRecord(done, pipe.h2d));
     };
     static const char *const in1[] = {"xyz", "vxyz", "axyz", "hpart"}; // what the drift and the search read
-    static const char *const in2[] = {"uint", "duint", "alpha_AV"};
+    // soundspeed is an INPUT of the AV switch (UpdateViscosity.cpp:52-222 reads the previous step's value)
+    static const char *const in2[] = {"uint", "duint", "alpha_AV", "soundspeed"};
     upload(in1, 4, pipe.ev_in1);
-    upload(in2, has_alpha ? 3 : 2, pipe.ev_in2);
+    upload(in2, has_alpha ? 4 : 2, pipe.ev_in2);
     SB_CUDA_CHECK(cudaStreamWaitEvent(s(), pipe.ev_in1, 0));
     if (!pipe.defer_in2)
         SB_CUDA_CHECK(cudaStreamWaitEvent(s(), pipe.ev_in2, 0));

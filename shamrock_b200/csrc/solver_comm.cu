@@ -87,6 +87,16 @@ void comm_unique_id(void *out128) {
 void comm_init(Model &m, int rank, int world, const void *id128) {
     if (world < 1 || rank < 0 || rank >= world)
         throw std::invalid_argument("invalid rank / world size");
+    // set_box deals the patches to the ranks known at that time: a communicator that arrives later re-deals
+    // them (same contiguous id blocks as plan_patch_grid) — allowed only while no patch holds objects
+    if (!m.patches.empty() && (world != m.world || rank != m.rank)) {
+        for (auto &p : m.patches)
+            if (p.f.n)
+                throw std::invalid_argument("init_comm: the patches already hold objects (call it before push_particles)");
+        const size_t np = m.patches.size();
+        for (size_t k = 0; k < np; k++)
+            m.patches[k].owner = int((uint64_t(k) * uint64_t(world)) / np);
+    }
     m.rank  = rank;
     m.world = world;
     if (world == 1)
@@ -162,27 +172,3 @@ void comm_destroy(Model &m) {
 
 } // namespace sb
 
-namespace {
-thread_local std::string g_comm_err;
-}
-extern "C" {
-const char *shamb200_comm_last_error(void) { return g_comm_err.c_str(); }
-int shamb200_nccl_unique_id(void *out128) {
-    try {
-        sb::comm_unique_id(out128);
-        return SHAMB200_OK;
-    } catch (const std::exception &e) {
-        g_comm_err = e.what();
-        return SHAMB200_ERR_NCCL;
-    }
-}
-int shamb200_model_init_comm(shamb200_model *m, int rank, int world_size, const void *nccl_id128) {
-    try {
-        sb::comm_init(m->m, rank, world_size, nccl_id128);
-        return SHAMB200_OK;
-    } catch (const std::exception &e) {
-        g_comm_err = e.what();
-        return SHAMB200_ERR_NCCL;
-    }
-}
-}

@@ -215,6 +215,38 @@ def test_momentum_conservation_bench_size():
     assert np.isfinite(m.get(0, "duint")).all() and (m.get(0, "hpart") > 0).all()
 
 
+def empty_patch_scenario():
+    """(4, 1, 1) patches, patch 1 emptied, the layers next to it on both sides move in: an EMPTY patch receives
+    several hundred objects from TWO senders in one reattribution (ReattributeDataUtility.hpp:40-230)"""
+    sc = S.periodic_box(12000, "M4", "cd10", jitter=0.1, grid=(4, 1, 1))
+    x = sc["xyz"]
+    bmin, bmax = np.array(sc["bmin"]), np.array(sc["bmax"])
+    w = (bmax[0] - bmin[0]) / 4
+    lo1, hi1 = bmin[0] + w, bmin[0] + 2 * w
+    keep = ~((x[:, 0] >= lo1) & (x[:, 0] < hi1))
+    for k in ("xyz", "vxyz", "hpart", "uint"):
+        sc[k] = sc[k][keep]
+    x, v = sc["xyz"], sc["vxyz"].copy()
+    band = 2 * sc["dr"]
+    v[(x[:, 0] < lo1) & (x[:, 0] >= lo1 - band), 0] = +0.5
+    v[(x[:, 0] >= hi1) & (x[:, 0] < hi1 + band), 0] = -0.5
+    sc["vxyz"] = v
+    return sc
+
+
+def test_empty_patch_receives_from_two_senders():
+    sc = empty_patch_scenario()
+    o, m = S.make_oracle(sc), S.make_cuda(sc)
+    assert m.patch_size(1) == 0
+    o.evolve_once(), m.evolve_once()
+    dt = 1.2 * sc["dr"] / 0.5
+    o.set_next_dt(dt), m.set_next_dt(dt)
+    so, sm = o.evolve_once(), m.evolve_once()
+    assert o.patch_size(1) > 128 and [m.patch_size(i) for i in range(4)] == [o.patch_size(i) for i in range(4)]
+    assert so["corrector_iter"] == sm["corrector_iter"] and so["h_subcycles"] == sm["h_subcycles"]
+    compare(m, o, sc, 0.0)
+
+
 def test_errors_are_loud():
     sc = S.periodic_box(2000, "M4", "cd10")
     sc["cfg"]["gpart_mass"] = 0.0
@@ -243,7 +275,8 @@ def test_evolve_once_host_matches_device_resident(scenario):
     for nm in ALL_FIELDS:
         host[nm].numpy()[:] = m.get(0, nm).reshape(-1)
     has_alpha = sc["cfg"]["av"] in (2, 3)
-    in_names = ["xyz", "vxyz", "axyz", "hpart", "uint", "duint"] + (["alpha_AV"] if has_alpha else [])
+    # soundspeed is an input of the AV switch (previous step's value): it travels with alpha_AV
+    in_names = ["xyz", "vxyz", "axyz", "hpart", "uint", "duint"] + (["alpha_AV", "soundspeed"] if has_alpha else [])
     for step in range(3):
         ref.evolve_once()
         # poison the device copy of the inputs: the step must run on what the host passes in

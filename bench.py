@@ -161,12 +161,35 @@ def alg_work(stage, N, M, K, L, sweeps, tests=0):
     }.get(stage)
 
 
+def host_cores():
+    """cores this process may use (torchrun exports OMP_NUM_THREADS=1 to its workers: undo that for the CPU arm)"""
+    try:
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))
+    except Exception:
+        pass
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def oracle_all_cores():
+    """load the oracle with every host core: OMP_NUM_THREADS must be right BEFORE libgomp starts"""
+    n = host_cores()
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    os.environ.pop("OMP_THREAD_LIMIT", None)
+    from oracle import pyoracle as po
+
+    po.set_num_threads(n)
+    return po, n
+
+
 def run_reference(args):
     """CPU arm: the oracle port on all host cores, bounded sample of the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import pyoracle as po
+    po, ncores = oracle_all_cores()
     from tests import scenarios as S
 
     n_sample = args.cpu_sample
@@ -187,7 +210,7 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "C4 periodic HCP box, M4, CD10 AV, adiabatic, dt=0 replay (sph_homogeneous_benchmark "
                    "protocol)", "npart_sample": n},
-        "cpu_baseline": {"value": v, "unit": "particles/s", "cores": po.num_threads(), "kind": "port",
+        "cpu_baseline": {"value": v, "unit": "particles/s", "cores": ncores, "kind": "port",
                          "sample": f"{n} particles of the same box (oracle port of the reference algorithms, "
                                    f"OpenMP), {args.steps} dt=0 replays"},
         "e2e": {"value": v, "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -195,8 +218,26 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline(args):
-    from oracle import pyoracle as po
+def rel_err(a, b):
+    """max over particles of |a - b| / max(|b|, mean|b|): the north-star tolerance (1e-10) is on this number"""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    if a.shape != b.shape:
+        return float("inf")
+    if a.size == 0:
+        return 0.0
+    scale = np.maximum(np.abs(b), np.abs(b).mean())
+    return float((np.abs(a - b) / np.where(scale > 0, scale, 1.0)).max())
+
+
+CHECK_FIELDS = ["xyz", "vxyz", "hpart", "uint", "axyz", "duint", "alpha_AV", "divv", "dtdivv", "curlv", "soundspeed"]
+INT_NAMES = ["tree.sorted_morton", "tree.sort_index_map", "tree.reduc_index_map", "tree.reduced_morton",
+             "tree.lchild_id", "tree.rchild_id", "tree.endrange", "cache.cnt_neigh", "cache.index_neigh_map"]
+
+
+def cpu_baseline(args, ctx):
+    """the oracle timed on a bounded sample of the workload, all host cores — and, on the same sample, the
+    CUDA model checked against the state the oracle ends in (not only timed)"""
+    po, ncores = oracle_all_cores()
     from tests import scenarios as S
 
     sc = workload(args.cpu_sample, 1)
@@ -207,11 +248,91 @@ def cpu_baseline(args):
     k = 2
     for _ in range(k):
         o.set_next_dt(0.0)
-        o.evolve_once()
+        so = o.evolve_once()
     dt = time.perf_counter() - t0
-    return {"value": n * k / dt, "unit": "particles/s", "cores": po.num_threads(), "kind": "port",
+    m = S.make_cuda(sc, ctx=ctx, keep_step_data=False, fp_mode=args.fp)
+    m.evolve_once()
+    for _ in range(k):
+        m.set_next_dt(0.0)
+        sm = m.evolve_once()
+    errs = {nm: rel_err(m.get(0, nm), o.get(0, nm)) for nm in CHECK_FIELDS}
+    errs["dt"] = abs(sm["dt"] - so["dt"]) / abs(so["dt"])
+    cnt_equal = bool(np.array_equal(m.get(0, "cache.cnt_neigh"), o.get(0, "cache.cnt_neigh")))
+    m.close()
+    return {"value": n * k / dt, "unit": "particles/s", "cores": ncores, "kind": "port",
             "sample": f"{n} particles of the same periodic box, 1 warm-up + {k} dt=0 replays, oracle (C++/OpenMP port "
-                      "of the reference algorithms; the SYCL reference cannot be built here)"}
+                      "of the reference algorithms, -O3 -march=native; the SYCL reference cannot be built here)",
+            "parity_on_sample": {"n": n, "steps": 1 + k, "max_rel_err": max(errs.values()),
+                                 "worst_field": max(errs, key=errs.get), "neighbour_counts_equal": cnt_equal}}
+
+
+def parity_check(args, rank, world, local, ctx, dist, torch, _capi):
+    """Outside the timed region, for every N: a ~2e5-particle C4 box sharded over the N ranks like the bench
+    workload, two steps, compared with the single-process oracle on rank 0.  Twice: in the configuration the
+    bench times (fast fp, radix sort: every main-layout field and dt, relative error per particle) and in the
+    bit-exact configuration (strict fp, the reference's bitonic tie order: Morton codes, permutation, tree,
+    neighbour lists and every field identical)."""
+    from tests import scenarios as S
+
+    n_target = args.parity_npart
+    out = {"n": None, "world": world, "steps": 2}
+
+    def run(fp_mode, sort_mode):
+        sc = S.periodic_box(n_target, "M4", "cd10", jitter=0.1, grid=(world, 1, 1), stretch=(world, 1, 1),
+                            sort_mode=sort_mode)
+        ids = [_capi.nccl_unique_id() if rank == 0 else None]
+        if world > 1:
+            dist.broadcast_object_list(ids, src=0)
+        m = S.make_cuda(sc, ctx=ctx, keep_step_data=True, rank=rank, world=world, nccl_id=ids[0], fp_mode=fp_mode)
+        for _ in range(2):
+            sm = m.evolve_once()
+        names = CHECK_FIELDS + (INT_NAMES if fp_mode == "strict" else [])
+        mine = {ip: {nm: m.get(ip, nm) for nm in names} for ip in range(m.patch_count)
+                if m.patch_is_local(ip) and m.patch_size(ip)}
+        m.close()
+        parts = [None] * world
+        if world > 1:
+            dist.all_gather_object(parts, mine)
+        else:
+            parts = [mine]
+        if rank != 0:
+            return None
+        got = {}
+        for d in parts:
+            got.update(d)
+        oracle_all_cores()
+        o = S.make_oracle(sc)
+        for _ in range(2):
+            so = o.evolve_once()
+        worst, worst_nm, ints_ok, bits_ok = 0.0, "", True, True
+        for ip in range(o.patch_count):
+            if o.patch_size(ip) == 0:
+                continue
+            for nm in names:
+                a, b = got[ip][nm], o.get(ip, nm)
+                if nm in INT_NAMES:
+                    ints_ok = ints_ok and a.shape == b.shape and bool(np.array_equal(a, b))
+                    continue
+                e = rel_err(a, b)
+                bits_ok = bits_ok and bool(np.array_equal(a, b))
+                if e > worst:
+                    worst, worst_nm = e, f"{nm}@patch{ip}"
+        e_dt = abs(sm["dt"] - so["dt"]) / abs(so["dt"])
+        if e_dt > worst:
+            worst, worst_nm = e_dt, "dt"
+        return {"n": len(sc["xyz"]), "max_rel_err": worst, "worst": worst_nm, "ints_exact": ints_ok,
+                "fields_bit_identical": bits_ok, "h_subcycles": sm["h_subcycles"] == so["h_subcycles"]}
+
+    fast = run(args.fp, "radix")
+    strict = run("strict", "bitonic")
+    if rank != 0:
+        return None
+    out.update(n=fast["n"], max_rel_err=fast["max_rel_err"], worst=fast["worst"],
+               ints_exact=strict["ints_exact"], strict_fields_bit_identical=strict["fields_bit_identical"],
+               strict_max_rel_err=strict["max_rel_err"],
+               config={"bench_mode": f"fp {args.fp}, radix sort", "exact_mode": "fp strict, bitonic sort (reference tie order)",
+                       "tolerance": "1e-10 relative per particle, |d| <= tol * max(|x|, mean|x|), no floors"})
+    return out
 
 
 def main():
@@ -220,7 +341,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--npart-per-gpu", type=int, default=16 * 2**20)
-    ap.add_argument("--cpu-sample", type=int, default=400000)
+    ap.add_argument("--cpu-sample", type=int, default=4 * 2**20,
+                    help="particles of the CPU arm's sample box (BASELINE.md §3: a subset box, scaled linearly)")
+    ap.add_argument("--parity-npart", type=int, default=200000)
+    ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--fp", default="fast", choices=["fast", "strict"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -403,13 +527,19 @@ def main():
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
             if abs(tj["npart"] - n_local) <= 0.01 * n_local:
-                if top in tj["stages"]:
+                def fresh(k):  # a capture of other code (kernel time off by > 5 %) is not evidence for this run
+                    v = tj["stages"][k]
+                    return k in table and abs(v["ncu_time_ms"] - table[k]["ms"]) <= 0.05 * table[k]["ms"]
+
+                if top in tj["stages"] and fresh(top):
                     traffic = tj["stages"][top]["traffic"]
                     traffic_src = "profiles/traffic_17M.json (" + tj["stages"][top]["kernel"] + ")"
                 for k, v in tj["stages"].items():
-                    if k in table:
-                        table[k]["ncu"] = {q: v[q] for q in ("fp64_pipe_pct", "l1_lsu_data_pipe_pct", "issue_active_pct")
-                                           if q in v}
+                    if k in table and fresh(k):
+                        table[k]["ncu"] = {q: v[q] for q in ("fp64_pipe_pct", "l1_lsu_data_pipe_pct", "issue_active_pct",
+                                                             "ncu_time_ms") if q in v}
+                    elif k in table:
+                        table[k]["ncu"] = {"stale": f"capture {v['ncu_time_ms']:.2f} ms vs {table[k]['ms']:.2f} ms live"}
         roofline = {"bound": tt["bound"], "kernel": top,
                     "achieved": tt["TFLOP/s"] if tt["bound"] == "fp64" else tt["GB/s"],
                     "peak": fp64_peak if tt["bound"] == "fp64" else hbm_peak,
@@ -449,12 +579,19 @@ def main():
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "h_subcycles": st["h_subcycles"], "corrector_iter": st["corrector_iter"],
         }
+    m.close()
+    pc = None
+    if not args.no_parity_check:
+        if rank == 0 and cpus_before:
+            os.sched_setaffinity(0, cpus_before)  # the oracle uses every host core again
+        pc = parity_check(args, rank, world, local, ctx, dist, torch, _capi)
+    if rank == 0:
+        line["parity_check"] = pc
         if not args.no_cpu_baseline and world == 1:
             if cpus_before:
-                os.sched_setaffinity(0, cpus_before)  # the CPU baseline uses every host core again
-            line["cpu_baseline"] = cpu_baseline(args)
+                os.sched_setaffinity(0, cpus_before)
+            line["cpu_baseline"] = cpu_baseline(args, ctx)
         print(json.dumps(line), flush=True)
-    m.close()
     if world > 1:
         dist.destroy_process_group()
 

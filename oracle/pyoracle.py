@@ -13,14 +13,39 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "_build", "liboracle.so")
 
 
+_STAMP = os.path.join(_HERE, "_build", "cpu.stamp")
+
+
+def _cpu_id():
+    """model + ISA flags of this host: the library is built with -march=native"""
+    try:
+        model, flags = "", ""
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name") and not model:
+                model = line.split(":", 1)[1].strip()
+            if line.startswith("flags") and not flags:
+                flags = " ".join(sorted(line.split(":", 1)[1].split()))
+            if model and flags:
+                break
+        import hashlib
+
+        return model + " " + hashlib.sha1(flags.encode()).hexdigest()
+    except OSError:
+        return "unknown"
+
+
 def build(force=False):
-    """Compile the oracle (g++, OpenMP) if needed."""
-    srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "shamrock_oracle.hpp", "sph_step.hpp")]
-    if (not force) and os.path.exists(_LIB) and all(
+    """Compile the oracle (g++, OpenMP) if needed: sources newer than the library, or a library that was built
+    on another CPU (-march=native; the in-tree .so travels to the GPU box)."""
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "shamrock_oracle.hpp", "sph_step.hpp", "Makefile")]
+    same_cpu = os.path.exists(_STAMP) and open(_STAMP).read() == _cpu_id()
+    if (not force) and same_cpu and os.path.exists(_LIB) and all(
         os.path.getmtime(_LIB) >= os.path.getmtime(s) for s in srcs
     ):
         return _LIB
-    subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s"])
+    subprocess.check_call(["make", "-C", _HERE, "-B", "-s"])
+    with open(_STAMP, "w") as f:
+        f.write(_cpu_id())
     return _LIB
 
 

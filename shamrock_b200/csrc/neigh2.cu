@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, 32) group_walk_kernel(
                             if (len >= (1u << 24))
                                 atomicOr(flags + 2, 1u);
                             emit = 1;
-                            o0   = make_uint2(n.left, (mask << 24) | (len & 0xffffffu));
+                            o0   = make_uint2(e.x, (mask << 24) | (len & 0xffffffu)); // node id: see euclid_cull_kernel
                         } else {
                             emit    = 2;
                             o0      = make_uint2(n.left, mask << 24);
@@ -472,6 +472,60 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, 32) group_walk_kernel(
     if (lane == 0) {
         gc_off[g] = ebase;
         gcount[g] = ncur;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage 1b: Euclidean cull of the candidate leaves
+// ---------------------------------------------------------------------------------------------
+/// The reference's leaf test compares boxes axis by axis: a candidate leaf b passes for leaf A when its box
+/// reaches into A's box grown by R on every axis — a CUBE around A.  A pair (a in A, b' in b) is only accepted
+/// when r <= R_a or r <= R_b', and r is at least the Euclidean distance of the two boxes, so a candidate farther
+/// than max(R_A, R_b) from A (the corners of the cube: a quarter of the candidates on a lattice) cannot
+/// contribute to the lists of A.  One warp per group clears those member bits (1e-9 safety margin on the
+/// rounding of the distance: the cull is conservative, the lists are unchanged) and replaces the node id the
+/// walk left in the entry by the leaf's first rank.  Lanes = entries: the work is two node loads and
+/// eight box distances per entry, fully parallel — the same test inside the walk costs 4 ms, here 1.
+__global__ void __launch_bounds__(128) euclid_cull_kernel(
+    const NodePack *__restrict__ nodes, u32 I, u32 L, f64 Rkern, uint2 *__restrict__ gcand,
+    const u64 *__restrict__ gc_off, const u32 *__restrict__ gcount, const u32 *__restrict__ group_ids, u32 ngroups) {
+    __shared__ f64 mb[4][GL][8]; // per warp: the members' boxes (lo, hi) and interaction radius
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const u32 gi   = blockIdx.x * 4 + warp;
+    if (gi >= ngroups)
+        return;
+    const u32 g  = group_ids ? group_ids[gi] : gi;
+    const u32 gn = gcount[g];
+    if (gn == 0)
+        return;
+    if (lane < GL) {
+        const u32 leaf = g * GL + lane;
+        f64 *m         = mb[warp][lane];
+        if (leaf < L) {
+            NodeRegs a = load_node(nodes + I + leaf);
+            m[0] = a.lo0, m[1] = a.lo1, m[2] = a.lo2, m[3] = a.hi0, m[4] = a.hi1, m[5] = a.hi2, m[6] = a.rint * Rkern;
+        } else {
+            m[0] = m[1] = m[2] = m[3] = m[4] = m[5] = m[6] = 0;
+        }
+    }
+    __syncwarp();
+    uint2 *gc = gcand + gc_off[g];
+    for (u32 k = lane; k < gn; k += 32) {
+        uint2 e    = gc[k];
+        NodeRegs n = load_node(nodes + e.x);
+        const f64 r = n.rint * Rkern;
+        u32 mask    = e.y >> 24;
+#pragma unroll
+        for (int i = 0; i < GL; i++) {
+            const f64 *m = mb[warp][i];
+            f64 g0 = fmax(fmax(m[0] - n.hi0, n.lo0 - m[3]), 0.);
+            f64 g1 = fmax(fmax(m[1] - n.hi1, n.lo1 - m[4]), 0.);
+            f64 g2 = fmax(fmax(m[2] - n.hi2, n.lo2 - m[5]), 0.);
+            f64 Rm = fmax(m[6], r);
+            if (g0 * g0 + g1 * g1 + g2 * g2 > Rm * Rm * (1. + 1e-9))
+                mask &= ~(1u << i);
+        }
+        gc[k] = make_uint2(n.left, (mask << 24) | (e.y & 0xffffffu));
     }
 }
 
@@ -826,6 +880,9 @@ void search_build(
             sb.nodes.p, I, L, sb.real_prefix.p, Rkern, sb.frontier_cap, sb.top_front.p, sb.top_count.p, ecap, d_ecursor,
             sb.gcand.p, sb.gc_off.p, sb.gcount.p, d_flags, sb.over_list.p, OVER_CAP, nullptr);
         SB_COUNT_LAUNCH();
+        euclid_cull_kernel<<<grid_for(G, 4), 128, 0, s>>>(
+            sb.nodes.p, I, L, Rkern, sb.gcand.p, sb.gc_off.p, sb.gcount.p, nullptr, G);
+        SB_COUNT_LAUNCH();
         if (mark)
             mark("neigh_lists");
         lists_kernel<<<G, S2_WARPS * 32, s2_bytes, s>>>(
@@ -851,6 +908,9 @@ void search_build(
                 group_walk_kernel<true><<<nb, WALK_WARPS * 32, sizeof(LeafBox) * (GL + 1), s>>>(
                     sb.nodes.p, I, L, sb.real_prefix.p, Rkern, L, sb.top_front.p, sb.top_count.p, ecap, d_ecursor,
                     sb.gcand.p, sb.gc_off.p, sb.gcount.p, d_flags, sb.over_list.p + b0, OVER_CAP, sb.big_scratch.p);
+                SB_COUNT_LAUNCH();
+                euclid_cull_kernel<<<grid_for(nb, 4), 128, 0, s>>>(
+                    sb.nodes.p, I, L, Rkern, sb.gcand.p, sb.gc_off.p, sb.gcount.p, sb.over_list.p + b0, nb);
                 SB_COUNT_LAUNCH();
                 lists_kernel<<<nb, S2_WARPS * 32, s2_bytes, s>>>(
                     sb.nodes.p, I, L, sb.SA.p, sb.real_flag.p, sb.real_prefix.p, sb.gcand.p, sb.gc_off.p, sb.gcount.p,

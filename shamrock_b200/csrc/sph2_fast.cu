@@ -257,15 +257,20 @@ __global__ void __launch_bounds__(BLK) av_operators_fast_kernel(
     const f64 hinv  = 1. / h_a;
     const f64 dWn_a = K::norm_3d * (hinv * hinv) * (hinv * hinv);
     const f64 lim_a = h_a * h_a * Rker2;
+    // MAT: Rij = -Σ r ⊗ ∇W is symmetric (∇W ∥ r): six sums; Rv = -Σ ∇W ⊗ v holds every product v_m ∂_i W, so
+    // the SPH divergence and curl (Σ v·∇W, Σ v × ∇W) are read off it instead of being summed a second time
+    constexpr bool OWN_DIV = SPHDIV && !MAT;
     f64 snv = 0, cx = 0, cy = 0, cz = 0;
-    f64 Rij[9], Rv[9], Ra[9];
+    f64 S[6], Rv[9], Ra[9]; // S: xx xy xz yy yz zz
     if (MAT) {
 #pragma unroll
         for (int i = 0; i < 9; i++) {
-            Rij[i] = 0;
-            Rv[i]  = 0;
-            Ra[i]  = 0;
+            Rv[i] = 0;
+            Ra[i] = 0;
         }
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+            S[i] = 0;
     }
     const u32 s0 = c.off[kk], s1 = s0 + c.cnt[kk];
     u32 j  = s0 + sub;
@@ -287,7 +292,7 @@ __global__ void __launch_bounds__(BLK) av_operators_fast_kernel(
         f64 gs   = dWn_a * FastK<K>::df(q) * rinv; // ∇W_ab(h_a) = gs · r_ab  (mass factored out)
         f64 gx = gs * dx, gy = gs * dy, gz = gs * dz;
         f64 vx = va.a - vb.a, vy = va.b - vb.b, vz = va.c - vb.c;
-        if (SPHDIV) {
+        if (OWN_DIV) {
             snv += vx * gx + vy * gy + vz * gz;
             if (CURL) {
                 cx += vy * gz - vz * gy;
@@ -296,21 +301,22 @@ __global__ void __launch_bounds__(BLK) av_operators_fast_kernel(
             }
         }
         if (MAT) {
-            f64 v[3]  = {vx, vy, vz};
-            f64 a[3]  = {aa.a - ab.a, aa.b - ab.b, aa.c - ab.c};
-            f64 rr[3] = {dx, dy, dz};
-            f64 g[3]  = {gx, gy, gz};
+            f64 v[3] = {vx, vy, vz};
+            f64 a[3] = {aa.a - ab.a, aa.b - ab.b, aa.c - ab.c};
+            f64 g[3] = {gx, gy, gz};
+            S[0] -= dx * gx, S[1] -= dx * gy, S[2] -= dx * gz;
+            S[3] -= dy * gy, S[4] -= dy * gz, S[5] -= dz * gz;
 #pragma unroll
             for (int i = 0; i < 3; i++)
 #pragma unroll
                 for (int m = 0; m < 3; m++) {
-                    Rij[3 * i + m] -= rr[i] * g[m];
                     Rv[3 * i + m] -= v[m] * g[i];
                     Ra[3 * i + m] -= a[m] * g[i];
                 }
         }
     }
-    if (SPHDIV) {
+    f64 Rij[9];
+    if (OWN_DIV) {
         snv = group_sum<G>(snv);
         if (CURL) {
             cx = group_sum<G>(cx);
@@ -321,9 +327,19 @@ __global__ void __launch_bounds__(BLK) av_operators_fast_kernel(
     if (MAT) {
 #pragma unroll
         for (int i = 0; i < 9; i++) {
-            Rij[i] = group_sum<G>(Rij[i]);
-            Rv[i]  = group_sum<G>(Rv[i]);
-            Ra[i]  = group_sum<G>(Ra[i]);
+            Rv[i] = group_sum<G>(Rv[i]);
+            Ra[i] = group_sum<G>(Ra[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+            S[i] = group_sum<G>(S[i]);
+        Rij[0] = S[0], Rij[1] = S[1], Rij[2] = S[2], Rij[3] = S[1], Rij[4] = S[3], Rij[5] = S[4], Rij[6] = S[2],
+        Rij[7] = S[4], Rij[8] = S[5];
+        if (SPHDIV) { // Rv[3 i + m] = -Σ v_m ∂_i W
+            snv = -(Rv[0] + Rv[4] + Rv[8]);
+            cx  = Rv[5] - Rv[7];
+            cy  = Rv[6] - Rv[2];
+            cz  = Rv[1] - Rv[3];
         }
     }
     if (!valid || sub != 0)

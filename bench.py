@@ -146,16 +146,19 @@ def workload(npart_per_gpu, n_gpus, kernel="M4", rank=0, count_reduce=None):
 # M merged, N real, K = sum of list lengths, K_acc ~ K / htol^3 pairs inside the kernel support, L leaves.
 # Flop convention: FMA = 2, div / sqrt = 1; candidate test 10, density pair 39, div+curl+dtdivv 175,
 # force + v_sig 155 per accepted pair.
-def alg_work(stage, N, M, K, L, sweeps, tests=0):
+def alg_work(stage, N, M, K, L, sweeps, tests=0, omega_in_av=True):
+    """omega_in_av: fast fp + CD10 / MM97 — the Ω sum (one density-type pass, 39 flop per pair) is evaluated inside
+    the CD10 operator pass instead of after the h iteration"""
     K_acc = K / 1.1**3
+    h_passes = sweeps + (0 if omega_in_av else 1)
     return {
         # the search = one tree walk per group of 8 leaves + the accept / fill kernel; SURVEY.md §8d's figure
         # for the whole cache (64 M + 4 K + 12 N) split over the two launches: packed nodes (64 B, I + L = 2 L)
         # and candidate entries for the walk; sorted records (32 B), list and count / offset writes for the lists
         "neigh_walk": (64 * 2 * L + 8 * 12 * L, 30.0 * 2 * L),
         "neigh_lists": (32 * M + 4 * K + 8 * N, 10.0 * (tests or K)),  # one accept test per (particle, candidate)
-        "h_iteration": (4 * K + 32 * M + 40 * N, (sweeps + 1) * (10.0 * K + 39.0 * K_acc)),
-        "divv_curlv_dtdivv": (4 * K + 96 * M + 40 * N, 10.0 * K + 175.0 * K_acc),
+        "h_iteration": (h_passes * 4 * K + 32 * M + 40 * N, h_passes * (10.0 * K + 39.0 * K_acc)),
+        "divv_curlv_dtdivv": (4 * K + 96 * M + 40 * N, 10.0 * K + (175.0 + (39.0 if omega_in_av else 0.0)) * K_acc),
         "forces": (4 * K + 128 * M + 64 * N, 10.0 * K + 155.0 * K_acc),
         "build_trees": (176 * M + 90 * L, 0.0),
     }.get(stage)
@@ -513,7 +516,7 @@ def main():
             table[k] = {"ms": round(ms_k, 3), "bound": bound, "frac": max(t_hbm, t_fp) / (ms_k * 1e-3),
                         "GB/s": w[0] / (ms_k * 1e-3) / 1e9, "TFLOP/s": w[1] / (ms_k * 1e-3) / 1e12}
         # records gathered per launch by the three neighbour loops (one 32-byte record per list entry and array)
-        for k, nrec in (("h_iteration", (sweeps + 1) * K), ("divv_curlv_dtdivv", 3 * K), ("forces", 3 * K)):
+        for k, nrec in (("h_iteration", sweeps * K), ("divv_curlv_dtdivv", 3 * K), ("forces", 3 * K)):
             if k in table:
                 rate = nrec / (table[k]["ms"] * 1e-3) / 1e9
                 table[k]["gather"] = {"records": nrec, "Grec/s": rate, "frac_of_l1_random_gather": rate / gather_random}

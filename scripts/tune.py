@@ -58,6 +58,14 @@ def main():
 
     measure("default")
     for spec in args.vars:
+        if "+" in spec:  # a combination: A=1+B=2 sets both, one measurement
+            pairs = [kv.split("=") for kv in spec.split("+")]
+            for k, v in pairs:
+                os.environ[k] = v
+            measure(spec)
+            for k, _ in pairs:
+                del os.environ[k]
+            continue
         name, vals = spec.split("=")
         for v in vals.split(","):
             os.environ[name] = v

@@ -169,8 +169,20 @@ __device__ __forceinline__ f64 warp_max8(f64 v) {
     return __shfl_sync(0xffffffffu, v, 0);
 }
 
-constexpr u32 SUPER   = 64;  ///< groups per super-group (512 leaves) sharing the top of their walks
-constexpr u32 TOP_CAP = 128; ///< start-frontier entries per super-group
+constexpr u32 TOP_CAP_MAX = 512; ///< start-frontier entries per super-group: storage
+/// groups per super-group sharing the top of their walks, and the frontier length the top walk hands over
+/// (it stops once half of it is reached).  SHAMB200_SUPER / SHAMB200_TOPCAP override the defaults (tuning).
+struct TopCfg {
+    u32 super, cap;
+};
+static TopCfg top_cfg() {
+    TopCfg t{64u, 128u}; // read at every search: scripts/tune.py switches them inside one process
+    if (const char *e = getenv("SHAMB200_SUPER"))
+        t.super = std::max(1, atoi(e));
+    if (const char *e = getenv("SHAMB200_TOPCAP"))
+        t.cap = std::min<u32>(TOP_CAP_MAX, std::max(4, atoi(e)));
+    return t;
+}
 
 __device__ __forceinline__ f64 warp_min32(f64 v) {
 #pragma unroll
@@ -191,9 +203,9 @@ __device__ __forceinline__ f64 warp_max32(f64 v) {
 /// frontier holds 64 nodes, and leaves that frontier (node ids, left to right, untested) as the starting
 /// point of the 64 group walks.
 __global__ void __launch_bounds__(32) top_walk_kernel(
-    const NodePack *__restrict__ nodes, u32 I, u32 L, const u32 *__restrict__ real_prefix, f64 Rkern,
-    u32 *__restrict__ top_front, u32 *__restrict__ top_count) {
-    __shared__ u32 fa[TOP_CAP], fb[TOP_CAP];
+    const NodePack *__restrict__ nodes, u32 I, u32 L, const u32 *__restrict__ real_prefix, f64 Rkern, u32 SUPER,
+    u32 TOP_CAP, u32 *__restrict__ top_front, u32 *__restrict__ top_count) {
+    __shared__ u32 fa[TOP_CAP_MAX], fb[TOP_CAP_MAX];
     const int lane = threadIdx.x;
     const u32 lt   = (1u << lane) - 1u;
     const u32 sg   = blockIdx.x;
@@ -290,8 +302,8 @@ __global__ void __launch_bounds__(32) top_walk_kernel(
 /// around a particle with a very large h (the reference searches those too, slowly).
 template<bool BIG>
 __global__ void __launch_bounds__(WALK_WARPS * 32, 32) group_walk_kernel(
-    const NodePack *__restrict__ nodes, u32 I, u32 L, const u32 *__restrict__ real_prefix, f64 Rkern, u32 F,
-    const u32 *__restrict__ top_front, const u32 *__restrict__ top_count, u64 ecap,
+    const NodePack *__restrict__ nodes, u32 I, u32 L, const u32 *__restrict__ real_prefix, f64 Rkern, u32 F, u32 SUPER,
+    u32 TOP_CAP, const u32 *__restrict__ top_front, const u32 *__restrict__ top_count, u64 ecap,
     unsigned long long *__restrict__ ecursor, uint2 *__restrict__ gcand, u64 *__restrict__ gc_off,
     u32 *__restrict__ gcount, u32 *__restrict__ flags, u32 *__restrict__ over_list, u32 over_cap,
     uint2 *__restrict__ big_scratch) {
@@ -871,13 +883,14 @@ void search_build(
         SB_CUDA_CHECK(cudaMemsetAsync(sb.scalars.p + 2, 0, 5 * sizeof(u64), s));
         if (mark)
             mark("neigh_walk");
+        const u32 SUPER = top_cfg().super, TOP_CAP = top_cfg().cap;
         const u32 S = (G + SUPER - 1) / SUPER;
         sb.top_front.ensure(size_t(S) * TOP_CAP, 1.1);
         sb.top_count.ensure(S, 1.1);
-        top_walk_kernel<<<S, 32, 0, s>>>(sb.nodes.p, I, L, sb.real_prefix.p, Rkern, sb.top_front.p, sb.top_count.p);
+        top_walk_kernel<<<S, 32, 0, s>>>(sb.nodes.p, I, L, sb.real_prefix.p, Rkern, SUPER, TOP_CAP, sb.top_front.p, sb.top_count.p);
         SB_COUNT_LAUNCH();
         group_walk_kernel<false><<<grid_for(G, WALK_WARPS), WALK_WARPS * 32, per_warp * WALK_WARPS, s>>>(
-            sb.nodes.p, I, L, sb.real_prefix.p, Rkern, sb.frontier_cap, sb.top_front.p, sb.top_count.p, ecap, d_ecursor,
+            sb.nodes.p, I, L, sb.real_prefix.p, Rkern, sb.frontier_cap, SUPER, TOP_CAP, sb.top_front.p, sb.top_count.p, ecap, d_ecursor,
             sb.gcand.p, sb.gc_off.p, sb.gcount.p, d_flags, sb.over_list.p, OVER_CAP, nullptr);
         SB_COUNT_LAUNCH();
         euclid_cull_kernel<<<grid_for(G, 4), 128, 0, s>>>(
@@ -906,7 +919,7 @@ void search_build(
             for (u32 b0 = 0; b0 < n_over; b0 += batch) {
                 const u32 nb = std::min(batch, n_over - b0);
                 group_walk_kernel<true><<<nb, WALK_WARPS * 32, sizeof(LeafBox) * (GL + 1), s>>>(
-                    sb.nodes.p, I, L, sb.real_prefix.p, Rkern, L, sb.top_front.p, sb.top_count.p, ecap, d_ecursor,
+                    sb.nodes.p, I, L, sb.real_prefix.p, Rkern, L, top_cfg().super, top_cfg().cap, sb.top_front.p, sb.top_count.p, ecap, d_ecursor,
                     sb.gcand.p, sb.gc_off.p, sb.gcount.p, d_flags, sb.over_list.p + b0, OVER_CAP, sb.big_scratch.p);
                 SB_COUNT_LAUNCH();
                 euclid_cull_kernel<<<grid_for(nb, 4), 128, 0, s>>>(

@@ -752,6 +752,7 @@ void Model::sph_prestep() {
         // result as the reference's synchronous sweeps.  (epsilon_h != 1e-6 keeps the host loop.)  Ω is
         // evaluated in the same launch with the converged h (ComputeOmega.cpp:36-73).
         const bool fused = cfg.epsilon_h == 1e-6;
+        const bool omega_later = omega_in_av_pass(); // fast fp + MM97 / CD10: Ω comes out of av_operators
         if (fused) {
             reset_red();
             for (auto &p : patches)
@@ -761,7 +762,7 @@ void Model::sph_prestep() {
                     h_solve(
                         s(), cfg.fp_mode, cfg.kernel, rank_csr_of(st.srch, st.tree), st.srch.SA.p, st.h_old.p,
                         p.f.hpart.p, st.eps.p, st.omega.p, cfg.gpart_mass, cfg.htol_up_coarse_cycle,
-                        cfg.htol_up_fine_cycle, cfg.h_iter_per_subcycles, true, true, red.p);
+                        cfg.htol_up_fine_cycle, cfg.h_iter_per_subcycles, true, !omega_later, red.p);
                 }
             read_red(3);
             local_max_eps = ordered_to_f64(h_red.p[0]);
@@ -798,7 +799,7 @@ void Model::sph_prestep() {
         break;
     }
     h_subcycles = hstep_cnt + 1;
-    if (cfg.epsilon_h != 1e-6) {
+    if (cfg.epsilon_h != 1e-6 && !omega_in_av_pass()) {
         timer.mark(s(), "omega");
         for (auto &p : patches)
             if (is_local(p) && p.f.n) {
@@ -875,31 +876,38 @@ void Model::communicate_merge_ghosts_fields() {
     }
 }
 
-/// alpha_AV ghost exchange (Solver.cpp:2325-2368)
-void Model::exchange_alpha_ghosts() {
+/// alpha_AV ghost exchange (Solver.cpp:2325-2368).  with_omega (fast fp mode): Ω of every merged object is
+/// produced by the operator pass that precedes this exchange (av_operators) and rides along — 16 B per ghost.
+void Model::exchange_alpha_ghosts(bool with_omega) {
     for (auto &p : patches)
         if (is_local(p) && p.f.n)
-            pack_alpha(s(), p.st.n, nullptr, p.st.alpha_updated.p, p.st.SC.p, p.st.srch.inv_map.p);
-    // C3: 8 B per ghost; remote interfaces go through compact f64 staging on both sides
+            pack_alpha(s(), p.st.n, nullptr, p.st.alpha_updated.p, p.st.SC.p, p.st.srch.inv_map.p,
+                       with_omega ? p.st.omega.p : nullptr);
+    // C3: 8 (16) B per ghost; remote interfaces go through compact f64 staging on both sides
     size_t recv_total = 0;
     for (auto &itf : ifaces)
         if (is_local(patches[itf.receiver]) && !is_local(patches[itf.sender]))
             recv_total += itf.count;
-    send_stage_f.ensure(send_total, 1.1);
-    recv_stage_f.ensure(recv_total, 1.1);
+    const size_t nv = with_omega ? 2 : 1; // staging: [alpha of the interface | omega of the interface]
+    send_stage_f.ensure(send_total * nv, 1.1);
+    recv_stage_f.ensure(recv_total * nv, 1.1);
     size_t roff = 0;
     comm_group_start(*this);
     for (auto &itf : ifaces) {
         PatchD &R = patches[itf.receiver];
         PatchD &S = patches[itf.sender];
         if (is_local(R) && is_local(S)) {
-            pack_alpha(s(), itf.count, itf.ids, S.st.alpha_updated.p, R.st.SC.p, R.st.srch.inv_map.p + R.st.n + itf.dst_off);
+            pack_alpha(s(), itf.count, itf.ids, S.st.alpha_updated.p, R.st.SC.p, R.st.srch.inv_map.p + R.st.n + itf.dst_off,
+                       with_omega ? S.st.omega.p : nullptr);
         } else if (is_local(S)) {
-            gather_field(s(), itf.count, 1, itf.ids, S.st.alpha_updated.p, send_stage_f.p + itf.stage_off);
-            comm_send(*this, send_stage_f.p + itf.stage_off, size_t(itf.count) * sizeof(f64), R.owner);
+            f64 *stg = send_stage_f.p + itf.stage_off * nv;
+            gather_field(s(), itf.count, 1, itf.ids, S.st.alpha_updated.p, stg);
+            if (with_omega)
+                gather_field(s(), itf.count, 1, itf.ids, S.st.omega.p, stg + itf.count);
+            comm_send(*this, stg, size_t(itf.count) * nv * sizeof(f64), R.owner);
         } else if (is_local(R)) {
-            comm_recv(*this, recv_stage_f.p + roff, size_t(itf.count) * sizeof(f64), S.owner);
-            roff += itf.count;
+            comm_recv(*this, recv_stage_f.p + roff, size_t(itf.count) * nv * sizeof(f64), S.owner);
+            roff += size_t(itf.count) * nv;
         }
     }
     comm_group_end(*this);
@@ -907,8 +915,10 @@ void Model::exchange_alpha_ghosts() {
     for (auto &itf : ifaces) {
         PatchD &R = patches[itf.receiver];
         if (is_local(R) && !is_local(patches[itf.sender])) {
-            pack_alpha(s(), itf.count, nullptr, recv_stage_f.p + roff, R.st.SC.p, R.st.srch.inv_map.p + R.st.n + itf.dst_off);
-            roff += itf.count;
+            const f64 *stg = recv_stage_f.p + roff;
+            pack_alpha(s(), itf.count, nullptr, stg, R.st.SC.p, R.st.srch.inv_map.p + R.st.n + itf.dst_off,
+                       with_omega ? stg + itf.count : nullptr);
+            roff += size_t(itf.count) * nv;
         }
     }
 }
@@ -993,10 +1003,11 @@ void Model::evolve_once() {
                 if (!is_local(p) || !p.f.n)
                     continue;
                 PatchStep &st = p.st;
+                st.omega.ensure(st.n);
                 av_operators(
                     s(), cfg.fp_mode, cfg.kernel, rank_csr_of(st.srch, st.tree), st.srch.SA.p, st.SB.p, st.SC.p, st.SD.p,
                     cfg.gpart_mass, has_curl, has_dtdivv, cfg.combined_dtdiv_divcurlv_compute != 0, p.f.divv.p,
-                    p.f.curlv.p, p.f.dtdivv.p);
+                    p.f.curlv.p, p.f.dtdivv.p, omega_in_av_pass() ? st.omega.p : nullptr);
             }
         timer.mark(s(), "av_eos");
         if (has_alpha) {
@@ -1005,7 +1016,7 @@ void Model::evolve_once() {
                     update_av(
                         s(), cfg.av, p.st.n, dt_, cfg.sigma_decay, cfg.alpha_min, cfg.alpha_max, p.f.divv.p,
                         p.f.curlv.p, p.f.dtdivv.p, p.f.soundspeed.p, p.f.hpart.p, p.f.alpha_AV.p, p.st.alpha_updated.p);
-            exchange_alpha_ghosts();
+            exchange_alpha_ghosts(omega_in_av_pass());
         }
         for (auto &p : patches)
             if (is_local(p) && p.f.n)

@@ -159,7 +159,12 @@ struct Model {
     void start_neighbors_cache();
     void sph_prestep();
     void communicate_merge_ghosts_fields();
-    void exchange_alpha_ghosts();
+    void exchange_alpha_ghosts(bool with_omega);
+    /// fast fp mode with a varying-alpha switch: the Ω sum rides in the CD10 / MM97 operator pass instead of
+    /// costing a pass of its own after the h iteration (sph2_fast.cu: av_operators_fast_kernel<..., OMEGA>)
+    bool omega_in_av_pass() const {
+        return cfg.fp_mode == SHAMB200_FP_FAST && (cfg.av == SHAMB200_AV_MM97 || cfg.av == SHAMB200_AV_CD10);
+    }
     void reset_red();
     void read_red(int n);
 };

@@ -15,9 +15,11 @@ void h_solve(
 
 void av_operators(
     cudaStream_t s, int fp_mode, int kernel, RankCsr c, const Pack4 *SA, const Pack4 *SB, const Pack4 *SC,
-    const Pack4 *SD, f64 pmass, bool want_curl, bool want_dtdivv, bool combined, f64 *divv, f64 *curlv, f64 *dtdivv) {
+    const Pack4 *SD, f64 pmass, bool want_curl, bool want_dtdivv, bool combined, f64 *divv, f64 *curlv, f64 *dtdivv,
+    f64 *omega_out) {
     if (fp_mode == FP_FAST)
-        av_operators_fast(s, kernel, c, SA, SB, SC, SD, pmass, want_curl, want_dtdivv, combined, divv, curlv, dtdivv);
+        av_operators_fast(s, kernel, c, SA, SB, SC, SD, pmass, want_curl, want_dtdivv, combined, divv, curlv, dtdivv,
+                          omega_out);
     else
         av_operators_strict(s, kernel, c, SA, SB, SC, SD, pmass, want_curl, want_dtdivv, combined, divv, curlv, dtdivv);
 }

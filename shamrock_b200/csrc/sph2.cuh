@@ -23,9 +23,12 @@ void h_solve(
     f64 *omega, f64 pmass, f64 h_evol_max, f64 h_evol_iter_max, u32 max_sweeps, bool do_iter, bool do_omega,
     u64 *red);
 
+/// omega_out (fast fp mode only): the pass also sums Ω of every real particle (ComputeOmega.cpp:36-73) with the
+/// converged h and uses it for its own 1 / (ρ Ω) factor — h_solve is then run without its Ω pass
 void av_operators(
     cudaStream_t s, int fp_mode, int kernel, RankCsr c, const Pack4 *SA, const Pack4 *SB, const Pack4 *SC,
-    const Pack4 *SD, f64 pmass, bool want_curl, bool want_dtdivv, bool combined, f64 *divv, f64 *curlv, f64 *dtdivv);
+    const Pack4 *SD, f64 pmass, bool want_curl, bool want_dtdivv, bool combined, f64 *divv, f64 *curlv, f64 *dtdivv,
+    f64 *omega_out = nullptr);
 
 void force_cfl(
     cudaStream_t s, int fp_mode, int kernel, int av, RankCsr c, const Pack4 *SA, const Pack4 *SB, const Pack4 *SC,
@@ -47,7 +50,8 @@ void h_solve_fast(
     f64 pmass, f64 h_evol_max, f64 h_evol_iter_max, u32 max_sweeps, bool do_iter, bool do_omega, u64 *red);
 void av_operators_fast(
     cudaStream_t s, int kernel, RankCsr c, const Pack4 *SA, const Pack4 *SB, const Pack4 *SC, const Pack4 *SD,
-    f64 pmass, bool want_curl, bool want_dtdivv, bool combined, f64 *divv, f64 *curlv, f64 *dtdivv);
+    f64 pmass, bool want_curl, bool want_dtdivv, bool combined, f64 *divv, f64 *curlv, f64 *dtdivv,
+    f64 *omega_out = nullptr);
 /// SE / SF: per-particle derived factors written by derive_fast (merged range, sorted order)
 void derive_fast(
     cudaStream_t s, int kernel, int av, u32 M, const Pack4 *SA, const Pack4 *SB, const Pack4 *SC, f64 pmass,

@@ -75,6 +75,12 @@ struct FastK<KM4> {
         f64 u1 = t1 + fabs(t1), u2 = t2 + fabs(t2); // 2 x+
         return fma(-0.1875, u1 * u1, 0.75 * (u2 * u2));
     }
+    /// f for q <= 2
+    __device__ static __forceinline__ f64 f_in(f64 q) {
+        f64 t1 = 2. - q, t2 = 1. - q;
+        f64 u2 = t2 + fabs(t2);
+        return fma(-0.125, (u2 * u2) * u2, 0.25 * ((t1 * t1) * t1));
+    }
     /// f and df for q <= 2 (the caller's support test guarantees it up to rounding)
     __device__ static __forceinline__ void f_df(f64 q, f64 &f, f64 &df) {
         f64 t1 = 2. - q, t2 = 1. - q;
@@ -92,6 +98,12 @@ struct FastK<KM6> {
         f64 s1 = u1 * u1, s2 = u2 * u2, s3 = u3 * u3;
         // -5 (x1^4 - 6 x2^4 + 15 x3^4) with x = u / 2
         return -0.3125 * fma(15., s3 * s3, fma(-6., s2 * s2, s1 * s1));
+    }
+    /// f for q <= 3
+    __device__ static __forceinline__ f64 f_in(f64 q) {
+        f64 f, df;
+        f_df(q, f, df);
+        return f;
     }
     __device__ static __forceinline__ void f_df(f64 q, f64 &f, f64 &df) {
         f64 t1 = 3. - q, t2 = 2. - q, t3 = 1. - q;
@@ -238,11 +250,13 @@ __global__ void __launch_bounds__(BLK) h_solve_fast_kernel(
 }
 
 // ---- ∇·v, ∇×v, d(∇·v)/dt ------------------------------------------------------------------------------
-template<class K, int G, bool SPHDIV, bool CURL, bool MAT, bool COMBINED>
+/// OMEGA: the pass also accumulates Σ (3 f + q f') over the support of h_a (the Ω sum of h_solve, self pair
+/// included) and writes Ω_a: one pass over the lists less per step
+template<class K, int G, bool SPHDIV, bool CURL, bool MAT, bool COMBINED, bool OMEGA>
 __global__ void __launch_bounds__(BLK) av_operators_fast_kernel(
     RankCsr c, const Pack4 *__restrict__ SA, const Pack4 *__restrict__ SB, const Pack4 *__restrict__ SC,
     const Pack4 *__restrict__ SD, f64 pmass, f64 *__restrict__ divv, f64 *__restrict__ curlv,
-    f64 *__restrict__ dtdivv) {
+    f64 *__restrict__ dtdivv, f64 *__restrict__ omega_out) {
     const u32 t      = blockIdx.x * blockDim.x + threadIdx.x;
     const u32 k      = t / G;
     const int sub    = int(t % G);
@@ -260,7 +274,7 @@ __global__ void __launch_bounds__(BLK) av_operators_fast_kernel(
     // MAT: Rij = -Σ r ⊗ ∇W is symmetric (∇W ∥ r): six sums; Rv = -Σ ∇W ⊗ v holds every product v_m ∂_i W, so
     // the SPH divergence and curl (Σ v·∇W, Σ v × ∇W) are read off it instead of being summed a second time
     constexpr bool OWN_DIV = SPHDIV && !MAT;
-    f64 snv = 0, cx = 0, cy = 0, cz = 0;
+    f64 snv = 0, cx = 0, cy = 0, cz = 0, sg = 0;
     f64 S[6], Rv[9], Ra[9]; // S: xx xy xz yy yz zz
     if (MAT) {
 #pragma unroll
@@ -285,11 +299,17 @@ __global__ void __launch_bounds__(BLK) av_operators_fast_kernel(
         f64 dx = pa.a - pb.a, dy = pa.b - pb.b, dz = pa.c - pb.c;
         f64 r2  = dx * dx + dy * dy + dz * dz;
         f64 h_b = pb.d;
-        if ((r2 > lim_a && r2 > h_b * h_b * Rker2) || r2 < 1e-18) // r < 1e-9: zero unit vector in the reference
+        if (r2 > lim_a && r2 > h_b * h_b * Rker2)
             continue;
-        f64 rinv = fast_rsqrt(r2);
-        f64 q    = (r2 * rinv) * hinv;
-        f64 gs   = dWn_a * FastK<K>::df(q) * rinv; // ∇W_ab(h_a) = gs · r_ab  (mass factored out)
+        f64 x    = OMEGA ? r2 + 1e-280 : r2; // the particle itself (r2 = 0) counts in the Ω sum
+        f64 rinv = fast_rsqrt(x);
+        f64 q    = (x * rinv) * hinv;
+        f64 dfq  = FastK<K>::df(q);
+        if (OMEGA && r2 <= lim_a)
+            sg += fma(q, dfq, 3. * FastK<K>::f_in(q));
+        if (r2 < 1e-18) // r < 1e-9: zero unit vector in the reference
+            continue;
+        f64 gs   = dWn_a * dfq * rinv; // ∇W_ab(h_a) = gs · r_ab  (mass factored out)
         f64 gx = gs * dx, gy = gs * dy, gz = gs * dz;
         f64 vx = va.a - vb.a, vy = va.b - vb.b, vz = va.c - vb.c;
         if (OWN_DIV) {
@@ -342,10 +362,17 @@ __global__ void __launch_bounds__(BLK) av_operators_fast_kernel(
             cz  = Rv[1] - Rv[3];
         }
     }
+    f64 omega_new = 0;
+    if (OMEGA) { // Ω = 1 + h/(3 ρ_h) Σ m ∂W/∂h = 1 - (norm / (3 hfact³)) Σ (3 f + q f')   (h_solve_fast_kernel)
+        constexpr f64 hf3 = K::hfactd * K::hfactd * K::hfactd;
+        omega_new         = 1 - (K::norm_3d / (3 * hf3)) * group_sum<G>(sg);
+    }
     if (!valid || sub != 0)
         return;
+    if (OMEGA)
+        omega_out[id] = omega_new;
     if (SPHDIV) {
-        f64 omega_a = SC[r].b;
+        f64 omega_a = OMEGA ? omega_new : SC[r].b;
         f64 hfh     = K::hfactd * hinv;
         f64 rho_a   = pmass * hfh * hfh * hfh;
         f64 fac     = -pmass / (omega_a * rho_a);
@@ -602,12 +629,19 @@ void h_solve_fast(
 
 void av_operators_fast(
     cudaStream_t s, int kernel, RankCsr c, const Pack4 *SA, const Pack4 *SB, const Pack4 *SC, const Pack4 *SD,
-    f64 pmass, bool want_curl, bool want_dtdivv, bool combined, f64 *divv, f64 *curlv, f64 *dtdivv) {
+    f64 pmass, bool want_curl, bool want_dtdivv, bool combined, f64 *divv, f64 *curlv, f64 *dtdivv, f64 *omega_out) {
     if (!c.N)
         return;
+#define AVOP2(S_, C_, M_, CB_, OM_)                                                              \
+    SB_KDG(kernel, (av_operators_fast_kernel<KT, G, S_, C_, M_, CB_, OM_><<<grid_groups<G>(c.N), BLK, 0, s>>>( \
+                       c, SA, SB, SC, SD, pmass, divv, curlv, dtdivv, omega_out)))
 #define AVOP(S_, C_, M_, CB_)                                                                    \
-    SB_KDG(kernel, (av_operators_fast_kernel<KT, G, S_, C_, M_, CB_><<<grid_groups<G>(c.N), BLK, 0, s>>>(   \
-                       c, SA, SB, SC, SD, pmass, divv, curlv, dtdivv)))
+    do {                                                                                         \
+        if (omega_out)                                                                           \
+            AVOP2(S_, C_, M_, CB_, true);                                                        \
+        else                                                                                     \
+            AVOP2(S_, C_, M_, CB_, false);                                                       \
+    } while (0)
     if (want_dtdivv) {
         if (combined)
             AVOP(false, false, true, true);
@@ -622,6 +656,7 @@ void av_operators_fast(
             AVOP(true, false, false, false);
     }
 #undef AVOP
+#undef AVOP2
 }
 
 void derive_fast(

@@ -493,19 +493,25 @@ void unpack_ghost_fields(
     SB_COUNT_LAUNCH();
     SB_LAUNCH_CHECK();
 }
-/// C[k].d = alpha[ids ? ids[k] : k]
+/// C[k].d = alpha[ids ? ids[k] : k]; with omega (fast fp mode: Ω comes out of the CD10 / MM97 operator pass
+/// and travels with alpha) also C[k].b = omega[...]
 __global__ void __launch_bounds__(256) pack_alpha_kernel(
     u32 cnt, const u32 *__restrict__ ids, const u32 *__restrict__ dst_map, const f64 *__restrict__ alpha,
-    Pack4 *__restrict__ C) {
+    const f64 *__restrict__ omega, Pack4 *__restrict__ C) {
     u32 k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= cnt)
         return;
-    C[dst_map ? dst_map[k] : k].d = alpha[ids ? ids[k] : k];
+    const u32 src = ids ? ids[k] : k;
+    Pack4 &c      = C[dst_map ? dst_map[k] : k];
+    c.d           = alpha[src];
+    if (omega)
+        c.b = omega[src];
 }
-void pack_alpha(cudaStream_t s, u32 cnt, const u32 *ids, const f64 *alpha, Pack4 *C, const u32 *dst_map) {
+void pack_alpha(cudaStream_t s, u32 cnt, const u32 *ids, const f64 *alpha, Pack4 *C, const u32 *dst_map,
+                const f64 *omega) {
     if (!cnt)
         return;
-    pack_alpha_kernel<<<grid_for(cnt, 256), 256, 0, s>>>(cnt, ids, dst_map, alpha, C);
+    pack_alpha_kernel<<<grid_for(cnt, 256), 256, 0, s>>>(cnt, ids, dst_map, alpha, omega, C);
     SB_COUNT_LAUNCH();
     SB_LAUNCH_CHECK();
 }

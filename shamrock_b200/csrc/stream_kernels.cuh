@@ -28,7 +28,8 @@ void pack_fields(cudaStream_t s, u32 cnt, const u32 *ids, const f64 *h, const f6
                  const f64 *omega, const f64 *axyz, Pack4 *A, Pack4 *B, Pack4 *C, Pack4 *D, const u32 *dst_map = nullptr);
 void unpack_ghost_fields(cudaStream_t s, u32 cnt, const Pack4 *sA, const Pack4 *sB, const Pack4 *sC, const Pack4 *sD,
                          Pack4 *A, Pack4 *B, Pack4 *C, Pack4 *D, const u32 *dst_map = nullptr);
-void pack_alpha(cudaStream_t s, u32 cnt, const u32 *ids, const f64 *alpha, Pack4 *C, const u32 *dst_map = nullptr);
+void pack_alpha(cudaStream_t s, u32 cnt, const u32 *ids, const f64 *alpha, Pack4 *C, const u32 *dst_map = nullptr,
+                const f64 *omega = nullptr);
 void unpack_cs(cudaStream_t s, u32 n, const Pack4 *C, f64 *cs, const u32 *src_map = nullptr);
 void unpack_comp(cudaStream_t s, u32 n, const Pack4 *P, int first, int nc, f64 *out, const u32 *src_map = nullptr);
 void max_reduce(cudaStream_t s, u32 n, const f64 *v, u64 *red);

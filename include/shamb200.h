@@ -132,6 +132,12 @@ int shamb200_neigh_cache_build(shamb200_ctx *ctx, const shamb200_tree *tree, con
                                size_t stride_dbl, const double *d_hpart, const double *d_rint,
                                uint32_t obj_cnt, double Rkern, double h_tolerance, int two_stage,
                                shamb200_csr *out);
+/* How the last two-stage shamb200_neigh_cache_build of this context went: out = {sum of the list lengths,
+ * (particle, candidate) accept tests, attempts (1 = every internal capacity was large enough; more = the
+ * candidate / list arrays or the tree-walk frontier were regrown and the search repeated), leaf groups walked
+ * with a frontier in global memory (objects with a very large h), shared-memory frontier capacity, capacity of
+ * the candidate-entry array}.  Diagnostics of the B200 search (no reference counterpart). */
+int shamb200_neigh_cache_stats(shamb200_ctx *ctx, uint64_t out[6]);
 
 /* ---- smoothing length, density ------------------------------------------------------------------
  * replaces modules::IterateSmoothingLengthDensity::_impl_evaluate_internal (one Newton sweep,

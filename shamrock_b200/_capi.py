@@ -81,7 +81,7 @@ SYMBOLS = [
     "shamb200_last_error", "shamb200_build_info", "shamb200_launch_count", "shamb200_reset_launch_count",
     "shamb200_ctx_create", "shamb200_ctx_destroy", "shamb200_ctx_stream", "shamb200_ctx_synchronize",
     "shamb200_tree_build", "shamb200_tree_build_auto_bbox", "shamb200_tree_field_max",
-    "shamb200_neigh_cache_build", "shamb200_h_iterate", "shamb200_h_iterate_loop", "shamb200_compute_omega",
+    "shamb200_neigh_cache_build", "shamb200_neigh_cache_stats", "shamb200_h_iterate", "shamb200_h_iterate_loop", "shamb200_compute_omega",
     "shamb200_solver_config_default", "shamb200_model_create", "shamb200_model_destroy",
     "shamb200_model_set_config", "shamb200_model_set_box", "shamb200_nccl_unique_id",
     "shamb200_model_init_comm", "shamb200_model_push_particles", "shamb200_model_patch_count",
@@ -238,6 +238,12 @@ class Context:
             C.c_void_p(h_t.data_ptr()), C.c_void_p(rint_t.data_ptr()), C.c_uint32(obj_cnt),
             C.c_double(Rkern), C.c_double(htol), int(two_stage), C.byref(cv)))
         return cv
+
+    def neigh_cache_stats(self):
+        out = (C.c_uint64 * 6)()
+        check(lib().shamb200_neigh_cache_stats(self.h, out))
+        return dict(K=out[0], pair_tests=out[1], attempts=out[2], over_groups=out[3], frontier_cap=out[4],
+                    candidate_cap=out[5])
 
     def h_iterate(self, kernel, cv, xyz_t, h_old_t, h_new_t, eps_t, pmass, h_evol_max, h_evol_iter_max,
                   stride_dbl=3):

@@ -235,6 +235,19 @@ int shamb200_neigh_cache_build(
     });
 }
 
+int shamb200_neigh_cache_stats(shamb200_ctx *ctx, uint64_t out[6]) {
+    return guard([&] {
+        need_live(ctx);
+        const SearchBuffers &sb = ctx->c.api_srch;
+        out[0] = sb.K;
+        out[1] = sb.pair_tests;
+        out[2] = sb.attempts_last;
+        out[3] = sb.over_groups_last;
+        out[4] = sb.frontier_cap;
+        out[5] = sb.gcand.cap;
+    });
+}
+
 static void ctx_reset_red(Ctx &c) {
     c.red.ensure(8);
     c.h_red.ensure(8);

@@ -948,6 +948,8 @@ void search_build(
             sb.list_s.ensure(sb.K, 1.1);
             redo = true;
         }
+        sb.attempts_last    = u32(attempt) + 1;
+        sb.over_groups_last = n_over;
         if (!redo)
             break;
         if (attempt >= 8)

@@ -24,6 +24,9 @@ struct SearchBuffers {
     u64 K        = 0; ///< total neighbour count
     u64 pair_tests = 0; ///< (particle, candidate) accept tests of the last search
     u32 frontier_cap = 320; ///< walk frontier entries per group in shared memory (doubled on demand)
+    // how the last search went (shamb200_neigh_cache_stats): attempts (1 = every capacity was large enough),
+    // groups that were walked with a frontier in global memory
+    u32 attempts_last = 0, over_groups_last = 0;
     DevBuf<NodePack> nodes;  // [I+L]
     DevBuf<Pack4> SA;        // [M] (x,y,z,h) in sorted order
     DevBuf<u32> inv_map;     // [M] rank of merged index i

@@ -46,17 +46,17 @@ def close(a, b, rtol, floor=0.0):
     return bool((err <= rtol).all()), f"max rel err {err.max():.3e}"
 
 
-def term_floors(o, ip):
-    """natural scale of the derived fields (fast fp mode only): an input known to 1e-10 (v from the previous
-    step's forces) cannot give div/curl v better than 1e-10 |v|/h, whatever the cancellation inside the sum
-    (perfect lattice + spherical blast: curl v is 1e-3 of |v|/h)."""
-    v, a, h = np.abs(o.get(ip, "vxyz")).max(), np.abs(o.get(ip, "axyz")).max(), o.get(ip, "hpart").min()
-    cs2 = (o.get(ip, "step.soundspeed") ** 2).max()
-    return {"divv": v / h, "curlv": v / h, "dtdivv": a / h + (v / h) ** 2, "axyz": cs2 / h,
-            "duint": cs2 * max(v, np.sqrt(cs2)) / h, "step.g_a": cs2 / h}
+def curl_floor(o, ip):
+    """The ONE place where the 1e-10 bound gets a floor, and why: on the UNPERTURBED lattice with a spherical
+    blast the curl of v is zero analytically — the reference's own value is the round-off of a sum whose terms
+    (|v| |grad W|) are 1e3 times larger than the result, so a relative bound on the result tests nothing but the
+    summation order.  There the bound is relative to the terms, |v| / h.  Every other field and every other
+    scenario (jittered lattices, Sod, disc, several patches) is held to 1e-10 * max(|x|, mean |x|), no floors."""
+    v, h = np.abs(o.get(ip, "vxyz")).max(), o.get(ip, "hpart").min()
+    return {"curlv": v / h}
 
 
-def compare(m, o, sc, rtol, names_extra=(), ints_exact=True):
+def compare(m, o, sc, rtol, names_extra=(), ints_exact=True, floors_fn=None):
     cfg = sc["cfg"]
     names = list(MAIN) + list(STEP) + list(names_extra)
     if cfg["av"] in (2, 3):
@@ -77,7 +77,7 @@ def compare(m, o, sc, rtol, names_extra=(), ints_exact=True):
                 assert g.shape == r.shape and np.array_equal(g, r), f"patch {ip} {nm} differs (bit-exact contract)"
             else:  # float inputs differ in the last bits: a borderline pair / cell may flip
                 assert abs(len(g) - len(r)) <= 1e-5 * len(r) + 2, f"patch {ip} {nm} size"
-        floors = term_floors(o, ip) if rtol else {}
+        floors = floors_fn(o, ip) if (rtol and floors_fn) else {}
         for nm in names:
             ok, msg = close(m.get(ip, nm), o.get(ip, nm), rtol, floors.get(nm, 0.0))
             if not ok:
@@ -85,7 +85,7 @@ def compare(m, o, sc, rtol, names_extra=(), ints_exact=True):
     assert not report, "\n".join(report)
 
 
-def run_and_compare(sc, steps=2, rtol=None, fp_mode="strict"):
+def run_and_compare(sc, steps=2, rtol=None, fp_mode="strict", floors_fn=None):
     exact = fp_mode == "strict"
     if rtol is None:
         rtol = 0.0 if exact else 1e-10
@@ -104,7 +104,7 @@ def run_and_compare(sc, steps=2, rtol=None, fp_mode="strict"):
         # (it only gates the corrector at 1e-2; on a perfect lattice dv is round-off of cancelling sums)
         assert abs(sm["eps_v"] - so["eps_v"]) <= max(rtol, 1e-12) * max(abs(so["eps_v"]), 1e-2 if rtol else 1e-300), (
             k, so["eps_v"], sm["eps_v"])
-        compare(m, o, sc, rtol, ints_exact=exact or k == 0)
+        compare(m, o, sc, rtol, ints_exact=exact or k == 0, floors_fn=floors_fn)
     m.close()
     return so
 
@@ -120,7 +120,7 @@ def test_periodic_box_step(kernel, av, two_stage, fp_mode):
 @pytest.mark.parametrize("fp_mode", FP_MODES)
 def test_periodic_box_lattice_ties(fp_mode):
     """unperturbed HCP lattice: exact ties in distances and Morton codes"""
-    run_and_compare(S.periodic_box(9000, "M4", "cd10", jitter=0.0), fp_mode=fp_mode)
+    run_and_compare(S.periodic_box(9000, "M4", "cd10", jitter=0.0), fp_mode=fp_mode, floors_fn=curl_floor)
 
 
 @pytest.mark.parametrize("fp_mode", FP_MODES)
@@ -247,6 +247,21 @@ def test_empty_patch_receives_from_two_senders():
     compare(m, o, sc, 0.0)
 
 
+@pytest.mark.parametrize("fp_mode", FP_MODES)
+def test_more_than_64_interfaces_per_sender(fp_mode):
+    """64 small patches, an interaction radius close to the patch width: every sender has 74 candidate
+    interfaces (second neighbours and periodic images included), i.e. more than one 64-box launch of the
+    ghost selection per sender (solver.cu: build_ghost_cache)"""
+    sc = S.periodic_box(1500, "M6", "cd10", jitter=0.1, grid=(4, 4, 4))
+    boxes, _ = _capi.plan_patch_grid(sc["bmin"], sc["bmax"], sc["grid"], 1)
+    b = np.array([[*lo, *hi] for lo, hi in boxes])
+    ir = np.full(len(boxes), sc["hpart"].max() * 1.1 * 3.0)
+    itf = _capi.plan_interfaces(b, sc["bmin"], sc["bmax"], True, ir, np.full(len(boxes), 30))
+    per_sender = np.bincount([i.sender for i in itf])
+    assert per_sender.max() > 64
+    run_and_compare(sc, steps=2, fp_mode=fp_mode)
+
+
 def test_errors_are_loud():
     sc = S.periodic_box(2000, "M4", "cd10")
     sc["cfg"]["gpart_mass"] = 0.0
@@ -304,9 +319,8 @@ def test_bench_path_fields_match_oracle():
     m = S.make_cuda(sc, fp_mode="fast", keep_step_data=False)
     for _ in range(3):
         so, sm = o.evolve_once(), m.evolve_once()
-    floors = term_floors(o, 0)
     for nm in ("xyz", "vxyz", "hpart", "uint", "axyz", "duint", "alpha_AV", "divv", "dtdivv", "curlv", "soundspeed"):
-        ok, msg = close(m.get(0, nm), o.get(0, nm), 1e-10, floors.get(nm, 0.0))
+        ok, msg = close(m.get(0, nm), o.get(0, nm), 1e-10)
         assert ok, f"{nm}: {msg}"
     assert abs(sm["dt"] - so["dt"]) <= 1e-10 * abs(so["dt"])
 

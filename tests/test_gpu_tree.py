@@ -176,6 +176,71 @@ def test_neighbour_cache_bit_exact(ctx, kernel, two_stage, kind, n):
     assert np.array_equal(fetch(cv.d_index_neigh_map, cv.sum_neigh_cnt, np.uint32), cref["index_neigh_map"])
 
 
+def _cache_case(c, xyz, h, n_real, kernel, sort_mode="bitonic"):
+    R = {"M4": 2.0, "M6": 3.0}[kernel]
+    n = len(xyz)
+    bb = ([0.0, 0.0, 0.0], [1.0, 1.0, 1.0])
+    ref = po.Tree(xyz, *bb, 3, bits=32)
+    ref.field_max(h, 1.1)
+    cref = ref.neigh_cache(h, n_real, R, 1.1, True)
+    dx, dh = dev(xyz), dev(h)
+    tv = c.tree_build(dx, n, *bb, reduction_level=3, sort_mode=sort_mode)
+    got = tree_arrays(tv)
+    for k, v in got.items():
+        assert np.array_equal(v, ref.get(k)), k
+    rint = torch.empty(tv.leaf_count + tv.int_count, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    c.tree_field_max(tv, dh, 1.1, rint)
+    cv = c.neigh_cache_build(tv, dx, dh, rint, n_real, R, 1.1, True)
+    c.synchronize()
+    assert cv.sum_neigh_cnt == len(cref["index_neigh_map"])
+    assert np.array_equal(fetch(cv.d_cnt_neigh, n_real, np.uint32), cref["cnt_neigh"])
+    assert np.array_equal(fetch(cv.d_index_neigh_map, cv.sum_neigh_cnt, np.uint32), cref["index_neigh_map"])
+    return c.neigh_cache_stats()
+
+
+@pytest.mark.parametrize("kind,n", [("uniform", 1 << 21), ("lattice", 3 << 20)])
+def test_tree_and_cache_millions_bit_exact(ctx, kind, n):
+    """the sizes the benchmark runs at, against the oracle: tree (codes, permutation, topology, boxes) and the
+    ordered neighbour lists of 2 - 3 Mi objects, ~77 neighbours each, bit for bit (radix tiles over hundreds of
+    CTAs, 10^5 leaf groups, 1.6 - 2.4 x 10^8 list entries)"""
+    xyz = positions(kind, n, 4242)
+    rng = np.random.default_rng(n)
+    if kind == "lattice":  # jittered lattice: the benchmark's kind of input
+        xyz = np.clip(xyz + rng.uniform(-0.1, 0.1, xyz.shape) / n ** (1 / 3), 0.0, 1.0 - 1e-12)
+    h = (1.2 / n ** (1 / 3)) * rng.uniform(0.9, 1.1, n)
+    st = _cache_case(ctx, xyz, h, n, "M4")
+    assert st["K"] > 60 * n
+
+
+def test_neighbour_cache_candidate_array_regrow():
+    """a fresh context sizes the candidate-entry array for ~24 candidate leaves per leaf; M6 with a large h needs
+    more: the search reads the exact need back, regrows and repeats (attempts > 1) — lists still bit-exact"""
+    c = _capi.Context(0)
+    n = 60000
+    xyz = positions("uniform", n, 11)
+    h = np.full(n, 1.6 / n ** (1 / 3))
+    st = _cache_case(c, xyz, h, n, "M6")
+    assert st["attempts"] > 1, st
+    st2 = _cache_case(c, xyz, h, n, "M6")  # the second search of the same context fits at once
+    assert st2["attempts"] == 1, st2
+    c.close()
+
+
+def test_neighbour_cache_global_frontier_groups_at_scale():
+    """half a million objects, three of them with an h of a tenth of the box: thousands of leaf groups overflow
+    the shared-memory frontier and are walked with a frontier in global memory (group_walk_kernel<true>)"""
+    n = 500000
+    xyz = positions("uniform", n, 5)
+    rng = np.random.default_rng(9)
+    h = (1.0 / n ** (1 / 3)) * rng.uniform(0.9, 1.1, n)
+    h[[17, 4711, 200000]] = [0.1, 0.12, 0.08]
+    c = _capi.Context(0)
+    st = _cache_case(c, xyz, h, n, "M4")
+    assert st["over_groups"] > 0, st
+    c.close()
+
+
 @pytest.mark.parametrize("kernel", ["M4", "M6"])
 def test_neighbour_cache_outlier_h(ctx, kernel):
     """A few particles with a smoothing length of the size of the box (what an unconverged h iteration leaves

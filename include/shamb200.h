@@ -371,6 +371,11 @@ int shamb200_model_host_traffic(shamb200_model *m, uint64_t out[2]);
 /* state: {time, next dt, cfl_multiplier, eps_v, h_subcycles, h_iters_last, corrector_iter,
  *         npart(global), t_step seconds (host wall), rate(part/s, this rank), K (local neighbour count)} */
 int shamb200_model_state(shamb200_model *m, double out[12]);
+/* modules::ConservativeCheck::check_conservation (shammodels/sph/src/modules/ConservativeCheck.cpp:26-190), the
+ * sums the reference logs at every step right before the corrector (Solver.cpp:2503-2504), over all ranks:
+ * out = {m sum v (x, y, z), m sum a (x, y, z), m sum (u + v.v / 2), m sum (v.a + du/dt)}.  They are reduced inside the
+ * corrector kernel of the last evolve_once (no extra pass over the fields). */
+int shamb200_model_conservation(shamb200_model *m, double out[8]);
 int shamb200_model_set_next_dt(shamb200_model *m, double dt);
 int shamb200_model_set_time(shamb200_model *m, double t);
 int shamb200_model_set_cfl_multiplier(shamb200_model *m, double v);

@@ -89,7 +89,7 @@ SYMBOLS = [
     "shamb200_model_set_field", "shamb200_model_reorder_particles", "shamb200_model_evolve_once",
     "shamb200_model_evolve_once_host",
     "shamb200_host_register", "shamb200_host_unregister", "shamb200_model_host_traffic",
-    "shamb200_model_search_stats", "shamb200_model_state",
+    "shamb200_model_search_stats", "shamb200_model_state", "shamb200_model_conservation",
     "shamb200_model_set_next_dt", "shamb200_model_set_time", "shamb200_model_set_cfl_multiplier",
     "shamb200_model_stage_times", "shamb200_plan_patch_grid", "shamb200_plan_interfaces",
     "shamb200_microbench", "shamb200_hilbert_index", "shamb200_plan_load_balance",
@@ -455,6 +455,12 @@ class Model:
         o = (C.c_uint64 * 2)()
         check(lib().shamb200_model_search_stats(self.h, o))
         return int(o[0]), int(o[1])
+
+    def conservation(self):
+        """modules::ConservativeCheck of the last step: dict(sum_p, sum_a, sum_e, sum_de), all ranks"""
+        o = (C.c_double * 8)()
+        check(lib().shamb200_model_conservation(self.h, o))
+        return dict(sum_p=np.array(o[0:3]), sum_a=np.array(o[3:6]), sum_e=float(o[6]), sum_de=float(o[7]))
 
     def host_traffic(self):
         o = (C.c_uint64 * 2)()

@@ -588,6 +588,13 @@ int shamb200_model_state(shamb200_model *m, double out[12]) {
         out[11] = f64(nloc);
     });
 }
+int shamb200_model_conservation(shamb200_model *m, double out[8]) {
+    return guard([&] {
+        need_live(m);
+        for (int k = 0; k < 8; k++)
+            out[k] = m->m.conservation[k];
+    });
+}
 int shamb200_model_set_next_dt(shamb200_model *m, double dt) {
     return guard([&] {
         need_live(m);

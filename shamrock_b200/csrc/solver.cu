@@ -545,6 +545,9 @@ void Model::build_ghost_cache() {
     comm_allreduce_host_u64(*this, meta.data(), meta.size(), 1);
     std::vector<f64> interactR(np, std::numeric_limits<f64>::lowest());
     std::vector<u32> pcount(np, 0);
+    npart_all = 0;
+    for (size_t k = 0; k < np; k++)
+        npart_all += meta[np + k];
     for (size_t k = 0; k < np; k++)
         if (meta[np + k]) {
             interactR[k] = ordered_to_f64(meta[k]) * cfg.htol_up_coarse_cycle * Rkern;
@@ -954,11 +957,7 @@ void Model::evolve_once() {
     compute_ext_forces_indep_v();
     timer.mark(s(), "position_boundary");
     apply_position_boundary();
-    npart_all = 0;
-    for (auto &p : patches)
-        if (is_local(p))
-            npart_all += p.f.n;
-    comm_allreduce_host_u64(*this, &npart_all, 1, 0);
+    // (the global object count comes out of the ghost-zone metadata all-reduce of the prestep)
 
     // Solver.cpp:2043-2048
     if (cfg.enable_particle_reordering && cfg.particle_reordering_step_freq
@@ -1070,16 +1069,26 @@ void Model::evolve_once() {
                 red.p + 4);
         }
         timer.mark(s(), "corrector");
+        step_sc.ensure(16);
+        h_step_sc.ensure(16);
+        SB_CUDA_CHECK(cudaMemsetAsync(step_sc.p, 0, 16 * sizeof(f64), s()));
         for (auto &p : patches)
             if (is_local(p) && p.f.n)
                 leapfrog_corrector(
                     s(), p.st.n, dt_ / 2, p.f.vxyz.p, p.f.axyz.p, p.st.a_old.p, p.f.uint_.p, p.f.duint.p, p.st.du_old.p,
-                    red.p + 2, reinterpret_cast<f64 *>(red.p + 3));
-        read_red(5);
-        f64 rank_veps_v = std::sqrt(ordered_to_f64(h_red.p[2]));
-        f64 sum_vsq     = bits_to_f64(h_red.p[3]);
-        comm_allreduce_host_f64(*this, &sum_vsq, 1, 0);     // C7 (Solver.cpp:2587)
-        comm_allreduce_host_f64(*this, &rank_veps_v, 1, 1); // C7 (Solver.cpp:2597)
+                    red.p + 2, reinterpret_cast<f64 *>(red.p + 3), step_sc.p + 1);
+        // C7 + C8 (Solver.cpp:2587, :2597, :3119) and the sums of ConservativeCheck, fused: Σ v² and the
+        // conservation sums in one sum all-reduce, max eps_v² and -min dt in one max all-reduce, both queued on
+        // the stream, then ONE copy and ONE synchronisation (the dt is only used if the corrector holds)
+        step_scalars(s(), red.p, step_sc.p);
+        comm_allreduce_f64(*this, step_sc.p, 9, 0);
+        comm_allreduce_f64(*this, step_sc.p + 9, 2, 1);
+        SB_CUDA_CHECK(cudaMemcpyAsync(h_step_sc.p, step_sc.p, 11 * sizeof(f64), cudaMemcpyDeviceToHost, s()));
+        SB_CUDA_CHECK(cudaStreamSynchronize(s()));
+        f64 rank_veps_v = std::sqrt(h_step_sc.p[9]);
+        f64 sum_vsq     = h_step_sc.p[0];
+        for (int k = 0; k < 8; k++) // ConservativeCheck multiplies by the particle mass (ConservativeCheck.cpp:62-188)
+            conservation[k] = cfg.gpart_mass * h_step_sc.p[1 + k];
         f64 vmean_sq   = sum_vsq / f64(npart_all);
         f64 vmean      = std::sqrt(vmean_sq);
         f64 rank_eps_v = rank_veps_v / vmean;
@@ -1103,8 +1112,7 @@ void Model::evolve_once() {
                 if (has_cs_field)
                     unpack_cs(s(), st.n, st.SC.p, p.f.soundspeed.p, st.srch.inv_map.p);
             }
-            next_cfl = ordered_to_f64(h_red.p[4]);
-            comm_allreduce_host_f64(*this, &next_cfl, 1, 2); // C8: global dt (Solver.cpp:3119)
+            next_cfl = -h_step_sc.p[10];
         }
         corrector_iter_cnt++;
     } while (need_rerun_corrector);

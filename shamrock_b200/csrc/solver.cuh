@@ -120,6 +120,10 @@ struct Model {
     DevBuf<f64> send_stage_f, recv_stage_f;
     DevBuf<u64> comm_dev;
     PinnedBuf<u64> comm_host;
+    DevBuf<f64> step_sc;       ///< the step's cross-rank scalars (stream_kernels.cu: step_scalars)
+    PinnedBuf<f64> h_step_sc;
+    /// modules::ConservativeCheck of the last step: m Σ v (3), m Σ a (3), m Σ (u + v²/2), m Σ (v·a + du/dt)
+    f64 conservation[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
     /// host-resident patch data of the running step (evolve_once_host): copy streams + hand-over events
     struct HostPipe {

@@ -59,31 +59,53 @@ void leapfrog_predictor_u(cudaStream_t s, u32 n, f64 dt, f64 *uint_, const f64 *
     SB_LAUNCH_CHECK();
 }
 
-// ---- leapfrog corrector + eps_v² max + Σ v·v ----------------------------------------------------
+// ---- leapfrog corrector + eps_v² max + Σ v·v (+ the sums of modules::ConservativeCheck) -------------------
+/// cons (optional, 8 doubles, atomically accumulated): the quantities ConservativeCheck::check_conservation
+/// (ConservativeCheck.cpp:26-190) reduces right before the corrector — Σ v (3), Σ a (3), Σ (u + v²/2),
+/// Σ (v·a + du/dt), without the particle mass — from the values this kernel reads anyway.
 __global__ void __launch_bounds__(256) corrector_kernel(
     u32 n, f64 hdt, f64 *__restrict__ vxyz, const f64 *__restrict__ axyz, const f64 *__restrict__ axyz_old,
     f64 *__restrict__ uint_, const f64 *__restrict__ duint, const f64 *__restrict__ duint_old, u64 *red_max,
-    f64 *red_sum) {
+    f64 *red_sum, f64 *cons) {
     u32 i     = blockIdx.x * blockDim.x + threadIdx.x;
     f64 epsv2 = -INFINITY, vsq = 0;
+    f64 c[8]  = {0, 0, 0, 0, 0, 0, 0, 0};
     if (i < n) {
-        f64 ix = hdt * (axyz[3 * u64(i)] - axyz_old[3 * u64(i)]);
-        f64 iy = hdt * (axyz[3 * u64(i) + 1] - axyz_old[3 * u64(i) + 1]);
-        f64 iz = hdt * (axyz[3 * u64(i) + 2] - axyz_old[3 * u64(i) + 2]);
-        f64 vx = vxyz[3 * u64(i)] + ix, vy = vxyz[3 * u64(i) + 1] + iy, vz = vxyz[3 * u64(i) + 2] + iz;
+        f64 ax = axyz[3 * u64(i)], ay = axyz[3 * u64(i) + 1], az = axyz[3 * u64(i) + 2];
+        f64 ix = hdt * (ax - axyz_old[3 * u64(i)]);
+        f64 iy = hdt * (ay - axyz_old[3 * u64(i) + 1]);
+        f64 iz = hdt * (az - axyz_old[3 * u64(i) + 2]);
+        f64 v0x = vxyz[3 * u64(i)], v0y = vxyz[3 * u64(i) + 1], v0z = vxyz[3 * u64(i) + 2];
+        f64 vx = v0x + ix, vy = v0y + iy, vz = v0z + iz;
         vxyz[3 * u64(i)]     = vx;
         vxyz[3 * u64(i) + 1] = vy;
         vxyz[3 * u64(i) + 2] = vz;
         epsv2    = ix * ix + iy * iy + iz * iz;
         vsq      = vx * vx + vy * vy + vz * vz;
-        f64 incu = hdt * (duint[i] - duint_old[i]);
-        uint_[i] = uint_[i] + incu;
+        f64 du   = duint[i], u0 = uint_[i];
+        f64 incu = hdt * (du - duint_old[i]);
+        uint_[i] = u0 + incu;
+        if (cons) {
+            c[0] = v0x, c[1] = v0y, c[2] = v0z, c[3] = ax, c[4] = ay, c[5] = az;
+            c[6] = u0 + 0.5 * (v0x * v0x + v0y * v0y + v0z * v0z);
+            c[7] = (v0x * ax + v0y * ay + v0z * az) + du;
+        }
     }
-    __shared__ f64 smax[8], ssum[8];
+    __shared__ f64 smax[8], ssum[8], scons[8][8];
     f64 m = warp_max(epsv2), q = warp_sum(vsq);
+    if (cons) {
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            c[k] = warp_sum(c[k]);
+    }
     if ((threadIdx.x & 31) == 0) {
         smax[threadIdx.x >> 5] = m;
         ssum[threadIdx.x >> 5] = q;
+        if (cons) {
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                scons[threadIdx.x >> 5][k] = c[k];
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -95,13 +117,35 @@ __global__ void __launch_bounds__(256) corrector_kernel(
         atomicMax((unsigned long long *) red_max, (unsigned long long) f64_to_ordered(a));
         atomicAdd(red_sum, b);
     }
+    if (cons && threadIdx.x < 8) {
+        f64 t = 0;
+        for (int w = 0; w < 8; w++)
+            t += scons[w][threadIdx.x];
+        atomicAdd(cons + threadIdx.x, t);
+    }
 }
 void leapfrog_corrector(
     cudaStream_t s, u32 n, f64 hdt, f64 *vxyz, const f64 *axyz, const f64 *axyz_old, f64 *uint_, const f64 *duint,
-    const f64 *duint_old, u64 *red_max, f64 *red_sum) {
+    const f64 *duint_old, u64 *red_max, f64 *red_sum, f64 *cons) {
     if (!n)
         return;
-    corrector_kernel<<<grid_for(n, 256), 256, 0, s>>>(n, hdt, vxyz, axyz, axyz_old, uint_, duint, duint_old, red_max, red_sum);
+    corrector_kernel<<<grid_for(n, 256), 256, 0, s>>>(n, hdt, vxyz, axyz, axyz_old, uint_, duint, duint_old, red_max, red_sum, cons);
+    SB_COUNT_LAUNCH();
+    SB_LAUNCH_CHECK();
+}
+
+/// the scalars a step reduces over the ranks, gathered into one f64 vector on the device:
+/// sc[0] = Σ v² and sc[1..8] (the conservation sums, already there) are summed; sc[9] = max eps_v²,
+/// sc[10] = -min dt are maximised — two back-to-back NCCL all-reduces and ONE host synchronisation
+__global__ void step_scalars_kernel(const u64 *__restrict__ red, f64 *__restrict__ sc) {
+    if (threadIdx.x == 0) {
+        sc[0]  = __longlong_as_double((long long) red[3]);
+        sc[9]  = red[2] ? ordered_to_f64(red[2]) : 0.;                       // a rank without objects: neutral
+        sc[10] = red[4] != 0xFFFFFFFFFFFFFFFFull ? -ordered_to_f64(red[4]) : -INFINITY;
+    }
+}
+void step_scalars(cudaStream_t s, const u64 *red, f64 *sc) {
+    step_scalars_kernel<<<1, 32, 0, s>>>(red, sc);
     SB_COUNT_LAUNCH();
     SB_LAUNCH_CHECK();
 }

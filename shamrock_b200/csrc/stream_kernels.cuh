@@ -7,7 +7,8 @@ void leapfrog_predictor(cudaStream_t s, u32 n, f64 dt, f64 *xyz, f64 *vxyz, cons
 void leapfrog_predictor_pos(cudaStream_t s, u32 n, f64 dt, f64 *xyz, f64 *vxyz, const f64 *axyz);
 void leapfrog_predictor_u(cudaStream_t s, u32 n, f64 dt, f64 *uint_, const f64 *duint);
 void leapfrog_corrector(cudaStream_t s, u32 n, f64 hdt, f64 *vxyz, const f64 *axyz, const f64 *axyz_old, f64 *uint_,
-                        const f64 *duint, const f64 *duint_old, u64 *red_max, f64 *red_sum);
+                        const f64 *duint, const f64 *duint_old, u64 *red_max, f64 *red_sum, f64 *cons = nullptr);
+void step_scalars(cudaStream_t s, const u64 *red, f64 *sc);
 void periodic_wrap(cudaStream_t s, u32 n, f64 *xyz, const f64 bmin[3], const f64 bmax[3]);
 void ext_force_point_mass(cudaStream_t s, u32 n, const f64 *xyz, f64 *axyz_ext, f64 central_mass, f64 G);
 void flag_in_box(cudaStream_t s, u32 n, const f64 *xyz, const f64 lo[3], const f64 hi[3], u8 *flag);

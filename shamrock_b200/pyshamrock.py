@@ -90,6 +90,98 @@ class SodTube:
 phys = _types.SimpleNamespace(SodTube=SodTube)
 
 
+# ---- shamrock.backends / shamrock.math.AABB / shamrock.tree (the tree micro-benchmark surface) ----------
+class DeviceBuffer_f64_3:
+    """sham::DeviceBuffer<f64_3> as the reference's Python sees it (shampylib/src/pyShambackends.cpp: resize,
+    get_size, copy_from_stdvec, copy_to_stdvec): 3 doubles per element, packed, in device memory."""
+
+    def __init__(self):
+        self._t = None
+
+    def resize(self, n):
+        import torch
+
+        old = self._t
+        self._t = torch.zeros((int(n), 3), dtype=torch.float64, device="cuda")
+        if old is not None:
+            k = min(len(old), int(n))
+            self._t[:k] = old[:k]
+
+    def get_size(self):
+        return 0 if self._t is None else int(self._t.shape[0])
+
+    def copy_from_stdvec(self, values):
+        import torch
+
+        a = np.ascontiguousarray(values, dtype=np.float64).reshape(-1, 3)
+        if a.shape[0] != self.get_size():
+            raise ValueError("buffer size mismatch")
+        self._t.copy_(torch.from_numpy(a))
+
+    def copy_to_stdvec(self):
+        return [tuple(r) for r in self._t.cpu().numpy()]
+
+
+class AABB_f64_3:
+    """shammath::AABB<f64_3> (shampylib/src/pyShammath.cpp): lower, upper"""
+
+    def __init__(self, lower, upper):
+        self.lower, self.upper = tuple(float(v) for v in lower), tuple(float(v) for v in upper)
+
+
+class CLBVH_u32_f64_3:
+    """shamtree::CompressedLeafBVH<u32, f64_3, 3> — the instantiation the SPH solver uses
+    (SolverConfig.hpp:443) — with the Python surface of shampylib/src/pyShamtree.cpp:28-60
+    (rebuild_from_positions, get_leaf_cell_count, get_internal_cell_count, get_total_cell_count) on top of
+    shamb200_tree_build.  `positions`: a DeviceBuffer_f64_3, a CUDA torch tensor (n, 3) f64, or host
+    coordinates (copied to the device first).  sort_mode "bitonic" reproduces the reference's order of
+    equal Morton codes; "radix" is the fast stable sort (same tree)."""
+
+    def __init__(self, device=0, sort_mode="bitonic"):
+        self._ctx = _capi.Context(device)
+        self._sort_mode = sort_mode
+        self._tv = None
+        self._keep = None
+
+    def rebuild_from_positions(self, positions, bounding_box, compression_level):
+        import torch
+
+        if isinstance(positions, DeviceBuffer_f64_3):
+            t = positions._t
+        elif isinstance(positions, torch.Tensor):
+            t = positions
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(positions, dtype=np.float64).reshape(-1, 3)).cuda()
+        if t is None or t.dtype != torch.float64 or not t.is_cuda or t.dim() != 2 or t.shape[1] != 3:
+            raise ValueError("positions must be n x 3 float64 in device memory")
+        t = t.contiguous()
+        torch.cuda.synchronize()
+        self._keep = t
+        self._tv = self._ctx.tree_build(t, int(t.shape[0]), bounding_box.lower, bounding_box.upper,
+                                        reduction_level=int(compression_level), sort_mode=self._sort_mode)
+        self._ctx.synchronize()
+
+    def _need(self):
+        if self._tv is None:
+            raise RuntimeError("the tree is empty (rebuild_from_positions has not been called)")
+        return self._tv
+
+    def get_leaf_cell_count(self):
+        return int(self._need().leaf_count)
+
+    def get_internal_cell_count(self):
+        return int(self._need().int_count)
+
+    def get_total_cell_count(self):
+        tv = self._need()
+        return int(tv.leaf_count + tv.int_count)
+
+
+backends = _types.SimpleNamespace(DeviceBuffer_f64_3=DeviceBuffer_f64_3)
+math.AABB_f64_3 = AABB_f64_3
+tree = _types.SimpleNamespace(CLBVH_u32_f64_3=CLBVH_u32_f64_3)
+
+
 # ---- shamrock.Context ------------------------------------------------------------------------------------
 class Context:
     """shamrock.Context: holds the scheduler / patch data of one model"""

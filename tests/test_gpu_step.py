@@ -262,6 +262,32 @@ def test_more_than_64_interfaces_per_sender(fp_mode):
     run_and_compare(sc, steps=2, fp_mode=fp_mode)
 
 
+def test_conservative_check():
+    """modules::ConservativeCheck (ConservativeCheck.cpp:26-190): the four sums the reference logs before the
+    corrector, reduced inside the corrector kernel, against numpy on the fields of the step (v, u taken back
+    from the corrected values)"""
+    sc = S.periodic_box(8000, "M4", "cd10", jitter=0.15)
+    m = S.make_cuda(sc)
+    m.evolve_once()
+    st = m.state()
+    m.evolve_once()
+    hdt = st["dt"] / 2
+    pm = sc["cfg"]["gpart_mass"]
+    v1, a, u1, du = m.get(0, "vxyz"), m.get(0, "axyz"), m.get(0, "uint"), m.get(0, "duint")
+    cons = m.conservation()
+    # sum a and sum (v.a + du) use a and du/dt of this step; v, u before the corrector differ from the corrected
+    # ones by hdt (a - a_old): compare what does not need a_old exactly, the rest to the size of that increment
+    assert np.allclose(cons["sum_a"], pm * a.sum(0), rtol=0, atol=1e-12 * pm * np.abs(a).sum())
+    inc = hdt * np.abs(a).max() * len(a) * pm
+    assert np.all(np.abs(cons["sum_p"] - pm * v1.sum(0)) <= 2 * inc + 1e-12 * pm * np.abs(v1).sum())
+    e1 = pm * (u1.sum() + 0.5 * (v1 * v1).sum())
+    assert abs(cons["sum_e"] - e1) <= 1e-3 * abs(e1)
+    de = pm * ((v1 * a).sum() + du.sum())
+    assert abs(cons["sum_de"] - de) <= 1e-3 * pm * (np.abs(v1 * a).sum() + np.abs(du).sum())
+    # momentum is conserved by the pairwise forces: m sum a ~ 0 compared with m sum |a|
+    assert np.abs(cons["sum_a"]).max() <= 1e-9 * pm * np.abs(a).sum()
+
+
 def test_errors_are_loud():
     sc = S.periodic_box(2000, "M4", "cd10")
     sc["cfg"]["gpart_mass"] = 0.0

@@ -442,3 +442,24 @@ def test_tree_large_properties(ctx, n, mode):
     assert np.array_equal(a["aabb_min"][0], pos.min(0)) and np.array_equal(a["aabb_max"][0], pos.max(0))
     assert np.array_equal(a["aabb_min"][:I], np.minimum(a["aabb_min"][lc], a["aabb_min"][rc]))
     assert np.array_equal(a["aabb_max"][:I], np.maximum(a["aabb_max"][lc], a["aabb_max"][rc]))
+
+
+def test_pyshamrock_tree_surface():
+    """shamrock.tree.CLBVH_*().rebuild_from_positions / get_*_cell_count (shampylib/src/pyShamtree.cpp:28-60)
+    through shamrock_b200.pyshamrock, against the oracle"""
+    from shamrock_b200 import pyshamrock as shamrock
+
+    n = 20000
+    xyz = positions("uniform", n, 3)
+    buf = shamrock.backends.DeviceBuffer_f64_3()
+    buf.resize(n)
+    buf.copy_from_stdvec(xyz)
+    assert buf.get_size() == n
+    bvh = shamrock.tree.CLBVH_u32_f64_3()
+    with pytest.raises(RuntimeError):
+        bvh.get_leaf_cell_count()
+    bvh.rebuild_from_positions(buf, shamrock.math.AABB_f64_3((0.0, 0.0, 0.0), (1.0, 1.0, 1.0)), 3)
+    ref = po.Tree(xyz, [0, 0, 0], [1, 1, 1], 3, bits=32)
+    assert bvh.get_leaf_cell_count() == ref.leaf_count
+    assert bvh.get_internal_cell_count() == ref.int_count
+    assert bvh.get_total_cell_count() == ref.leaf_count + ref.int_count

@@ -352,6 +352,8 @@ def main():
     ap.add_argument("--fp", default="fast", choices=["fast", "strict"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--host-setup", action="store_true",
+                    help="build the initial conditions with numpy on the host instead of on the device")
     ap.add_argument("--no-reorder", action="store_true",
                     help="keep the generation order of the lattice (the reference's apply_setup reorders by default)")
     args = ap.parse_args()
@@ -388,9 +390,18 @@ def main():
         dist.all_reduce(t)
         return int(t.item())
 
-    sc = workload(args.npart_per_gpu, world, rank=rank, count_reduce=count_reduce if world > 1 else None)
     ctx = _capi.Context(local)
-    m = S.make_cuda(sc, ctx=ctx, keep_step_data=False, rank=rank, world=world, nccl_id=nccl_id, fp_mode=args.fp)
+    t_setup = time.perf_counter()
+    if args.host_setup:  # numpy lattice on the host, pushed patch by patch (round-1 path)
+        sc = workload(args.npart_per_gpu, world, rank=rank, count_reduce=count_reduce if world > 1 else None)
+        m = S.make_cuda(sc, ctx=ctx, keep_step_data=False, rank=rank, world=world, nccl_id=nccl_id, fp_mode=args.fp)
+    else:  # generated on the device, every rank its own patches (shamb200_model_add_lattice_hcp + setters)
+        sc = S.periodic_box(args.npart_per_gpu * world, "M4", "cd10", jitter=0.0, grid=(world, 1, 1),
+                            stretch=(world, 1, 1), sort_mode="radix", local_boxes="device")
+        m = S.make_cuda(sc, ctx=ctx, keep_step_data=False, rank=rank, world=world, nccl_id=nccl_id, fp_mode=args.fp)
+        S.periodic_box_on_device(m, args.npart_per_gpu * world, "M4", stretch=(world, 1, 1))
+    ctx.synchronize()
+    t_setup = time.perf_counter() - t_setup
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
     if not args.no_reorder:  # SPHSetup::apply_setup(part_reordering = true), the protocol's default
         m.reorder_particles()
@@ -572,6 +583,9 @@ def main():
                        "injection, dt=0 replay (reference protocol sph_homogeneous_benchmark.py)",
                        "npart_total": n_total, "npart_per_gpu": n_total // world, "neighbours_per_particle": K / max(N, 1),
                        "patches": list(sc["grid"]), "sort": sc["sort_mode"],
+                       "ic": ("host numpy lattice" if args.host_setup else
+                              "generated on the device (shamb200_model_add_lattice_hcp, set_value_in_a_box, "
+                              "add_kernel_value)") + f", {t_setup:.2f} s",
                        "setup": "lattice order" if args.no_reorder else
                        "patch data Morton-reordered once after the setup (apply_setup part_reordering=True, the "
                        "reference's default)",

@@ -317,6 +317,31 @@ int shamb200_model_init_comm(shamb200_model *m, int rank, int world_size, const 
  * deterministic stream on every rank). */
 int shamb200_model_push_particles(shamb200_model *m, uint64_t n, const double *xyz, const double *vxyz,
                                   const double *hpart, const double *uint_);
+/* ---- initial conditions generated on the device ---------------------------------------------
+ * The reference builds its initial conditions on the host (SPHSetup::apply_setup, shammodels/sph/src/modules/
+ * SPHSetup.cpp:112-267, with GeneratorLatticeHCP / GeneratorMCDisc) and edits fields with host loops
+ * (Model::set_value_in_a_box / set_value_in_sphere / add_kernel_value / get_sum, Model.hpp:669-785).  Here every
+ * rank generates the objects of ITS patches in device memory; the counts returned are global.
+ * add_lattice_hcp: shammath::LatticeHCP (crystalLattice.hpp:52-290) points r with box_min <= r < box_max, hpart =
+ *   dr, every other field 0, appended to the owning patch in the reference's iteration order (x index fastest,
+ *   :244-248) - bit-identical to the host generator.
+ * add_disc_mc: Monte-Carlo disc (GeneratorMCDisc.cpp): Sigma ~ r^-p between r_in and r_out, H / r = H_r_in
+ *   (r / r_in)^(1/2 - q), Keplerian velocities around the configured point mass, h from the local density; object
+ *   i draws from its own counter-based stream (seed, i), so the disc does not depend on the patch / rank layout.
+ *   Needs the particle mass (shamb200_model_set_particle_mass or the config). */
+int shamb200_model_add_lattice_hcp(shamb200_model *m, double dr, const double box_min[3], const double box_max[3],
+                                   uint64_t *added);
+int shamb200_model_add_disc_mc(shamb200_model *m, uint64_t npart, uint64_t seed, double r_in, double r_out, double p,
+                               double q, double H_r_in, double disc_mass, uint64_t *added);
+int shamb200_model_set_value_in_a_box(shamb200_model *m, const char *field, int ivar, double val,
+                                      const double box_min[3], const double box_max[3]);
+int shamb200_model_set_value_in_sphere(shamb200_model *m, const char *field, double val, const double center[3],
+                                       double radius);
+int shamb200_model_add_kernel_value(shamb200_model *m, const char *field, double val, const double center[3],
+                                    double h_ker);
+int shamb200_model_get_sum(shamb200_model *m, const char *field, double out[3]); /* all ranks */
+int shamb200_model_total_part_count(shamb200_model *m, uint64_t *out);           /* Model::get_total_part_count */
+int shamb200_model_set_particle_mass(shamb200_model *m, double gpart_mass);      /* Model::set_particle_mass */
 uint32_t shamb200_model_patch_count(shamb200_model *m);       /* global number of patches   */
 int shamb200_model_patch_is_local(shamb200_model *m, uint32_t ip);
 uint32_t shamb200_model_patch_size(shamb200_model *m, uint32_t ip); /* 0 for remote patches  */

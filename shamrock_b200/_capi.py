@@ -90,6 +90,9 @@ SYMBOLS = [
     "shamb200_model_evolve_once_host",
     "shamb200_host_register", "shamb200_host_unregister", "shamb200_model_host_traffic",
     "shamb200_model_search_stats", "shamb200_model_state", "shamb200_model_conservation",
+    "shamb200_model_add_lattice_hcp", "shamb200_model_add_disc_mc", "shamb200_model_set_value_in_a_box",
+    "shamb200_model_set_value_in_sphere", "shamb200_model_add_kernel_value", "shamb200_model_get_sum",
+    "shamb200_model_total_part_count", "shamb200_model_set_particle_mass",
     "shamb200_model_set_next_dt", "shamb200_model_set_time", "shamb200_model_set_cfl_multiplier",
     "shamb200_model_stage_times", "shamb200_plan_patch_grid", "shamb200_plan_interfaces",
     "shamb200_microbench", "shamb200_hilbert_index", "shamb200_plan_load_balance",
@@ -397,6 +400,48 @@ class Model:
         keep = [xyz]
         check(lib().shamb200_model_push_particles(self.h, C.c_uint64(n), xyz.ctypes.data_as(C.c_void_p),
                                                   p(vxyz, 3), p(h, 1), p(u, 1)))
+
+    # -- initial conditions generated on the device (setup.cu)
+    def add_lattice_hcp(self, dr, box_min, box_max):
+        n = C.c_uint64()
+        check(lib().shamb200_model_add_lattice_hcp(self.h, C.c_double(dr), (C.c_double * 3)(*box_min),
+                                                   (C.c_double * 3)(*box_max), C.byref(n)))
+        return int(n.value)
+
+    def add_disc_mc(self, npart, seed, r_in, r_out, p, q, H_r_in, disc_mass):
+        n = C.c_uint64()
+        check(lib().shamb200_model_add_disc_mc(self.h, C.c_uint64(npart), C.c_uint64(seed), C.c_double(r_in),
+                                               C.c_double(r_out), C.c_double(p), C.c_double(q), C.c_double(H_r_in),
+                                               C.c_double(disc_mass), C.byref(n)))
+        return int(n.value)
+
+    def set_value_in_a_box(self, field, val, box_min, box_max, ivar=0):
+        vals = np.atleast_1d(np.asarray(val, dtype=np.float64))
+        for k, v in enumerate(vals):
+            check(lib().shamb200_model_set_value_in_a_box(self.h, field.encode(), int(ivar + k if len(vals) > 1 else ivar),
+                                                          C.c_double(v), (C.c_double * 3)(*box_min),
+                                                          (C.c_double * 3)(*box_max)))
+
+    def set_value_in_sphere(self, field, val, center, radius):
+        check(lib().shamb200_model_set_value_in_sphere(self.h, field.encode(), C.c_double(val),
+                                                       (C.c_double * 3)(*center), C.c_double(radius)))
+
+    def add_kernel_value(self, field, val, center, h_ker):
+        check(lib().shamb200_model_add_kernel_value(self.h, field.encode(), C.c_double(val),
+                                                    (C.c_double * 3)(*center), C.c_double(h_ker)))
+
+    def get_sum(self, field):
+        o = (C.c_double * 3)()
+        check(lib().shamb200_model_get_sum(self.h, field.encode(), o))
+        return np.array(o[:])
+
+    def total_part_count(self):
+        n = C.c_uint64()
+        check(lib().shamb200_model_total_part_count(self.h, C.byref(n)))
+        return int(n.value)
+
+    def set_particle_mass(self, gpart_mass):
+        check(lib().shamb200_model_set_particle_mass(self.h, C.c_double(gpart_mass)))
 
     @property
     def patch_count(self):

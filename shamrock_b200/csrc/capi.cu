@@ -508,6 +508,60 @@ int shamb200_model_push_particles(shamb200_model *m, uint64_t n, const double *x
         m->m.push_particles(n, xyz, vxyz, hpart, uint_);
     });
 }
+int shamb200_model_add_lattice_hcp(shamb200_model *m, double dr, const double box_min[3], const double box_max[3], uint64_t *added) {
+    return guard([&] {
+        need_live(m);
+        u64 n = m->m.add_lattice_hcp(dr, box_min, box_max);
+        if (added)
+            *added = n;
+    });
+}
+int shamb200_model_add_disc_mc(shamb200_model *m, uint64_t npart, uint64_t seed, double r_in, double r_out, double p,
+                               double q, double H_r_in, double disc_mass, uint64_t *added) {
+    return guard([&] {
+        need_live(m);
+        u64 n = m->m.add_disc_mc(npart, seed, r_in, r_out, p, q, H_r_in, disc_mass);
+        if (added)
+            *added = n;
+    });
+}
+int shamb200_model_set_value_in_a_box(shamb200_model *m, const char *field, int ivar, double val,
+                                      const double box_min[3], const double box_max[3]) {
+    return guard([&] {
+        need_live(m);
+        m->m.set_value_in_a_box(field, ivar, val, box_min, box_max);
+    });
+}
+int shamb200_model_set_value_in_sphere(shamb200_model *m, const char *field, double val, const double center[3], double radius) {
+    return guard([&] {
+        need_live(m);
+        m->m.set_value_in_sphere(field, val, center, radius);
+    });
+}
+int shamb200_model_add_kernel_value(shamb200_model *m, const char *field, double val, const double center[3], double h_ker) {
+    return guard([&] {
+        need_live(m);
+        m->m.add_kernel_value(field, val, center, h_ker);
+    });
+}
+int shamb200_model_get_sum(shamb200_model *m, const char *field, double out[3]) {
+    return guard([&] {
+        need_live(m);
+        m->m.get_sum(field, out);
+    });
+}
+int shamb200_model_total_part_count(shamb200_model *m, uint64_t *out) {
+    return guard([&] {
+        need_live(m);
+        *out = m->m.total_part_count();
+    });
+}
+int shamb200_model_set_particle_mass(shamb200_model *m, double gpart_mass) {
+    return guard([&] {
+        need_live(m);
+        m->m.cfg.gpart_mass = gpart_mass;
+    });
+}
 uint32_t shamb200_model_patch_count(shamb200_model *m) {
     return model_is_live(m) ? (uint32_t) m->m.patches.size() : 0;
 }

@@ -147,6 +147,14 @@ struct Model {
     void evolve_once_host(u32 ip, const shamb200_host_patchdata *in, shamb200_host_patchdata *out);
     int64_t get(u32 ip, const std::string &name, void *out, int64_t cap);
     void set_field(u32 ip, const std::string &name, const f64 *in, u64 count);
+    // initial conditions generated on the device (setup.cu); counts are global (all ranks)
+    u64 add_lattice_hcp(f64 dr, const f64 bmin[3], const f64 bmax[3]);
+    u64 add_disc_mc(u64 npart, u64 seed, f64 r_in, f64 r_out, f64 p_exp, f64 q_exp, f64 H_r_in, f64 disc_mass);
+    void set_value_in_a_box(const std::string &name, int ivar, f64 val, const f64 bmin[3], const f64 bmax[3]);
+    void set_value_in_sphere(const std::string &name, f64 val, const f64 center[3], f64 radius);
+    void add_kernel_value(const std::string &name, f64 val, const f64 center[3], f64 h_ker);
+    void get_sum(const std::string &name, f64 out[3]);
+    u64 total_part_count();
 
     // pieces of the step (names follow the reference's Solver methods)
     void keep_flagged(PatchD &p, u32 *out_kept = nullptr);

@@ -25,6 +25,31 @@ def m4_w(q):
     return (t1 + t2) / math.pi
 
 
+def periodic_box_geometry(n_target, stretch=(1, 1, 1)):
+    """lattice spacing and ideal periodic HCP box of periodic_box (no particles generated)"""
+    half = np.array([0.6 * stretch[0], 0.6 * stretch[1], 0.6 * stretch[2]])
+    vol = float(np.prod(2 * half))
+    dr = (vol / (n_target * 4 * math.sqrt(2))) ** (1.0 / 3.0)
+    bmin, bmax = lattice.get_ideal_hcp_box(dr, tuple(-half), tuple(half))
+    return dr, bmin, bmax
+
+
+def periodic_box_on_device(m, n_target, kernel="M4", stretch=(1, 1, 1)):
+    """the unjittered periodic_box scenario generated on the device (shamb200_model_add_lattice_hcp and the
+    device-side setters): every rank builds the particles of its own patches.  Same particles, fields and
+    particle mass as periodic_box(jitter=0) up to the last bit of the injected energy (numpy's pow vs x*x*x)."""
+    dr, bmin, bmax = periodic_box_geometry(n_target, stretch)
+    n = m.add_lattice_hcp(dr, bmin, bmax)
+    vol = float(np.prod(np.array(bmax) - np.array(bmin)))
+    pmass = 1.0 * vol / n
+    m.set_particle_mass(pmass)
+    big = ([-1e300] * 3, [1e300] * 3)
+    m.set_value_in_a_box("hpart", HFACT[kernel] * (pmass / 1.0) ** (1.0 / 3.0), *big)
+    m.set_value_in_a_box("uint", 1.0, *big)
+    m.add_kernel_value("uint", 50.0 * pmass, (0.0, 0.0, 0.0), 16 * dr)
+    return dict(n=n, dr=dr, bmin=bmin, bmax=bmax, pmass=pmass)
+
+
 def periodic_box(n_target, kernel="M4", av="cd10", jitter=0.0, seed=42, grid=(1, 1, 1), stretch=(1, 1, 1),
                  two_stage=True, inject=True, sort_mode="bitonic", local_boxes=None, count_reduce=None):
     """sph_homogeneous_benchmark.py: HCP lattice in a periodic box, adiabatic gamma=5/3, CD10 AV,
@@ -33,12 +58,12 @@ def periodic_box(n_target, kernel="M4", av="cd10", jitter=0.0, seed=42, grid=(1,
     Multi-rank setup: `local_boxes(bmin, bmax)` returns the [lo, hi) boxes of this rank's patches and only
     their particles are generated; `count_reduce(n_local)` returns the global particle count (an
     all-reduce) that fixes the particle mass.  Same particles as the single-process call, rank by rank."""
-    half = np.array([0.6 * stretch[0], 0.6 * stretch[1], 0.6 * stretch[2]])
-    vol = float(np.prod(2 * half))
     # HCP: one particle per dr^3 * sqrt(2) * 4  (cell volume per particle = 4 sqrt(2) dr^3)
-    dr = (vol / (n_target * 4 * math.sqrt(2))) ** (1.0 / 3.0)
-    bmin, bmax = lattice.get_ideal_hcp_box(dr, tuple(-half), tuple(half))
-    if local_boxes is None:
+    dr, bmin, bmax = periodic_box_geometry(n_target, stretch)
+    if local_boxes == "device":  # geometry and configuration only: the particles are generated on the device
+        pos = np.zeros((0, 3))
+        n = 1
+    elif local_boxes is None:
         pos = lattice.hcp_positions(dr, bmin, bmax)
         n = len(pos)
     else:
@@ -193,5 +218,6 @@ def make_cuda(sc, ctx=None, keep_step_data=True, rank=0, world=1, nccl_id=None, 
     if balance:
         owner, _ = _capi.plan_load_balance(m.patch_coords(), patch_loads(sc, world), world)
         m.set_patch_owners(owner)
-    m.push_particles(sc["xyz"], sc["vxyz"], sc["hpart"], sc["uint"])
+    if len(sc["xyz"]):
+        m.push_particles(sc["xyz"], sc["vxyz"], sc["hpart"], sc["uint"])
     return m

@@ -317,6 +317,26 @@ int shamb200_model_init_comm(shamb200_model *m, int rank, int world_size, const 
  * deterministic stream on every rank). */
 int shamb200_model_push_particles(shamb200_model *m, uint64_t n, const double *xyz, const double *vxyz,
                                   const double *hpart, const double *uint_);
+/* ---- patch scheduler ---------------------------------------------------------------------
+ * PatchScheduler (shamrock/src/scheduler/PatchScheduler.cpp:308-500): patches on the 2^21 integer grid are split
+ * into their eight children above crit_split objects, an octet of sibling leaves is merged below crit_merge,
+ * and the patches are dealt to the ranks along the Hilbert curve of their coordinates by object count
+ * (HilbertLoadBalance.cpp:46-75); a patch that changes owner moves with all its fields over NCCL send / recv.
+ * The patch list is replicated, every rank calls these functions with the same arguments (collective).
+ * init_scheduler = Model::init_scheduler(crit_split, crit_merge) (Model.hpp:82-98); step_freq > 0 runs
+ *   scheduler_step(true, true) at the start of every step_freq-th evolve_once (Solver.cpp:1970-1976), 0 = only
+ *   when called.  Ids and list order follow the reference: child 0 keeps the parent's id and place, children
+ *   1..7 (child c = 4 ix + 2 iy + iz) get fresh ids at the end of the list; a merged patch keeps child 0's id.
+ * patch_info: out = {id, coord_min[3], coord_max[3], owner rank}, box = [lo, hi) in simulation coordinates.
+ * scheduler_log (last scheduler_step): {splits, merges, patches moved, objects moved, patch count, largest rank
+ *   load, mean rank load, imbalance = max / mean - 1}. */
+int shamb200_model_init_scheduler(shamb200_model *m, uint64_t crit_split, uint64_t crit_merge, uint32_t step_freq);
+int shamb200_model_scheduler_step(shamb200_model *m, int do_split_merge, int do_load_balancing);
+int shamb200_model_split_patch(shamb200_model *m, uint32_t ip);
+int shamb200_model_merge_patches(shamb200_model *m, uint32_t ip0);
+int shamb200_model_migrate_patch(shamb200_model *m, uint32_t ip, int new_owner);
+int shamb200_model_patch_info(shamb200_model *m, uint32_t ip, uint64_t out[8], double box[6]);
+int shamb200_model_scheduler_log(shamb200_model *m, double out[8]);
 /* ---- initial conditions generated on the device ---------------------------------------------
  * The reference builds its initial conditions on the host (SPHSetup::apply_setup, shammodels/sph/src/modules/
  * SPHSetup.cpp:112-267, with GeneratorLatticeHCP / GeneratorMCDisc) and edits fields with host loops

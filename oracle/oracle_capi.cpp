@@ -425,6 +425,15 @@ int oracle_solver_reorder_particles(void *ss) {
     auto *S = (Solver *) ss;
     return guard([&] { S->reorder_particles(); });
 }
+int oracle_solver_split_patch(void *ss, uint32_t ip) {
+    auto *S = (Solver *) ss;
+    return guard([&] { S->split_patch(ip); });
+}
+int oracle_solver_merge_patches(void *ss, uint32_t ip0) {
+    auto *S = (Solver *) ss;
+    return guard([&] { S->merge_patches(ip0); });
+}
+uint64_t oracle_solver_patch_id(void *ss, uint32_t ip) { return ((Solver *) ss)->patches.at(ip).id; }
 int oracle_solver_evolve_once(void *ss) {
     auto *S = (Solver *) ss;
     return guard([&] { S->evolve_once(); });

@@ -262,6 +262,16 @@ class Solver:
     def reorder_particles(self):
         _chk(lib().oracle_solver_reorder_particles(C.c_void_p(self.s)))
 
+    def split_patch(self, ip):
+        _chk(lib().oracle_solver_split_patch(C.c_void_p(self.s), C.c_uint32(ip)))
+
+    def merge_patches(self, ip0):
+        _chk(lib().oracle_solver_merge_patches(C.c_void_p(self.s), C.c_uint32(ip0)))
+
+    def patch_id(self, ip):
+        lib().oracle_solver_patch_id.restype = C.c_uint64
+        return int(lib().oracle_solver_patch_id(C.c_void_p(self.s), C.c_uint32(ip)))
+
     def evolve_once(self):
         _chk(lib().oracle_solver_evolve_once(C.c_void_p(self.s)))
         return self.state()

@@ -8,7 +8,8 @@
 // Supported configuration subset: kernels M4/M6; EOS adiabatic / isothermal /
 // locally-isothermal LP07; AV constant / MM97 / CD10 / constant-disc; BC free / periodic;
 // external force: central point mass (with accretion radius); kill spheres; density-based h.
-// Patches: a static grid of patches on the 2^21 integer grid (no split/merge/load-balancing).
+// Patches: a grid of patches on the 2^21 integer grid; split_patch / merge_patches restate the scheduler's
+// patch-list operations (ids, order, data partition); no load balancing (one process).
 // -------------------------------------------------------------------------------------------
 #pragma once
 #include "shamrock_oracle.hpp"
@@ -227,6 +228,7 @@ struct Solver {
                     }
                     patches.push_back(std::move(p));
                 }
+        next_patch_id = u64(nx) * ny * nz;
     }
 
     /// owner patch of a position (SerialPatchTree::compute_patch_owner semantics: the patch
@@ -247,6 +249,91 @@ struct Solver {
         for (auto &p : patches)
             s += p.pdat.n;
         return s;
+    }
+
+    u64 next_patch_id = 0; ///< SchedulerPatchList::_next_patch_id (set by init_patch_grid)
+
+    /// PatchScheduler::split_patches for one patch.  ref: shamrock/include/shamrock/patch/PatchCoord.hpp:36-120
+    /// (split coordinate = ((max - min + 1) / 2) - 1 + min per axis; child c = 4 ix + 2 iy + iz),
+    /// shamrock/src/scheduler/scheduler_patch_list.cpp:109-157 (child 0 keeps the id and the place of the
+    /// parent, children 1..7 get new ids and are appended), SchedulerPatchData.cpp:302-358 +
+    /// PatchDataLayer::split_patchdata (every object goes to the child whose [lo, hi) box holds it, order kept)
+    void split_patch(u32 ip) {
+        Patch parent = std::move(patches.at(ip));
+        u64 sp[3];
+        for (int d = 0; d < 3; d++) {
+            if (parent.coord_max[d] == parent.coord_min[d])
+                throw std::runtime_error("patch cannot be split any further");
+            sp[d] = ((parent.coord_max[d] - parent.coord_min[d]) + 1) / 2 - 1 + parent.coord_min[d];
+        }
+        Patch ch[8];
+        for (int c = 0; c < 8; c++) {
+            int up[3]  = {(c >> 2) & 1, (c >> 1) & 1, c & 1};
+            ch[c].id   = c == 0 ? parent.id : next_patch_id++;
+            for (int d = 0; d < 3; d++) {
+                ch[c].coord_min[d] = up[d] ? sp[d] + 1 : parent.coord_min[d];
+                ch[c].coord_max[d] = up[d] ? parent.coord_max[d] : sp[d];
+            }
+            ch[c].pdat.resize(0);
+        }
+        std::vector<std::vector<u32>> ids(8);
+        for (u32 i = 0; i < parent.pdat.n; i++) {
+            const f64 *r = &parent.pdat.xyz[3 * size_t(i)];
+            int own      = -1;
+            for (int c = 0; c < 8 && own < 0; c++) {
+                f64 lo[3], hi[3];
+                patch_box(ch[c], lo, hi);
+                if (lo[0] <= r[0] && r[0] < hi[0] && lo[1] <= r[1] && r[1] < hi[1] && lo[2] <= r[2] && r[2] < hi[2])
+                    own = c;
+            }
+            if (own < 0)
+                throw std::runtime_error("split_patchdata: an object is outside of the patch that is split");
+            ids[own].push_back(i);
+        }
+        for (int c = 0; c < 8; c++)
+            ch[c].pdat.append_subset_from(parent.pdat, ids[c]);
+        patches[ip] = std::move(ch[0]);
+        for (int c = 1; c < 8; c++)
+            patches.push_back(std::move(ch[c]));
+        step.clear();
+    }
+
+    /// PatchScheduler::merge_patches for the octet whose child 0 is patch `ip0`.  ref:
+    /// scheduler_patch_list.cpp:160-185 + Patch::merge_patch (Patch.hpp:253-286: the merged patch keeps the id
+    /// of child 0), SchedulerPatchData::merge_patchdata (children appended in child order 0..7)
+    void merge_patches(u32 ip0) {
+        Patch &p0 = patches.at(ip0);
+        u64 ext[3];
+        for (int d = 0; d < 3; d++)
+            ext[d] = p0.coord_max[d] - p0.coord_min[d] + 1;
+        std::vector<size_t> sib(8, size_t(-1));
+        for (int c = 0; c < 8; c++) {
+            int up[3] = {(c >> 2) & 1, (c >> 1) & 1, c & 1};
+            for (size_t k = 0; k < patches.size(); k++) {
+                bool ok = true;
+                for (int d = 0; d < 3; d++)
+                    ok = ok && patches[k].coord_min[d] == p0.coord_min[d] + up[d] * ext[d]
+                         && patches[k].coord_max[d] == p0.coord_max[d] + up[d] * ext[d];
+                if (ok)
+                    sib[c] = k;
+            }
+            if (sib[c] == size_t(-1))
+                throw std::runtime_error("merge_patches: the octet of siblings is not complete");
+        }
+        for (int c = 1; c < 8; c++) {
+            PatchData &src = patches[sib[c]].pdat;
+            std::vector<u32> all(src.n);
+            for (u32 i = 0; i < src.n; i++)
+                all[i] = i;
+            p0.pdat.append_subset_from(src, all);
+        }
+        for (int d = 0; d < 3; d++)
+            p0.coord_max[d] = p0.coord_min[d] + 2 * ext[d] - 1;
+        std::vector<size_t> dead(sib.begin() + 1, sib.end());
+        std::sort(dead.begin(), dead.end());
+        for (size_t q = dead.size(); q-- > 0;)
+            patches.erase(patches.begin() + dead[q]);
+        step.clear();
     }
 
     void evolve_once();

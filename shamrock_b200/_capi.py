@@ -93,6 +93,9 @@ SYMBOLS = [
     "shamb200_model_add_lattice_hcp", "shamb200_model_add_disc_mc", "shamb200_model_set_value_in_a_box",
     "shamb200_model_set_value_in_sphere", "shamb200_model_add_kernel_value", "shamb200_model_get_sum",
     "shamb200_model_total_part_count", "shamb200_model_set_particle_mass",
+    "shamb200_model_init_scheduler", "shamb200_model_scheduler_step", "shamb200_model_split_patch",
+    "shamb200_model_merge_patches", "shamb200_model_migrate_patch", "shamb200_model_patch_info",
+    "shamb200_model_scheduler_log",
     "shamb200_model_set_next_dt", "shamb200_model_set_time", "shamb200_model_set_cfl_multiplier",
     "shamb200_model_stage_times", "shamb200_plan_patch_grid", "shamb200_plan_interfaces",
     "shamb200_microbench", "shamb200_hilbert_index", "shamb200_plan_load_balance",
@@ -400,6 +403,36 @@ class Model:
         keep = [xyz]
         check(lib().shamb200_model_push_particles(self.h, C.c_uint64(n), xyz.ctypes.data_as(C.c_void_p),
                                                   p(vxyz, 3), p(h, 1), p(u, 1)))
+
+    # -- patch scheduler (scheduler.cu)
+    def init_scheduler(self, crit_split, crit_merge, step_freq=0):
+        check(lib().shamb200_model_init_scheduler(self.h, C.c_uint64(int(crit_split)), C.c_uint64(int(crit_merge)),
+                                                  C.c_uint32(step_freq)))
+
+    def scheduler_step(self, do_split_merge=True, do_load_balancing=True):
+        check(lib().shamb200_model_scheduler_step(self.h, int(do_split_merge), int(do_load_balancing)))
+        return self.scheduler_log()
+
+    def split_patch(self, ip):
+        check(lib().shamb200_model_split_patch(self.h, C.c_uint32(ip)))
+
+    def merge_patches(self, ip0):
+        check(lib().shamb200_model_merge_patches(self.h, C.c_uint32(ip0)))
+
+    def migrate_patch(self, ip, new_owner):
+        check(lib().shamb200_model_migrate_patch(self.h, C.c_uint32(ip), int(new_owner)))
+
+    def patch_info(self, ip):
+        o, b = (C.c_uint64 * 8)(), (C.c_double * 6)()
+        check(lib().shamb200_model_patch_info(self.h, C.c_uint32(ip), o, b))
+        return dict(id=int(o[0]), coord_min=tuple(o[1:4]), coord_max=tuple(o[4:7]), owner=int(o[7]),
+                    lo=tuple(b[0:3]), hi=tuple(b[3:6]))
+
+    def scheduler_log(self):
+        o = (C.c_double * 8)()
+        check(lib().shamb200_model_scheduler_log(self.h, o))
+        return dict(splits=int(o[0]), merges=int(o[1]), moves=int(o[2]), moved_objects=int(o[3]), npatch=int(o[4]),
+                    max_rank_load=int(o[5]), mean_rank_load=o[6], imbalance=o[7])
 
     # -- initial conditions generated on the device (setup.cu)
     def add_lattice_hcp(self, dr, box_min, box_max):

@@ -31,6 +31,7 @@ SOURCES = {
     "sph2_fast.cu": ["-fmad=true"],
     "solver.cu": ["-fmad=false"],
     "setup.cu": ["-fmad=false"],
+    "scheduler.cu": ["-fmad=false"],
     "solver_comm.cu": ["-fmad=false"],
     "capi.cu": ["-fmad=false"],
     "capi_stages.cu": ["-fmad=false"],

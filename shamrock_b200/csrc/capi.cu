@@ -508,6 +508,64 @@ int shamb200_model_push_particles(shamb200_model *m, uint64_t n, const double *x
         m->m.push_particles(n, xyz, vxyz, hpart, uint_);
     });
 }
+int shamb200_model_init_scheduler(shamb200_model *m, uint64_t crit_split, uint64_t crit_merge, uint32_t step_freq) {
+    return guard([&] {
+        need_live(m);
+        m->m.crit_split     = crit_split;
+        m->m.crit_merge     = crit_merge;
+        m->m.scheduler_freq = step_freq;
+    });
+}
+int shamb200_model_scheduler_step(shamb200_model *m, int do_split_merge, int do_load_balancing) {
+    return guard([&] {
+        need_live(m);
+        m->m.scheduler_step(do_split_merge != 0, do_load_balancing != 0);
+    });
+}
+int shamb200_model_split_patch(shamb200_model *m, uint32_t ip) {
+    return guard([&] {
+        need_live(m);
+        m->m.split_patch(ip);
+    });
+}
+int shamb200_model_merge_patches(shamb200_model *m, uint32_t ip0) {
+    return guard([&] {
+        need_live(m);
+        m->m.merge_patches(ip0);
+    });
+}
+int shamb200_model_migrate_patch(shamb200_model *m, uint32_t ip, int new_owner) {
+    return guard([&] {
+        need_live(m);
+        m->m.refresh_counts();
+        m->m.migrate_patch(ip, new_owner);
+    });
+}
+int shamb200_model_patch_info(shamb200_model *m, uint32_t ip, uint64_t out[8], double box[6]) {
+    return guard([&] {
+        need_live(m);
+        const PatchD &p = m->m.patches.at(ip);
+        out[0] = p.id;
+        for (int d = 0; d < 3; d++) {
+            out[1 + d] = p.cmin[d];
+            out[4 + d] = p.cmax[d];
+            if (box) {
+                box[d]     = p.lo[d];
+                box[3 + d] = p.hi[d];
+            }
+        }
+        out[7] = u64(p.owner);
+    });
+}
+int shamb200_model_scheduler_log(shamb200_model *m, double out[8]) {
+    return guard([&] {
+        need_live(m);
+        const auto &l = m->m.sched_log;
+        out[0] = l.splits, out[1] = l.merges, out[2] = l.moves, out[3] = f64(l.moved_objects), out[4] = l.npatch;
+        out[5] = f64(l.max_rank_load), out[6] = l.mean_rank_load;
+        out[7] = l.mean_rank_load > 0 ? f64(l.max_rank_load) / l.mean_rank_load - 1. : 0.;
+    });
+}
 int shamb200_model_add_lattice_hcp(shamb200_model *m, double dr, const double box_min[3], const double box_max[3], uint64_t *added) {
     return guard([&] {
         need_live(m);

@@ -112,6 +112,24 @@ template<class T>
 struct PinnedBuf {
     T *p       = nullptr;
     size_t cap = 0;
+    PinnedBuf() = default;
+    PinnedBuf(const PinnedBuf &)            = delete;
+    PinnedBuf &operator=(const PinnedBuf &) = delete;
+    PinnedBuf(PinnedBuf &&o) noexcept : p(o.p), cap(o.cap) {
+        o.p   = nullptr;
+        o.cap = 0;
+    }
+    PinnedBuf &operator=(PinnedBuf &&o) noexcept {
+        if (this != &o) {
+            if (p)
+                cudaFreeHost(p);
+            p     = o.p;
+            cap   = o.cap;
+            o.p   = nullptr;
+            o.cap = 0;
+        }
+        return *this;
+    }
     ~PinnedBuf() {
         if (p)
             cudaFreeHost(p);

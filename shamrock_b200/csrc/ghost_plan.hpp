@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <limits>
 #include <stdexcept>
 #include <vector>
 
@@ -77,17 +78,35 @@ inline std::vector<IfaceCand> plan_interfaces(
     double bsize[3] = {box_max[0] - box_min[0], box_max[1] - box_min[1], box_max[2] - box_min[2]};
     int rep         = periodic ? 1 : 0;
     std::vector<IfaceCand> cand;
+    // pruning that does not change the result (hundreds of patches: the 27 np² loop must stay cheap): only the
+    // patches that hold objects take part, and a shifted sender that does not even touch the hull of the grown
+    // receivers (most periodic images of most patches) is dropped before the loop over the receivers
+    std::vector<size_t> live;
+    for (size_t k = 0; k < np; k++)
+        if (pcount[k])
+            live.push_back(k);
+    double hull_lo[3], hull_hi[3];
+    for (int d = 0; d < 3; d++) {
+        hull_lo[d] = std::numeric_limits<double>::infinity();
+        hull_hi[d] = -std::numeric_limits<double>::infinity();
+    }
+    for (size_t k : live)
+        for (int d = 0; d < 3; d++) {
+            hull_lo[d] = std::fmin(hull_lo[d], patches[k].lo[d] - interactR[k]);
+            hull_hi[d] = std::fmax(hull_hi[d], patches[k].hi[d] + interactR[k]);
+        }
     for (int32_t xoff = -rep; xoff <= rep; xoff++)
         for (int32_t yoff = -rep; yoff <= rep; yoff++)
             for (int32_t zoff = -rep; zoff <= rep; zoff++) {
                 double off[3] = {xoff * bsize[0], yoff * bsize[1], zoff * bsize[2]};
-                for (size_t sd = 0; sd < np; sd++) {
-                    if (!pcount[sd])
-                        continue;
+                for (size_t sd : live) {
                     const PatchBox &S = patches[sd];
-                    for (size_t rc = 0; rc < np; rc++) {
-                        if (!pcount[rc])
-                            continue;
+                    bool reach        = true; // does the shifted sender touch the hull of the grown receivers?
+                    for (int d = 0; d < 3; d++)
+                        reach = reach && (S.hi[d] + off[d] >= hull_lo[d]) && (S.lo[d] + off[d] <= hull_hi[d]);
+                    if (!reach)
+                        continue;
+                    for (size_t rc : live) {
                         if (rc == sd && xoff == 0 && yoff == 0 && zoff == 0)
                             continue;
                         const PatchBox &R = patches[rc];

@@ -80,20 +80,21 @@ StageTimer::~StageTimer() {
 // ---------------------------------------------------------------------------------------------
 /// red slots: 0 eps max, 1 eps min, 2 eps_v² max, 3 Σv² (f64 bits), 4 cfl min, 8.. per-patch h max
 __global__ void reset_red_kernel(u64 *red, int n) {
-    int i = threadIdx.x;
-    if (i >= n)
-        return;
-    u64 v = 0; // max accumulators (ordered encoding: 0 is below every double) and the f64 sum
-    if (i == 1 || i == 4)
-        v = 0xFFFFFFFFFFFFFFFFull; // min accumulators
-    red[i] = v;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        u64 v = 0; // max accumulators (ordered encoding: 0 is below every double) and the f64 sum
+        if (i == 1 || i == 4)
+            v = 0xFFFFFFFFFFFFFFFFull; // min accumulators
+        red[i] = v;
+    }
 }
-constexpr int RED_SLOTS = 8 + 256;
+/// 8 step scalars + one slot per patch (max h)
+static int red_slots(const Model &m) { return 8 + int(std::max<size_t>(256, m.patches.size())); }
 
 void Model::reset_red() {
-    red.ensure(RED_SLOTS);
-    h_red.ensure(RED_SLOTS);
-    reset_red_kernel<<<1, 512, 0, s()>>>(red.p, RED_SLOTS);
+    const int n = red_slots(*this);
+    red.ensure(n);
+    h_red.ensure(n);
+    reset_red_kernel<<<1, 512, 0, s()>>>(red.p, n);
     SB_COUNT_LAUNCH();
 }
 void Model::read_red(int n) {
@@ -141,6 +142,7 @@ void Model::set_box(const f64 bmin[3], const f64 bmax[3], u32 nx, u32 ny, u32 nz
     for (size_t k = 0; k < grid.size(); k++)
         static_cast<PatchBox &>(patches[k]) = grid[k];
     u32 np = u32(grid.size());
+    next_patch_id = np;
     std::vector<f64> hb(size_t(np) * 6);
     for (u32 k = 0; k < np; k++)
         for (int d = 0; d < 3; d++) {
@@ -528,8 +530,8 @@ void Model::reattribute_patch_objects() {
 void Model::build_ghost_cache() {
     const size_t np = patches.size();
     const f64 Rkern = cfg.kernel == SHAMB200_KERNEL_M4 ? 2.0 : 3.0;
-    if (np > 256)
-        throw std::runtime_error("too many patches");
+    if (np > 65536)
+        throw std::runtime_error("too many patches (65536 at most)");
     // interactR_patch = max(h) * htol * Rkern  (SPHUtilities.hpp:84-92)
     reset_red();
     for (size_t k = 0; k < np; k++)
@@ -939,9 +941,14 @@ void Model::evolve_once() {
     const bool has_curl   = cfg.av == SHAMB200_AV_CD10;
     const bool has_dtdivv = cfg.av == SHAMB200_AV_CD10;
     const bool has_cs_field = has_alpha || cfg.eos == SHAMB200_EOS_LOCALLY_ISOTHERMAL_LP07;
-    red.ensure(RED_SLOTS);
-    h_red.ensure(RED_SLOTS);
+    red.ensure(red_slots(*this));
+    h_red.ensure(red_slots(*this));
 
+    // Solver.cpp:1970-1976: the scheduler step (split / merge / load balancing) opens the step
+    if (scheduler_freq && step_count % scheduler_freq == 0 && !pipe.active) {
+        timer.mark(s(), "scheduler");
+        scheduler_step(true, true);
+    }
     timer.mark(s(), "predictor");
     point_mass_accrete_particles();
     // host-resident patch data (evolve_once_host): copies overlap the kernels

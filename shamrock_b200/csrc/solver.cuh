@@ -143,6 +143,23 @@ struct Model {
 
     void set_box(const f64 bmin[3], const f64 bmax[3], u32 nx, u32 ny, u32 nz);
     void push_particles(u64 n, const f64 *xyz, const f64 *vxyz, const f64 *h, const f64 *u);
+    // patch scheduler (scheduler.cu): PatchScheduler::scheduler_step and its pieces
+    u64 next_patch_id = 0;            ///< SchedulerPatchList::_next_patch_id
+    u64 crit_split = 0, crit_merge = 0; ///< Model::init_scheduler(crit_split, crit_merge); 0 = never
+    u32 scheduler_freq = 0;           ///< run scheduler_step inside evolve_once every this many steps (0 = never)
+    std::vector<u64> patch_counts;    ///< replicated object count per patch (refresh_counts)
+    struct SchedLog {
+        u32 splits = 0, merges = 0, moves = 0, npatch = 0;
+        u64 moved_objects = 0, max_rank_load = 0;
+        f64 mean_rank_load = 0;
+    } sched_log;
+    void refresh_boxes();
+    void refresh_counts();
+    std::vector<u32> sibling_octet(u32 ip0) const;
+    void split_patch(u32 ip);
+    void merge_patches(u32 ip0);
+    void migrate_patch(u32 ip, int new_owner);
+    void scheduler_step(bool do_split_merge, bool do_load_balancing);
     void evolve_once();
     void evolve_once_host(u32 ip, const shamb200_host_patchdata *in, shamb200_host_patchdata *out);
     int64_t get(u32 ip, const std::string &name, void *out, int64_t cap);

@@ -242,12 +242,15 @@ __global__ void __launch_bounds__(256) patch_owner_kernel(
         return;
     f64 x = xyz[3 * u64(i)], y = xyz[3 * u64(i) + 1], z = xyz[3 * u64(i) + 2];
     u32 own = 0xFFFFFFFFu;
-    for (u32 k = 0; k < npatch; k++) {
+    {   // nearly every object is still in its patch (patch boxes are disjoint: the order of the tests is free)
+        const f64 *b = boxes + 6 * self;
+        if (self < npatch && b[0] <= x && x < b[3] && b[1] <= y && y < b[4] && b[2] <= z && z < b[5])
+            own = self;
+    }
+    for (u32 k = 0; k < npatch && own == 0xFFFFFFFFu; k++) {
         const f64 *b = boxes + 6 * k;
-        if (b[0] <= x && x < b[3] && b[1] <= y && y < b[4] && b[2] <= z && z < b[5]) {
+        if (b[0] <= x && x < b[3] && b[1] <= y && y < b[4] && b[2] <= z && z < b[5])
             own = k;
-            break;
-        }
     }
     owner[i]     = own;
     stay_flag[i] = (own == self) ? 1 : 0;

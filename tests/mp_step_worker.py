@@ -23,7 +23,10 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ids = [_capi.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
-    if which == "periodic":
+    if which == "scheduler":  # forced migration + forced split + merge + automatic load balancing
+        sc = S.periodic_box(16000, "M4", "cd10", jitter=0.2, grid=(2, 2, 1))
+        steps, rtol = 6, 0.0
+    elif which == "periodic":
         sc = S.periodic_box(16000, "M4", "cd10", jitter=0.2, grid=(2, 2, 1))
         steps, rtol = 4, 0.0
     elif which == "sod":
@@ -51,6 +54,21 @@ def main():
         names += ["alpha_AV", "divv", "curlv", "dtdivv", "step.g_a", "step.g_alpha"]
     nloc = 0
     for k in range(steps):
+        if which == "scheduler":
+            if k == 1:  # one forced migration: patch 1 changes rank with all its fields
+                was = m.patch_info(1)["owner"]
+                m.migrate_patch(1, 1 - was)
+                assert m.patch_info(1)["owner"] == 1 - was and m.patch_is_local(1) == (rank == 1 - was)
+            if k == 2:  # one forced split (both sides: same ids, same list order, same data partition)
+                o.split_patch(0), m.split_patch(0)
+                assert m.patch_count == o.patch_count == 11
+                assert [m.patch_info(ip)["id"] for ip in range(11)] == [o.patch_id(ip) for ip in range(11)]
+            if k == 3:  # the load balancer deals the 11 patches to the two ranks along the Hilbert curve
+                log = m.scheduler_step(False, True)
+                assert log["imbalance"] < 0.2, log
+            if k == 4:  # and the octet is merged back (the siblings travel to the owner of child 0 first)
+                o.merge_patches(0), m.merge_patches(0)
+                assert m.patch_count == o.patch_count == 4
         so, sm = o.evolve_once(), m.evolve_once()
         for key in ("h_subcycles", "corrector_iter", "npart"):
             assert so[key] == sm[key], (k, key, so[key], sm[key])

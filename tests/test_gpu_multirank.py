@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.parametrize("fp_mode", ["strict", "fast"])
-@pytest.mark.parametrize("which", ["periodic", "sod", "disc", "disc_balanced"])
+@pytest.mark.parametrize("which", ["periodic", "sod", "disc", "disc_balanced", "scheduler"])
 def test_two_rank_step_matches_oracle(which, fp_mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")

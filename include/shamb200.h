@@ -351,6 +351,11 @@ int shamb200_model_scheduler_log(shamb200_model *m, double out[8]);
  *   Needs the particle mass (shamb200_model_set_particle_mass or the config). */
 int shamb200_model_add_lattice_hcp(shamb200_model *m, double dr, const double box_min[3], const double box_max[3],
                                    uint64_t *added);
+/* add_disc_lattice: the HCP lattice cut to a flared disc (r_in < R < r_out, |z| < zcut R), Keplerian velocities,
+ * h = hfact (4 sqrt 2)^(1/3) dr: a regular stand-in for the Monte-Carlo disc (whose Poisson clumps leave objects
+ * with a non-converging h iteration, in the reference as well) for large benchmark runs. */
+int shamb200_model_add_disc_lattice(shamb200_model *m, double dr, double r_in, double r_out, double zcut,
+                                    uint64_t *added);
 int shamb200_model_add_disc_mc(shamb200_model *m, uint64_t npart, uint64_t seed, double r_in, double r_out, double p,
                                double q, double H_r_in, double disc_mass, uint64_t *added);
 int shamb200_model_set_value_in_a_box(shamb200_model *m, const char *field, int ivar, double val,

@@ -90,7 +90,7 @@ SYMBOLS = [
     "shamb200_model_evolve_once_host",
     "shamb200_host_register", "shamb200_host_unregister", "shamb200_model_host_traffic",
     "shamb200_model_search_stats", "shamb200_model_state", "shamb200_model_conservation",
-    "shamb200_model_add_lattice_hcp", "shamb200_model_add_disc_mc", "shamb200_model_set_value_in_a_box",
+    "shamb200_model_add_lattice_hcp", "shamb200_model_add_disc_lattice", "shamb200_model_add_disc_mc", "shamb200_model_set_value_in_a_box",
     "shamb200_model_set_value_in_sphere", "shamb200_model_add_kernel_value", "shamb200_model_get_sum",
     "shamb200_model_total_part_count", "shamb200_model_set_particle_mass",
     "shamb200_model_init_scheduler", "shamb200_model_scheduler_step", "shamb200_model_split_patch",
@@ -439,6 +439,12 @@ class Model:
         n = C.c_uint64()
         check(lib().shamb200_model_add_lattice_hcp(self.h, C.c_double(dr), (C.c_double * 3)(*box_min),
                                                    (C.c_double * 3)(*box_max), C.byref(n)))
+        return int(n.value)
+
+    def add_disc_lattice(self, dr, r_in, r_out, zcut):
+        n = C.c_uint64()
+        check(lib().shamb200_model_add_disc_lattice(self.h, C.c_double(dr), C.c_double(r_in), C.c_double(r_out),
+                                                    C.c_double(zcut), C.byref(n)))
         return int(n.value)
 
     def add_disc_mc(self, npart, seed, r_in, r_out, p, q, H_r_in, disc_mass):

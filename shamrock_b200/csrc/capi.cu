@@ -574,6 +574,14 @@ int shamb200_model_add_lattice_hcp(shamb200_model *m, double dr, const double bo
             *added = n;
     });
 }
+int shamb200_model_add_disc_lattice(shamb200_model *m, double dr, double r_in, double r_out, double zcut, uint64_t *added) {
+    return guard([&] {
+        need_live(m);
+        u64 n = m->m.add_disc_lattice(dr, r_in, r_out, zcut);
+        if (added)
+            *added = n;
+    });
+}
 int shamb200_model_add_disc_mc(shamb200_model *m, uint64_t npart, uint64_t seed, double r_in, double r_out, double p,
                                double q, double H_r_in, double disc_mass, uint64_t *added) {
     return guard([&] {

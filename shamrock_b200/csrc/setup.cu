@@ -55,6 +55,9 @@ struct LatticeArgs {
     IdxBox ib;                ///< index sub-box scanned for this patch (a superset of its lattice points)
     u64 first;                ///< first flat index of this launch (x fastest)
     u32 count;                ///< flat indices in this launch
+    // flared-disc filter (add_disc_lattice): keep r_in < R < r_out, |z| < zcut R; Keplerian speed sqrt(GM / R)
+    int disc = 0;
+    f64 r_in = 0, r_out = 0, zcut = 0, GM = 0, h_disc = 0;
 };
 
 __device__ __forceinline__ bool lattice_point(const LatticeArgs &a, u32 t, f64 &x, f64 &y, f64 &z) {
@@ -64,6 +67,11 @@ __device__ __forceinline__ bool lattice_point(const LatticeArgs &a, u32 t, f64 &
     const i64 j = a.ib.lo[1] + i64(r % u64(a.ib.n[1]));
     const i64 k = a.ib.lo[2] + i64(r / u64(a.ib.n[1]));
     hcp_point(a.dr, i, j, k, x, y, z);
+    if (a.disc) {
+        const f64 R = sqrt(x * x + y * y);
+        if (!(R > a.r_in && R < a.r_out && fabs(z) < a.zcut * R))
+            return false;
+    }
     return a.gen_lo[0] <= x && x < a.gen_hi[0] && a.gen_lo[1] <= y && y < a.gen_hi[1] && a.gen_lo[2] <= z
            && z < a.gen_hi[2] && a.pat_lo[0] <= x && x < a.pat_hi[0] && a.pat_lo[1] <= y && y < a.pat_hi[1]
            && a.pat_lo[2] <= z && z < a.pat_hi[2];
@@ -78,7 +86,7 @@ __global__ void __launch_bounds__(256) lattice_flag_kernel(LatticeArgs a, u8 *__
 }
 __global__ void __launch_bounds__(256) lattice_scatter_kernel(
     LatticeArgs a, const u8 *__restrict__ flag, const u32 *__restrict__ pos, u32 base, f64 *__restrict__ xyz,
-    f64 *__restrict__ hpart) {
+    f64 *__restrict__ hpart, f64 *__restrict__ vxyz) {
     u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.count || !flag[t])
         return;
@@ -88,7 +96,14 @@ __global__ void __launch_bounds__(256) lattice_scatter_kernel(
     xyz[3 * o]     = x;
     xyz[3 * o + 1] = y;
     xyz[3 * o + 2] = z;
-    hpart[o]       = a.dr; // GeneratorLatticeHCP: hpart = dr
+    hpart[o]       = a.disc ? a.h_disc : a.dr; // GeneratorLatticeHCP: hpart = dr
+    if (a.disc) {
+        const f64 R  = sqrt(x * x + y * y);
+        const f64 vk = sqrt(a.GM / R);
+        vxyz[3 * o]     = -vk * (y / R);
+        vxyz[3 * o + 1] = vk * (x / R);
+        vxyz[3 * o + 2] = 0;
+    }
 }
 
 __global__ void __launch_bounds__(256) set_in_box_kernel(
@@ -229,6 +244,19 @@ static void zero_tail(cudaStream_t s, PatchFields &f, u32 from, u32 to) {
 }
 
 u64 Model::add_lattice_hcp(f64 dr, const f64 bmin[3], const f64 bmax[3]) {
+    return add_lattice_impl(dr, bmin, bmax, nullptr);
+}
+/// HCP lattice cut to a flared disc (r_in < R < r_out, |z| < zcut R) on Keplerian orbits: a regular (relaxed)
+/// stand-in for the Monte-Carlo disc whose Poisson clumps leave objects with a non-converging h iteration
+u64 Model::add_disc_lattice(f64 dr, f64 r_in, f64 r_out, f64 zcut) {
+    const f64 zmax    = zcut * r_out;
+    const f64 lo[3]   = {-r_out, -r_out, -zmax}, hi[3] = {r_out, r_out, zmax};
+    const f64 hfact   = cfg.kernel == SHAMB200_KERNEL_M4 ? 1.2 : 1.0;
+    const f64 disc[5] = {r_in, r_out, zcut, cfg.constant_G * (cfg.has_point_mass ? cfg.pm_mass : 1.),
+                         hfact * std::cbrt(4 * std::sqrt(2.0)) * dr};
+    return add_lattice_impl(dr, lo, hi, disc);
+}
+u64 Model::add_lattice_impl(f64 dr, const f64 bmin[3], const f64 bmax[3], const f64 *disc) {
     if (patches.empty())
         throw std::runtime_error("the box size is not set, please resize the box to the domain size");
     if (!(dr > 0))
@@ -255,6 +283,10 @@ u64 Model::add_lattice_hcp(f64 dr, const f64 bmin[3], const f64 bmax[3]) {
             a.pat_lo[d] = p.lo[d], a.pat_hi[d] = p.hi[d];
         }
         a.ib          = hcp_index_box(dr, lo, hi);
+        if (disc) {
+            a.disc = 1;
+            a.r_in = disc[0], a.r_out = disc[1], a.zcut = disc[2], a.GM = disc[3], a.h_disc = disc[4];
+        }
         const u64 tot = u64(a.ib.n[0]) * u64(a.ib.n[1]) * u64(a.ib.n[2]);
         for (u64 first = 0; first < tot; first += CHUNK) {
             a.first = first;
@@ -276,7 +308,8 @@ u64 Model::add_lattice_hcp(f64 dr, const f64 bmin[3], const f64 bmax[3]) {
             const u32 n0 = p.f.n;
             p.f.reserve(u32(n0 + kept), s());
             zero_tail(s(), p.f, n0, u32(n0 + kept));
-            lattice_scatter_kernel<<<grid_for(a.count, 256), 256, 0, s()>>>(a, flag.p, pos.p, n0, p.f.xyz.p, p.f.hpart.p);
+            lattice_scatter_kernel<<<grid_for(a.count, 256), 256, 0, s()>>>(
+                a, flag.p, pos.p, n0, p.f.xyz.p, p.f.hpart.p, p.f.vxyz.p);
             SB_COUNT_LAUNCH();
             p.f.n = u32(n0 + kept);
             added += kept;

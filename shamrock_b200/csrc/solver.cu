@@ -410,29 +410,42 @@ void Model::reattribute_patch_objects() {
     const size_t np = patches.size();
     if (np == 1)
         return; // single patch: periodic → everything is inside after the wrap; free → no constraint
-    // 1. owners + per-destination counts of every local patch (one read-back per patch)
+    // 1. owners + per-destination counts of every local patch: all histograms land in one device array and come
+    //    back with ONE copy and ONE synchronisation (a read-back per patch costs 0.4 ms of latency each)
     std::vector<DevBuf<u32>> owners(np);
     std::vector<u64> cm(np * np, 0); // cm[src*np + dst]
-    box_counts.ensure(np + 1);
-    for (size_t k = 0; k < np; k++) {
-        PatchD &p = patches[k];
-        if (!is_local(p) || !p.f.n)
-            continue;
+    std::vector<size_t> loc;
+    for (size_t k = 0; k < np; k++)
+        if (is_local(patches[k]) && patches[k].f.n)
+            loc.push_back(k);
+    box_counts.ensure(loc.size() * (np + 1) + 1);
+    SB_CUDA_CHECK(cudaMemsetAsync(box_counts.p, 0, (loc.size() * (np + 1) + 1) * sizeof(u32), s()));
+    const size_t hist_smem = (np + 1) * sizeof(u32);
+    if (hist_smem > 48 * 1024)
+        throw std::runtime_error("reattribute_patch_objects: too many patches for the owner histogram");
+    for (size_t q = 0; q < loc.size(); q++) {
+        const size_t k = loc[q];
+        PatchD &p      = patches[k];
         flag.ensure(p.f.n);
         owners[k].ensure(p.f.n);
         patch_owner(s(), p.f.n, p.f.xyz.p, u32(np), d_boxes.p, u32(k), flag.p, owners[k].p);
-        SB_CUDA_CHECK(cudaMemsetAsync(box_counts.p, 0, (np + 1) * sizeof(u32), s()));
         unsigned nb = (unsigned) std::min<u64>(u64(kNumSM) * 8, (u64(p.f.n) + 255) / 256);
-        owner_hist_kernel<<<nb, 256, (np + 1) * sizeof(u32), s()>>>(p.f.n, owners[k].p, u32(np), box_counts.p);
+        owner_hist_kernel<<<nb, 256, hist_smem, s()>>>(p.f.n, owners[k].p, u32(np), box_counts.p + q * (np + 1));
         SB_COUNT_LAUNCH();
-        std::vector<u32> hc(np + 1);
-        SB_CUDA_CHECK(cudaMemcpyAsync(hc.data(), box_counts.p, (np + 1) * sizeof(u32), cudaMemcpyDeviceToHost, s()));
+    }
+    {
+        std::vector<u32> hc(loc.size() * (np + 1) + 1);
+        SB_CUDA_CHECK(cudaMemcpyAsync(hc.data(), box_counts.p, hc.size() * sizeof(u32), cudaMemcpyDeviceToHost, s()));
         SB_CUDA_CHECK(cudaStreamSynchronize(s()));
-        if (hc[np])
-            throw std::runtime_error("a new id could not be computed");
-        for (size_t d = 0; d < np; d++)
-            if (d != k)
-                cm[k * np + d] = hc[d];
+        for (size_t q = 0; q < loc.size(); q++) {
+            const size_t k = loc[q];
+            const u32 *h   = hc.data() + q * (np + 1);
+            if (h[np])
+                throw std::runtime_error("a new id could not be computed");
+            for (size_t d = 0; d < np; d++)
+                if (d != k)
+                    cm[k * np + d] = h[d];
+        }
     }
     comm_allreduce_host_u64(*this, cm.data(), cm.size(), 1);
     bool any = false;
@@ -708,6 +721,8 @@ void Model::compute_presteps_rint() {
 /// Solver::start_neighbors_cache (Solver.cpp:1364-1386): Morton-sorted storage + the B200 search
 void Model::start_neighbors_cache() {
     const f64 Rkern = cfg.kernel == SHAMB200_KERNEL_M4 ? 2.0 : 3.0;
+    if (verbose())
+        fprintf(stderr, "[shamb200 rank %d] neighbour cache: %zu interfaces\n", rank, ifaces.size());
     K_local         = 0;
     pair_tests_local = 0;
     for (auto &p : patches)
@@ -718,6 +733,10 @@ void Model::start_neighbors_cache() {
                 [&](const char *name) { timer.mark(s(), name); });
             K_local += p.st.srch.K;
             pair_tests_local += p.st.srch.pair_tests;
+            if (verbose() > 1)
+                fprintf(stderr, "[shamb200 rank %d]   patch %llu: n %u m %u L %u K %llu attempts %u over %u\n", rank,
+                        (unsigned long long) p.id, p.st.n, p.st.m, p.st.tree.L, (unsigned long long) p.st.srch.K,
+                        p.st.srch.attempts_last, p.st.srch.over_groups_last);
         }
 }
 
@@ -793,6 +812,10 @@ void Model::sph_prestep() {
             }
         }
         h_iters_last         = iter_h;
+        if (verbose())
+            fprintf(stderr, "[shamb200 rank %d] h sub-cycle %u: sweeps %u, eps in [%g, %g], K %llu, tests %llu\n", rank,
+                    hstep_cnt, iter_h, local_min_eps, local_max_eps, (unsigned long long) K_local,
+                    (unsigned long long) pair_tests_local);
         bool should_rerun_gz = local_min_eps < 0;
         bool below_tol       = local_max_eps < cfg.epsilon_h;
         bool converged       = below_tol && !should_rerun_gz;

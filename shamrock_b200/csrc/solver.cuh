@@ -138,6 +138,14 @@ struct Model {
     void pipe_download(const char *const *names, int count);
 
     explicit Model(Ctx *c, const shamb200_solver_config &cf) : ctx(c), cfg(cf) {}
+    /// SHAMB200_VERBOSE=1|2: progress of the prestep on stderr (sub-cycles; 2: every patch)
+    static int verbose() {
+        static int v = [] {
+            const char *e = getenv("SHAMB200_VERBOSE");
+            return e ? atoi(e) : 0;
+        }();
+        return v;
+    }
     cudaStream_t s() const { return ctx->stream; }
     bool is_local(const PatchD &p) const { return p.owner == rank; }
 
@@ -166,6 +174,8 @@ struct Model {
     void set_field(u32 ip, const std::string &name, const f64 *in, u64 count);
     // initial conditions generated on the device (setup.cu); counts are global (all ranks)
     u64 add_lattice_hcp(f64 dr, const f64 bmin[3], const f64 bmax[3]);
+    u64 add_disc_lattice(f64 dr, f64 r_in, f64 r_out, f64 zcut);
+    u64 add_lattice_impl(f64 dr, const f64 bmin[3], const f64 bmax[3], const f64 *disc);
     u64 add_disc_mc(u64 npart, u64 seed, f64 r_in, f64 r_out, f64 p_exp, f64 q_exp, f64 H_r_in, f64 disc_mass);
     void set_value_in_a_box(const std::string &name, int ivar, f64 val, const f64 bmin[3], const f64 bmax[3]);
     void set_value_in_sphere(const std::string &name, f64 val, const f64 center[3], f64 radius);

@@ -317,6 +317,18 @@ int shamb200_model_init_comm(shamb200_model *m, int rank, int world_size, const 
  * deterministic stream on every rank). */
 int shamb200_model_push_particles(shamb200_model *m, uint64_t n, const double *xyz, const double *vxyz,
                                   const double *hpart, const double *uint_);
+/* ---- checkpoint / restart ------------------------------------------------------------------
+ * Model::dump / Model::load_from_dump (shammodels/sph/include/shammodels/sph/Model.hpp:906-995) on the container of
+ * shamrock::write_shamrock_dump / load_shamrock_dump (shamrock/src/io/ShamrockDump.cpp:25-274): three
+ * length-prefixed JSON headers (user metadata = solver configuration, time, next dt, cfl multiplier; patch
+ * metadata = patch list, simulation box, scheduler criteria, layout; table = pids / bytecounts / offsets), then one
+ * blob per patch, written by the rank that owns it into ONE file.  load_dump replaces the configuration, the
+ * patches and the state of `m` (create it with any configuration; call init_comm first for several ranks): owners
+ * are folded onto the ranks present (owner % world), so a dump restarts on another number of GPUs.  A restarted
+ * model continues bit-identically.  The blob encoding is this library's ("shamb200-1"), not the reference's
+ * SerializeHelper byte stream.  Collective: every rank calls it with the same file name (shared file system). */
+int shamb200_model_dump(shamb200_model *m, const char *fname);
+int shamb200_model_load_dump(shamb200_model *m, const char *fname);
 /* ---- patch scheduler ---------------------------------------------------------------------
  * PatchScheduler (shamrock/src/scheduler/PatchScheduler.cpp:308-500): patches on the 2^21 integer grid are split
  * into their eight children above crit_split objects, an octet of sibling leaves is merged below crit_merge,

@@ -93,7 +93,7 @@ SYMBOLS = [
     "shamb200_model_add_lattice_hcp", "shamb200_model_add_disc_lattice", "shamb200_model_add_disc_mc", "shamb200_model_set_value_in_a_box",
     "shamb200_model_set_value_in_sphere", "shamb200_model_add_kernel_value", "shamb200_model_get_sum",
     "shamb200_model_total_part_count", "shamb200_model_set_particle_mass",
-    "shamb200_model_init_scheduler", "shamb200_model_scheduler_step", "shamb200_model_split_patch",
+    "shamb200_model_dump", "shamb200_model_load_dump", "shamb200_model_init_scheduler", "shamb200_model_scheduler_step", "shamb200_model_split_patch",
     "shamb200_model_merge_patches", "shamb200_model_migrate_patch", "shamb200_model_patch_info",
     "shamb200_model_scheduler_log",
     "shamb200_model_set_next_dt", "shamb200_model_set_time", "shamb200_model_set_cfl_multiplier",
@@ -403,6 +403,13 @@ class Model:
         keep = [xyz]
         check(lib().shamb200_model_push_particles(self.h, C.c_uint64(n), xyz.ctypes.data_as(C.c_void_p),
                                                   p(vxyz, 3), p(h, 1), p(u, 1)))
+
+    # -- checkpoint / restart (dump.cu)
+    def dump(self, fname):
+        check(lib().shamb200_model_dump(self.h, str(fname).encode()))
+
+    def load_dump(self, fname):
+        check(lib().shamb200_model_load_dump(self.h, str(fname).encode()))
 
     # -- patch scheduler (scheduler.cu)
     def init_scheduler(self, crit_split, crit_merge, step_freq=0):

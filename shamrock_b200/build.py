@@ -32,6 +32,7 @@ SOURCES = {
     "solver.cu": ["-fmad=false"],
     "setup.cu": ["-fmad=false"],
     "scheduler.cu": ["-fmad=false"],
+    "dump.cu": ["-fmad=false"],
     "solver_comm.cu": ["-fmad=false"],
     "capi.cu": ["-fmad=false"],
     "capi_stages.cu": ["-fmad=false"],

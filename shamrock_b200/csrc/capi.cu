@@ -508,6 +508,22 @@ int shamb200_model_push_particles(shamb200_model *m, uint64_t n, const double *x
         m->m.push_particles(n, xyz, vxyz, hpart, uint_);
     });
 }
+int shamb200_model_dump(shamb200_model *m, const char *fname) {
+    return guard([&] {
+        need_live(m);
+        if (!fname)
+            throw std::invalid_argument("null file name");
+        m->m.dump(fname);
+    });
+}
+int shamb200_model_load_dump(shamb200_model *m, const char *fname) {
+    return guard([&] {
+        need_live(m);
+        if (!fname)
+            throw std::invalid_argument("null file name");
+        m->m.load_dump(fname);
+    });
+}
 int shamb200_model_init_scheduler(shamb200_model *m, uint64_t crit_split, uint64_t crit_merge, uint32_t step_freq) {
     return guard([&] {
         need_live(m);

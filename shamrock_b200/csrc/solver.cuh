@@ -168,6 +168,9 @@ struct Model {
     void merge_patches(u32 ip0);
     void migrate_patch(u32 ip, int new_owner);
     void scheduler_step(bool do_split_merge, bool do_load_balancing);
+    // checkpoint / restart (dump.cu): write_shamrock_dump / load_shamrock_dump container
+    void dump(const std::string &fname);
+    void load_dump(const std::string &fname);
     void evolve_once();
     void evolve_once_host(u32 ip, const shamb200_host_patchdata *in, shamb200_host_patchdata *out);
     int64_t get(u32 ip, const std::string &name, void *out, int64_t cap);

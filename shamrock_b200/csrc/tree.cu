@@ -381,6 +381,212 @@ void radix_sort_by_key(
 }
 
 // =============================================================================================
+// Onesweep LSD radix sort (CUB-free): ONE histogram kernel reads the keys once for all digits, then one kernel
+// per 8-bit digit ranks a tile of 4096 keys, publishes the tile's digit counts and finds its global offsets by
+// decoupled look-back over the status words of the tiles before it (Adinets & Merrill 2022; the reference's own
+// experimental version: shamalgs/include/shamalgs/details/algorithm/radixSortOnesweep.hpp:53) — no per-pass
+// histogram / scan kernels, no host synchronisation.  Stable; same result as radix_sort_by_key.
+// Status word: [flag:2 | value:30], flag 1 = the tile's own count (aggregate), 2 = inclusive prefix.
+// =============================================================================================
+constexpr u32 OS_FLAG_AGG = 1u << 30, OS_FLAG_PRE = 2u << 30, OS_VALUE = (1u << 30) - 1u;
+
+__device__ __forceinline__ u32 ld_relaxed_gpu(const u32 *p) {
+    u32 v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu(u32 *p, u32 v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+/// all digit histograms in one pass over the keys: hist[pass * 256 + digit]
+__global__ void __launch_bounds__(256) onesweep_hist_kernel(const u32 *__restrict__ keys, u32 n, int passes, u32 *__restrict__ hist) {
+    __shared__ u32 sh[4 * 256];
+    for (int j = threadIdx.x; j < 4 * 256; j += 256)
+        sh[j] = 0;
+    __syncthreads();
+    for (u64 i = u64(blockIdx.x) * 256 + threadIdx.x; i < n; i += u64(gridDim.x) * 256) {
+        const u32 k = keys[i];
+        for (int p = 0; p < passes; p++)
+            atomicAdd(&sh[p * 256 + ((k >> (8 * p)) & 0xFF)], 1u);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < passes * 256; j += 256)
+        if (sh[j])
+            atomicAdd(&hist[j], sh[j]);
+}
+/// exclusive scan of every pass's 256 digit totals (one warp-scan block per pass), in place
+__global__ void __launch_bounds__(256) onesweep_bases_kernel(u32 *__restrict__ hist) {
+    __shared__ u32 wsum[8];
+    u32 *h   = hist + blockIdx.x * 256;
+    u32 v    = h[threadIdx.x];
+    u32 inc  = v;
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o)
+            inc += t;
+    }
+    if (lane == 31)
+        wsum[w] = inc;
+    __syncthreads();
+    u32 before = 0;
+#pragma unroll
+    for (int ww = 0; ww < 8; ww++)
+        before += ww < w ? wsum[ww] : 0u;
+    h[threadIdx.x] = before + inc - v;
+}
+
+template<bool IOTA>
+__global__ void __launch_bounds__(RADIX_THREADS) onesweep_pass_kernel(
+    const u32 *__restrict__ keys, const u32 *__restrict__ vals, u32 n, int shift, const u32 *__restrict__ gbase,
+    u32 *__restrict__ status, u32 *__restrict__ tile_counter, u32 *__restrict__ keys_out, u32 *__restrict__ vals_out) {
+    constexpr int NW = RADIX_THREADS / 32;
+    __shared__ u32 whist[NW][256];
+    __shared__ u32 dstart[256], gofs[256], wtot[NW];
+    __shared__ u32 skey[RADIX_TILE], sval[RADIX_TILE];
+    __shared__ u32 s_tile;
+    if (threadIdx.x == 0)
+        s_tile = atomicAdd(tile_counter, 1u); // tiles are numbered in the order they start: a tile only waits
+    for (int j = threadIdx.x; j < NW * 256; j += RADIX_THREADS) // for tiles that are already running
+        (&whist[0][0])[j] = 0;
+    __syncthreads();
+    const u32 tile = s_tile;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const u32 wbase = tile * RADIX_TILE + w * (RADIX_TILE / NW);
+    u32 k[RADIX_ITEMS], v[RADIX_ITEMS];
+    u32 rank[RADIX_ITEMS];
+#pragma unroll
+    for (int r = 0; r < RADIX_ITEMS; r++) {
+        u32 i      = wbase + r * 32 + lane;
+        bool valid = i < n;
+        k[r]       = valid ? keys[i] : 0xFFFFFFFFu;
+        v[r]       = valid ? (IOTA ? i : vals[i]) : 0u;
+        u32 d      = (k[r] >> shift) & 0xFF;
+        u32 md      = valid ? d : 256u + lane; // invalid lanes never match valid ones
+        u32 mask    = __match_any_sync(0xffffffffu, md);
+        u32 before  = __popc(mask & ((1u << lane) - 1u));
+        int leader  = __ffs(mask) - 1;
+        u32 pre     = 0;
+        if (valid && lane == leader) {
+            pre         = whist[w][d];
+            whist[w][d] = pre + __popc(mask);
+        }
+        pre     = __shfl_sync(0xffffffffu, pre, leader);
+        rank[r] = pre + before;
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        const u32 d = threadIdx.x;
+        u32 run     = 0;
+#pragma unroll
+        for (int ww = 0; ww < NW; ww++) {
+            u32 c        = whist[ww][d];
+            whist[ww][d] = run;
+            run += c;
+        }
+        // publish this tile's count of digit d, then sum the tiles before it (decoupled look-back)
+        u32 *st = status + size_t(tile) * 256 + d;
+        st_relaxed_gpu(st, (tile == 0 ? OS_FLAG_PRE : OS_FLAG_AGG) | run);
+        u32 excl = 0;
+        if (tile > 0) {
+            for (u32 t = tile - 1;;) {
+                const u32 sv = ld_relaxed_gpu(status + size_t(t) * 256 + d);
+                if ((sv >> 30) == 0)
+                    continue; // not published yet: that tile is running, spin
+                excl += sv & OS_VALUE;
+                if (sv & OS_FLAG_PRE)
+                    break;
+                t--; // an aggregate: keep walking (tile 0 always publishes a prefix)
+            }
+            st_relaxed_gpu(st, OS_FLAG_PRE | (excl + run));
+        }
+        u32 inc = run; // tile-local start of every digit: block scan over the 256 digit counts
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            u32 t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o)
+                inc += t;
+        }
+        if (lane == 31)
+            wtot[w] = inc;
+        __syncthreads();
+        u32 before = 0;
+#pragma unroll
+        for (int ww = 0; ww < NW; ww++)
+            before += ww < w ? wtot[ww] : 0u;
+        dstart[d] = before + inc - run;
+        gofs[d]   = gbase[d] + excl - (before + inc - run);
+    }
+    __syncthreads();
+    // stage the tile in digit order in shared memory (stable: warp, round, lane = input order) ...
+#pragma unroll
+    for (int r = 0; r < RADIX_ITEMS; r++) {
+        u32 i = wbase + r * 32 + lane;
+        if (i < n) {
+            u32 d    = (k[r] >> shift) & 0xFF;
+            u32 lp   = dstart[d] + whist[w][d] + rank[r];
+            skey[lp] = k[r];
+            sval[lp] = v[r];
+        }
+    }
+    __syncthreads();
+    // ... and write it out: consecutive threads write consecutive addresses inside each digit's run
+    const u32 tile0 = tile * RADIX_TILE;
+    const u32 ntile = n - tile0 < u32(RADIX_TILE) ? n - tile0 : u32(RADIX_TILE);
+    for (u32 i = threadIdx.x; i < ntile; i += RADIX_THREADS) {
+        u32 kk  = skey[i];
+        u32 pos = gofs[(kk >> shift) & 0xFF] + i;
+        keys_out[pos] = kk;
+        vals_out[pos] = sval[i];
+    }
+}
+
+/// stable onesweep sort on `bits` key bits; values = 0..len-1 when iota_values (the value array is then not
+/// read in the first pass).  Result in keys / vals.  No host synchronisation.
+void onesweep_sort_by_key(
+    cudaStream_t s, u32 *keys, u32 *vals, u32 *keys_alt, u32 *vals_alt, u32 len, int bits, DevBuf<u32> &work,
+    bool iota_values) {
+    if (len <= 1)
+        return;
+    if (len >= (1u << 30)) { // status words carry 30-bit prefixes
+        radix_sort_by_key(s, keys, vals, keys_alt, vals_alt, len, bits, work);
+        return;
+    }
+    int passes = (bits + 7) / 8;
+    if (passes & 1)
+        passes++; // even number of passes so that the result lands in keys / vals
+    if (passes > 4)
+        throw std::invalid_argument("onesweep: at most 32 key bits");
+    const u32 nt = (len + RADIX_TILE - 1) / RADIX_TILE;
+    // work: [4 * 256 histograms / bases | 4 tile counters (+ pad) | passes * nt * 256 status words]
+    const size_t words = 4 * 256 + 16 + size_t(passes) * nt * 256;
+    work.ensure(words);
+    SB_CUDA_CHECK(cudaMemsetAsync(work.p, 0, words * sizeof(u32), s));
+    u32 *hist = work.p, *counters = work.p + 4 * 256, *status = work.p + 4 * 256 + 16;
+    unsigned nb = (unsigned) std::min<u64>(u64(kNumSM) * 8, (u64(len) + 255) / 256);
+    onesweep_hist_kernel<<<nb, 256, 0, s>>>(keys, len, passes, hist);
+    SB_COUNT_LAUNCH();
+    onesweep_bases_kernel<<<passes, 256, 0, s>>>(hist);
+    SB_COUNT_LAUNCH();
+    u32 *ki = keys, *vi = vals, *ko = keys_alt, *vo = vals_alt;
+    for (int p = 0; p < passes; p++) {
+        if (p == 0 && iota_values)
+            onesweep_pass_kernel<true><<<nt, RADIX_THREADS, 0, s>>>(
+                ki, vi, len, 8 * p, hist + 256 * p, status + size_t(p) * nt * 256, counters + p, ko, vo);
+        else
+            onesweep_pass_kernel<false><<<nt, RADIX_THREADS, 0, s>>>(
+                ki, vi, len, 8 * p, hist + 256 * p, status + size_t(p) * nt * 256, counters + p, ko, vo);
+        SB_COUNT_LAUNCH();
+        std::swap(ki, ko);
+        std::swap(vi, vo);
+    }
+    SB_LAUNCH_CHECK();
+}
+
+// =============================================================================================
 // Leaf compression (K6-K9)
 // =============================================================================================
 __device__ __forceinline__ int karras_delta_d(int x, int y, u32 morton_length, const u32 *m) {
@@ -572,6 +778,16 @@ __global__ void __launch_bounds__(128) leaf_field_max_propagate_kernel(
 // =============================================================================================
 /// Morton codes over the box [bmin, bmax] + key/value sort: t.index_map[0..M) is the Morton order of the
 /// objects (shamtree/src/RadixTreeMortonBuilder.cpp:68-107, the part modules::ParticleReordering needs)
+/// sort_mode RADIX: the onesweep sort on the 30 bits of a Morton code (SHAMB200_ONESWEEP=0: the three-kernel
+/// LSD sort of round 1, for A / B runs)
+static void sort_radix(cudaStream_t s, TreeBuffers &t, u32 M) {
+    const char *e = getenv("SHAMB200_ONESWEEP");
+    if (e && atoi(e) == 0)
+        radix_sort_by_key(s, t.morton.p, t.index_map.p, t.morton_alt.p, t.index_alt.p, M, 32, t.radix_hist);
+    else // index_map holds 0..M-1 (morton_kernel): the first pass generates it instead of reading it
+        onesweep_sort_by_key(s, t.morton.p, t.index_map.p, t.morton_alt.p, t.index_alt.p, M, 30, t.radix_hist, true);
+}
+
 void morton_sort_permutation(
     cudaStream_t s, TreeBuffers &t, const f64 *d_xyz, size_t stride, u32 M, const f64 *bmin, const f64 *bmax,
     int sort_mode) {
@@ -593,7 +809,7 @@ void morton_sort_permutation(
     if (sort_mode == SORT_RADIX) {
         t.morton_alt.ensure(t.P2);
         t.index_alt.ensure(t.P2);
-        radix_sort_by_key(s, t.morton.p, t.index_map.p, t.morton_alt.p, t.index_alt.p, M, 32, t.radix_hist);
+        sort_radix(s, t, M);
     } else {
         bitonic_sort_by_key(s, t.morton.p, t.index_map.p, t.P2);
     }
@@ -636,13 +852,15 @@ void tree_build(
         t.morton_alt.ensure(t.P2);
         t.index_alt.ensure(t.P2);
         // only the M real keys: the padding (0xFFFFFFFF, above every 30-bit code) is already in place behind them
-        radix_sort_by_key(s, t.morton.p, t.index_map.p, t.morton_alt.p, t.index_alt.p, M, 32, t.radix_hist);
+        sort_radix(s, t, M);
     } else {
         bitonic_sort_by_key(s, t.morton.p, t.index_map.p, t.P2);
     }
     // leaf compression
     t.split1.ensure(M);
     t.split2.ensure(M);
+    // (a version that keeps the split table and the reduction iterations of a tile in shared memory was measured
+    // at 0.97 ms against 0.41 ms for these four streaming launches at 17 M keys: profiles/README.md)
     split_table_kernel<<<grid_for(M, 256), 256, 0, s>>>(t.morton.p, M, t.split1.p);
     SB_COUNT_LAUNCH();
     u8 *cur = t.split1.p, *oth = t.split2.p;

@@ -48,6 +48,11 @@ void radix_sort_by_key(
     cudaStream_t s, u32 *keys, u32 *vals, u32 *keys_alt, u32 *vals_alt, u32 len, int bits,
     DevBuf<u32> &hist);
 
+/// the same sort in one histogram kernel + one decoupled-look-back kernel per digit (no host synchronisation)
+void onesweep_sort_by_key(
+    cudaStream_t s, u32 *keys, u32 *vals, u32 *keys_alt, u32 *vals_alt, u32 len, int bits, DevBuf<u32> &work,
+    bool iota_values);
+
 inline u32 roundup_pow2(u32 v) {
     if (v <= 1)
         return 1;

@@ -997,10 +997,14 @@ void Model::evolve_once() {
         reorder_particles();
     }
 
+    if (piped) { // positions (and the external acceleration) are final once the boundary has been applied: they
+        static const char *const first[] = {"xyz", "axyz_ext"}; // go back while the tree and the cache are built
+        pipe_download(first, 2);
+    }
     sph_prestep();
     if (piped) {
-        static const char *const early[] = {"xyz", "hpart", "axyz_ext"};
-        pipe_download(early, 3); // final since the drift / the h iteration: go back during the CD10 operators
+        static const char *const early[] = {"hpart"};
+        pipe_download(early, 1); // final since the h iteration: goes back during the CD10 operators
     }
     if (piped_in) {
         SB_CUDA_CHECK(cudaStreamWaitEvent(s(), pipe.ev_in2, 0));
@@ -1038,6 +1042,10 @@ void Model::evolve_once() {
                     cfg.gpart_mass, has_curl, has_dtdivv, cfg.combined_dtdiv_divcurlv_compute != 0, p.f.divv.p,
                     p.f.curlv.p, p.f.dtdivv.p, omega_in_av_pass() ? st.omega.p : nullptr);
             }
+        if (piped && corrector_iter_cnt == 0 && has_alpha) { // out of the operator pass: back during the EOS / forces
+            static const char *const ops[] = {"divv", "curlv", "dtdivv"};
+            pipe_download(ops, 3);
+        }
         timer.mark(s(), "av_eos");
         if (has_alpha) {
             for (auto &p : patches)
@@ -1069,8 +1077,8 @@ void Model::evolve_once() {
                         cfg.alpha_AV, p.st.SE.p, p.st.SF.p, sf16 ? p.st.SG.p : nullptr);
                 }
         if (piped && corrector_iter_cnt == 0) {
-            static const char *const mid[] = {"divv", "curlv", "dtdivv", "alpha_AV@updated"};
-            pipe_download(mid, has_alpha ? 4 : 0); // go back during the force loop
+            static const char *const mid[] = {"alpha_AV@updated"};
+            pipe_download(mid, has_alpha ? 1 : 0); // goes back during the force loop
         }
         timer.mark(s(), "forces");
         // forces, v_sig and the CFL dt come out of one pass over the neighbour lists.  The CFL uses the cfl
@@ -1097,6 +1105,10 @@ void Model::evolve_once() {
                 s(), cfg.fp_mode, cfg.kernel, cfg.av, rank_csr_of(st.srch, st.tree), st.srch.SA.p, st.SB.p, st.SC.p,
                 st.SE.p, st.SF.p, spf, p.f.axyz_ext.p, p.f.axyz.p, p.f.duint.p, C_cour, C_force, st.vsig.p, st.cfl_dt.p,
                 red.p + 4);
+        }
+        if (piped && corrector_iter_cnt == 0) { // the accelerations are final before the corrector uses them
+            static const char *const acc[] = {"axyz", "duint"};
+            pipe_download(acc, 2);
         }
         timer.mark(s(), "corrector");
         step_sc.ensure(16);
@@ -1148,11 +1160,18 @@ void Model::evolve_once() {
     } while (need_rerun_corrector);
     corrector_iter = corrector_iter_cnt;
     if (piped) {
-        static const char *const tail[] = {"vxyz", "uint", "axyz", "duint", "soundspeed",
-                                           "divv", "curlv", "dtdivv", "alpha_AV"};
-        // the CD10 fields left during the force loop; a repeated corrector pass recomputed them (send them
-        // again), a configuration without them still returns the (untouched) arrays: every field comes back
-        pipe_download(tail, (corrector_iter_cnt > 1 || !has_alpha) ? 9 : 5);
+        // what left early is final unless the corrector pass was repeated (then it was recomputed: send it again);
+        // a configuration without the CD10 fields still returns the (untouched) arrays: every field comes back
+        static const char *const tail[] = {"vxyz", "uint", "soundspeed"};
+        pipe_download(tail, 3);
+        if (corrector_iter_cnt > 1) {
+            static const char *const again[] = {"axyz", "duint"};
+            pipe_download(again, 2);
+        }
+        if (corrector_iter_cnt > 1 || !has_alpha) {
+            static const char *const cd10[] = {"divv", "curlv", "dtdivv", "alpha_AV"};
+            pipe_download(cd10, 4);
+        }
     }
     timer.end_step(s());
     SB_CUDA_CHECK(cudaStreamSynchronize(s()));

@@ -241,6 +241,7 @@ void Model::migrate_patch(u32 ip, int new_owner) {
                 comm_recv(*this, r.buf->p, bytes, old_owner);
         }
         comm_group_end(*this);
+        comm_wait(*this);
         SB_CUDA_CHECK(cudaStreamSynchronize(s()));
     }
     if (rank == new_owner)

@@ -531,6 +531,7 @@ void Model::reattribute_patch_objects() {
         }
     }
     comm_group_end(*this);
+    comm_wait(*this);
     SB_CUDA_CHECK(cudaStreamSynchronize(s()));
 }
 
@@ -669,29 +670,38 @@ void Model::build_ghost_cache() {
 
 /// BasicSPHGhostHandler::build_comm_merge_positions (BasicSPHGhosts.hpp:294-321,476-514)
 void Model::merge_position_ghost() {
-    for (auto &p : patches) {
-        if (!is_local(p) || !p.f.n)
-            continue;
-        PatchStep &st = p.st;
-        st.A.ensure(st.m, 1.1);
-        pack_xyzh(s(), st.n, p.f.xyz.p, p.f.hpart.p, st.A.p);
-    }
+    for (auto &p : patches)
+        if (is_local(p) && p.f.n)
+            p.st.A.ensure(p.st.m, 1.1);
+    // the ghosts that leave this rank first: gather into the staging, hand the messages to the communication
+    // stream, and build the local part of the merged positions while they travel
     send_stage.ensure(send_total, 1.1);
+    for (auto &itf : ifaces) {
+        PatchD &R = patches[itf.receiver];
+        PatchD &S = patches[itf.sender];
+        if (is_local(S) && !is_local(R)) // C1: positions + h of the ghosts, 32 B each, straight from the gather
+            ghost_xyzh(s(), itf.count, itf.ids, S.f.xyz.p, S.f.hpart.p, itf.offset, send_stage.p + itf.stage_off);
+    }
     comm_group_start(*this);
     for (auto &itf : ifaces) {
         PatchD &R = patches[itf.receiver];
         PatchD &S = patches[itf.sender];
-        if (is_local(R) && is_local(S)) {
-            ghost_xyzh(s(), itf.count, itf.ids, S.f.xyz.p, S.f.hpart.p, itf.offset, R.st.A.p + R.st.n + itf.dst_off);
-        } else if (is_local(S)) { // C1: positions + h of the ghosts, 32 B each, straight from the gather
-            Pack4 *stg = send_stage.p + itf.stage_off;
-            ghost_xyzh(s(), itf.count, itf.ids, S.f.xyz.p, S.f.hpart.p, itf.offset, stg);
-            comm_send(*this, stg, size_t(itf.count) * sizeof(Pack4), R.owner);
-        } else if (is_local(R)) {
+        if (is_local(S) && !is_local(R))
+            comm_send(*this, send_stage.p + itf.stage_off, size_t(itf.count) * sizeof(Pack4), R.owner);
+        else if (is_local(R) && !is_local(S))
             comm_recv(*this, R.st.A.p + R.st.n + itf.dst_off, size_t(itf.count) * sizeof(Pack4), S.owner);
-        }
     }
     comm_group_end(*this);
+    for (auto &p : patches)
+        if (is_local(p) && p.f.n)
+            pack_xyzh(s(), p.st.n, p.f.xyz.p, p.f.hpart.p, p.st.A.p);
+    for (auto &itf : ifaces) {
+        PatchD &R = patches[itf.receiver];
+        PatchD &S = patches[itf.sender];
+        if (is_local(R) && is_local(S))
+            ghost_xyzh(s(), itf.count, itf.ids, S.f.xyz.p, S.f.hpart.p, itf.offset, R.st.A.p + R.st.n + itf.dst_off);
+    }
+    comm_wait(*this);
     if (cfg.keep_step_data)
         for (auto &p : patches)
             if (is_local(p) && p.f.n) {
@@ -855,43 +865,60 @@ void Model::communicate_merge_ghosts_fields() {
         st.SC.ensure(st.m, 1.1);
         if (has_a)
             st.SD.ensure(st.m, 1.1);
-        pack_fields(
-            s(), st.n, nullptr, p.f.hpart.p, p.f.vxyz.p, p.f.uint_.p, st.omega.p, has_a ? p.f.axyz.p : nullptr,
-            st.srch.SA.p, st.SB.p, st.SC.p, st.SD.p, st.srch.inv_map.p);
     }
     // C2: the ghost fields.  Remote interfaces are staged as [A | B | C | (D)] blocks of Pack4 (one NCCL
-    // message per interface) and scattered into the receiver's sorted records on arrival.
+    // message per interface) and scattered into the receiver's sorted records on arrival.  The messages are
+    // staged and handed to the communication stream first; the records of the local objects and of the local
+    // interfaces are packed while they travel.
     const size_t nblk = has_a ? 4 : 3;
     send_stage.ensure(send_total * nblk, 1.1);
-    comm_group_start(*this);
     for (auto &itf : ifaces) {
         PatchD &R = patches[itf.receiver];
         PatchD &S = patches[itf.sender];
-        const size_t bytes = size_t(itf.count) * sizeof(Pack4);
-        if (is_local(R) && is_local(S)) {
-            u32 o = R.st.n + itf.dst_off;
-            pack_fields(
-                s(), itf.count, itf.ids, S.f.hpart.p, S.f.vxyz.p, S.f.uint_.p, S.st.omega.p,
-                has_a ? S.f.axyz.p : nullptr, R.st.srch.SA.p, R.st.SB.p, R.st.SC.p, has_a ? R.st.SD.p : nullptr,
-                R.st.srch.inv_map.p + o);
-        } else if (is_local(S)) {
+        if (is_local(S) && !is_local(R)) {
             Pack4 *sA = send_stage.p + itf.stage_off * nblk;
             Pack4 *sB = sA + itf.count, *sC = sB + itf.count, *sD = has_a ? sC + itf.count : nullptr;
             ghost_xyzh(s(), itf.count, itf.ids, S.f.xyz.p, S.f.hpart.p, itf.offset, sA);
             pack_fields(
                 s(), itf.count, itf.ids, S.f.hpart.p, S.f.vxyz.p, S.f.uint_.p, S.st.omega.p,
                 has_a ? S.f.axyz.p : nullptr, sA, sB, sC, sD);
-            comm_send(*this, sA, bytes * nblk, R.owner);
-        } else if (is_local(R)) {
+        } else if (is_local(R) && !is_local(S)) {
             recv_plan.push_back({&itf, recv_total});
             recv_total += size_t(itf.count) * nblk;
         }
     }
     recv_stage.ensure(recv_total, 1.1);
+    comm_group_start(*this);
+    for (auto &itf : ifaces) {
+        PatchD &R = patches[itf.receiver];
+        PatchD &S = patches[itf.sender];
+        if (is_local(S) && !is_local(R))
+            comm_send(*this, send_stage.p + itf.stage_off * nblk, size_t(itf.count) * nblk * sizeof(Pack4), R.owner);
+    }
     for (auto &rp : recv_plan)
         comm_recv(*this, recv_stage.p + rp.second, size_t(rp.first->count) * nblk * sizeof(Pack4),
                   patches[rp.first->sender].owner);
     comm_group_end(*this);
+    for (auto &p : patches) {
+        if (!is_local(p) || !p.f.n)
+            continue;
+        PatchStep &st = p.st;
+        pack_fields(
+            s(), st.n, nullptr, p.f.hpart.p, p.f.vxyz.p, p.f.uint_.p, st.omega.p, has_a ? p.f.axyz.p : nullptr,
+            st.srch.SA.p, st.SB.p, st.SC.p, st.SD.p, st.srch.inv_map.p);
+    }
+    for (auto &itf : ifaces) {
+        PatchD &R = patches[itf.receiver];
+        PatchD &S = patches[itf.sender];
+        if (is_local(R) && is_local(S)) {
+            u32 o = R.st.n + itf.dst_off;
+            pack_fields(
+                s(), itf.count, itf.ids, S.f.hpart.p, S.f.vxyz.p, S.f.uint_.p, S.st.omega.p,
+                has_a ? S.f.axyz.p : nullptr, R.st.srch.SA.p, R.st.SB.p, R.st.SC.p, has_a ? R.st.SD.p : nullptr,
+                R.st.srch.inv_map.p + o);
+        }
+    }
+    comm_wait(*this);
     for (auto &rp : recv_plan) {
         const Iface &itf = *rp.first;
         PatchD &R        = patches[itf.receiver];
@@ -907,11 +934,8 @@ void Model::communicate_merge_ghosts_fields() {
 /// alpha_AV ghost exchange (Solver.cpp:2325-2368).  with_omega (fast fp mode): Ω of every merged object is
 /// produced by the operator pass that precedes this exchange (av_operators) and rides along — 16 B per ghost.
 void Model::exchange_alpha_ghosts(bool with_omega) {
-    for (auto &p : patches)
-        if (is_local(p) && p.f.n)
-            pack_alpha(s(), p.st.n, nullptr, p.st.alpha_updated.p, p.st.SC.p, p.st.srch.inv_map.p,
-                       with_omega ? p.st.omega.p : nullptr);
-    // C3: 8 (16) B per ghost; remote interfaces go through compact f64 staging on both sides
+    // C3: 8 (16) B per ghost; remote interfaces go through compact f64 staging on both sides; the local part is
+    // packed while the messages travel
     size_t recv_total = 0;
     for (auto &itf : ifaces)
         if (is_local(patches[itf.receiver]) && !is_local(patches[itf.sender]))
@@ -919,26 +943,41 @@ void Model::exchange_alpha_ghosts(bool with_omega) {
     const size_t nv = with_omega ? 2 : 1; // staging: [alpha of the interface | omega of the interface]
     send_stage_f.ensure(send_total * nv, 1.1);
     recv_stage_f.ensure(recv_total * nv, 1.1);
+    for (auto &itf : ifaces) {
+        PatchD &R = patches[itf.receiver];
+        PatchD &S = patches[itf.sender];
+        if (is_local(S) && !is_local(R)) {
+            f64 *stg = send_stage_f.p + itf.stage_off * nv;
+            gather_field(s(), itf.count, 1, itf.ids, S.st.alpha_updated.p, stg);
+            if (with_omega)
+                gather_field(s(), itf.count, 1, itf.ids, S.st.omega.p, stg + itf.count);
+        }
+    }
     size_t roff = 0;
     comm_group_start(*this);
     for (auto &itf : ifaces) {
         PatchD &R = patches[itf.receiver];
         PatchD &S = patches[itf.sender];
-        if (is_local(R) && is_local(S)) {
-            pack_alpha(s(), itf.count, itf.ids, S.st.alpha_updated.p, R.st.SC.p, R.st.srch.inv_map.p + R.st.n + itf.dst_off,
-                       with_omega ? S.st.omega.p : nullptr);
-        } else if (is_local(S)) {
-            f64 *stg = send_stage_f.p + itf.stage_off * nv;
-            gather_field(s(), itf.count, 1, itf.ids, S.st.alpha_updated.p, stg);
-            if (with_omega)
-                gather_field(s(), itf.count, 1, itf.ids, S.st.omega.p, stg + itf.count);
-            comm_send(*this, stg, size_t(itf.count) * nv * sizeof(f64), R.owner);
-        } else if (is_local(R)) {
+        if (is_local(S) && !is_local(R)) {
+            comm_send(*this, send_stage_f.p + itf.stage_off * nv, size_t(itf.count) * nv * sizeof(f64), R.owner);
+        } else if (is_local(R) && !is_local(S)) {
             comm_recv(*this, recv_stage_f.p + roff, size_t(itf.count) * nv * sizeof(f64), S.owner);
             roff += size_t(itf.count) * nv;
         }
     }
     comm_group_end(*this);
+    for (auto &p : patches)
+        if (is_local(p) && p.f.n)
+            pack_alpha(s(), p.st.n, nullptr, p.st.alpha_updated.p, p.st.SC.p, p.st.srch.inv_map.p,
+                       with_omega ? p.st.omega.p : nullptr);
+    for (auto &itf : ifaces) {
+        PatchD &R = patches[itf.receiver];
+        PatchD &S = patches[itf.sender];
+        if (is_local(R) && is_local(S))
+            pack_alpha(s(), itf.count, itf.ids, S.st.alpha_updated.p, R.st.SC.p, R.st.srch.inv_map.p + R.st.n + itf.dst_off,
+                       with_omega ? S.st.omega.p : nullptr);
+    }
+    comm_wait(*this);
     roff = 0;
     for (auto &itf : ifaces) {
         PatchD &R = patches[itf.receiver];

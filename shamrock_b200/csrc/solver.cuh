@@ -97,6 +97,8 @@ struct Model {
     std::vector<PatchD> patches;
     int rank = 0, world = 1;
     void *nccl_comm = nullptr;
+    cudaStream_t comm_s = nullptr; ///< stream of the ncclSend / ncclRecv groups (solver_comm.cu)
+    cudaEvent_t ev_comm_begin = nullptr, ev_comm_done = nullptr;
     f64 time = 0, dt = 0, cfl_multiplier = 1e-2; // Solver.hpp:131-147
     // log of the last step
     f64 eps_v = 0, t_step = 0;
@@ -223,6 +225,7 @@ void comm_allreduce_host_f64(Model &m, f64 *vals, size_t n, int op);
 void comm_allreduce_host_u64(Model &m, u64 *vals, size_t n, int op);
 void comm_group_start(Model &m);
 void comm_group_end(Model &m);
+void comm_wait(Model &m);
 void comm_send(Model &m, const void *d, size_t bytes, int peer);
 void comm_recv(Model &m, void *d, size_t bytes, int peer);
 void comm_destroy(Model &m);

@@ -107,6 +107,13 @@ void comm_init(Model &m, int rank, int world, const void *id128) {
     ncclComm_t c = nullptr;
     SB_NCCL_CHECK(nccl().CommInitRank(&c, world, id, rank));
     m.nccl_comm = c;
+    // point-to-point exchanges run on their own stream, tied to the compute stream by two events: the work that does
+    // not need the arriving data is queued between comm_group_end and comm_wait and overlaps the transfer
+    if (!m.comm_s) {
+        SB_CUDA_CHECK(cudaStreamCreateWithFlags(&m.comm_s, cudaStreamNonBlocking));
+        SB_CUDA_CHECK(cudaEventCreateWithFlags(&m.ev_comm_begin, cudaEventDisableTiming));
+        SB_CUDA_CHECK(cudaEventCreateWithFlags(&m.ev_comm_done, cudaEventDisableTiming));
+    }
 }
 
 void comm_allreduce_f64(Model &m, f64 *d_buf, size_t n, int op) {
@@ -145,28 +152,47 @@ void comm_allreduce_host_f64(Model &m, f64 *vals, size_t n, int op) {
     SB_CUDA_CHECK(cudaStreamSynchronize(m.s()));
     std::memcpy(vals, m.comm_host.p, n * sizeof(f64));
 }
+/// what the compute stream has queued so far (the staging of the outgoing messages) precedes the group
 void comm_group_start(Model &m) {
-    if (m.world > 1)
+    if (m.world > 1) {
+        SB_CUDA_CHECK(cudaEventRecord(m.ev_comm_begin, m.s()));
+        SB_CUDA_CHECK(cudaStreamWaitEvent(m.comm_s, m.ev_comm_begin, 0));
         SB_NCCL_CHECK(nccl().GroupStart());
+    }
 }
+/// the group is in flight on the communication stream; the compute stream goes on until comm_wait
 void comm_group_end(Model &m) {
-    if (m.world > 1)
+    if (m.world > 1) {
         SB_NCCL_CHECK(nccl().GroupEnd());
+        SB_CUDA_CHECK(cudaEventRecord(m.ev_comm_done, m.comm_s));
+    }
+}
+/// the compute stream waits for the last group (arrived data may be read, sent buffers reused)
+void comm_wait(Model &m) {
+    if (m.world > 1)
+        SB_CUDA_CHECK(cudaStreamWaitEvent(m.s(), m.ev_comm_done, 0));
 }
 void comm_send(Model &m, const void *d, size_t bytes, int peer) {
     if (!bytes)
         return;
-    SB_NCCL_CHECK(nccl().Send(d, bytes, ncclUint8_, peer, (ncclComm_t) m.nccl_comm, m.s()));
+    SB_NCCL_CHECK(nccl().Send(d, bytes, ncclUint8_, peer, (ncclComm_t) m.nccl_comm, m.comm_s));
 }
 void comm_recv(Model &m, void *d, size_t bytes, int peer) {
     if (!bytes)
         return;
-    SB_NCCL_CHECK(nccl().Recv(d, bytes, ncclUint8_, peer, (ncclComm_t) m.nccl_comm, m.s()));
+    SB_NCCL_CHECK(nccl().Recv(d, bytes, ncclUint8_, peer, (ncclComm_t) m.nccl_comm, m.comm_s));
 }
 void comm_destroy(Model &m) {
     if (m.nccl_comm) {
         nccl().CommDestroy((ncclComm_t) m.nccl_comm);
         m.nccl_comm = nullptr;
+    }
+    if (m.comm_s) {
+        cudaStreamSynchronize(m.comm_s);
+        cudaEventDestroy(m.ev_comm_begin);
+        cudaEventDestroy(m.ev_comm_done);
+        cudaStreamDestroy(m.comm_s);
+        m.comm_s = nullptr;
     }
 }
 

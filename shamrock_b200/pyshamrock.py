@@ -620,6 +620,27 @@ class Model:
                 break
         return n
 
+    # -- checkpoint / restart (Model::dump / Model::load_from_dump, Model.hpp:906-995)
+    def dump(self, fname):
+        if getattr(self, "_dirty", True) or self._dev is None:
+            self._push()
+        self._dev.dump(fname)
+
+    def load_from_dump(self, fname):
+        """configuration, patches and state come from the dump; one patch list entry per patch of the dump"""
+        if self._dev is None:
+            if self._bmin is None:
+                self._bmin, self._bmax = (0.0, 0.0, 0.0), (1.0, 1.0, 1.0)
+            self._make_device_model()
+        self._dev.load_dump(fname)
+        if self._dev.patch_count != 1:
+            raise RuntimeError("this Python surface drives one patch; load multi-patch dumps through _capi.Model")
+        self._dirty, self._on_device, self._host_fresh = False, True, False
+        self._pull()
+
+    def get_total_part_count_device(self):
+        return self._dev.total_part_count() if self._dev else len(self._host["xyz"])
+
     def solver_logs_last_rate(self):
         return self._last.get("rate", 0.0)
 

@@ -521,7 +521,10 @@ def main():
                "d2h_GBps_over_step": float(tot[1].item()) / (ms2 / k2 * 1e-3) / 1e9,
                "api": "shamb200_model_evolve_once_host (pinned host patch data; copies on two copy streams, "
                       "overlapped with the kernels)",
-               "fields_up": IN, "fields_down": OUT}
+               "fields_up": IN, "fields_down": OUT,
+               # id ranges the operator / force / corrector passes of the host step are cut into (finished ranges
+               # travel while the next is computed; needs Morton-ordered patch data: ParticleReordering)
+               "id_ranges": m.host_step_info(ips[0])[0] if ips else 0}
 
     if rank == 0:
         hbm_peak, peak_src = peaks()

@@ -430,6 +430,12 @@ int shamb200_host_unregister(void *p);
 int shamb200_model_search_stats(shamb200_model *m, uint64_t out[2]);
 /* bytes moved by the last shamb200_model_evolve_once_host: out[0] host->device, out[1] device->host */
 int shamb200_model_host_traffic(shamb200_model *m, uint64_t out[2]);
+/* how the last shamb200_model_evolve_once_host ran: out[0] = number of id ranges its operator / force / corrector
+ * passes were cut into so that finished ranges travel to the host while the next is computed (0: one launch per
+ * pass), out[1] = objects of the patch whose successor by id lay farther away than 8 h — above 1 % of the patch the
+ * ranges are not used: consecutive ids must be neighbours in space (shamb200_model_reorder_particles,
+ * ParticleReordering.hpp:38-120, makes them so) */
+int shamb200_model_host_step_info(shamb200_model *m, uint32_t ip, uint64_t out[2]);
 /* state: {time, next dt, cfl_multiplier, eps_v, h_subcycles, h_iters_last, corrector_iter,
  *         npart(global), t_step seconds (host wall), rate(part/s, this rank), K (local neighbour count)} */
 int shamb200_model_state(shamb200_model *m, double out[12]);

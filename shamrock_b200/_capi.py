@@ -89,6 +89,7 @@ SYMBOLS = [
     "shamb200_model_set_field", "shamb200_model_reorder_particles", "shamb200_model_evolve_once",
     "shamb200_model_evolve_once_host",
     "shamb200_host_register", "shamb200_host_unregister", "shamb200_model_host_traffic",
+    "shamb200_model_host_step_info",
     "shamb200_model_search_stats", "shamb200_model_state", "shamb200_model_conservation",
     "shamb200_model_add_lattice_hcp", "shamb200_model_add_disc_lattice", "shamb200_model_add_disc_mc", "shamb200_model_set_value_in_a_box",
     "shamb200_model_set_value_in_sphere", "shamb200_model_add_kernel_value", "shamb200_model_get_sum",
@@ -556,6 +557,12 @@ class Model:
     def host_traffic(self):
         o = (C.c_uint64 * 2)()
         check(lib().shamb200_model_host_traffic(self.h, o))
+        return int(o[0]), int(o[1])
+
+    def host_step_info(self, ip=0):
+        """(id ranges the last host step was cut into, objects stored far from their Morton position)"""
+        o = (C.c_uint64 * 2)()
+        check(lib().shamb200_model_host_step_info(self.h, C.c_uint32(ip), o))
         return int(o[0]), int(o[1])
 
     def state(self):

@@ -702,6 +702,14 @@ int shamb200_model_host_traffic(shamb200_model *m, uint64_t out[2]) {
         out[1] = m->m.pipe.bytes_d2h;
     });
 }
+int shamb200_model_host_step_info(shamb200_model *m, uint32_t ip, uint64_t out[2]) {
+    return guard([&] {
+        need_live(m);
+        out[0] = m->m.pipe.nslices;
+        (void) m->m.patches.at(ip);
+        out[1] = m->m.pipe.far_host.p ? m->m.pipe.far_host.p[0] : 0;
+    });
+}
 int shamb200_model_state(shamb200_model *m, double out[12]) {
     return guard([&] {
         need_live(m);

@@ -49,6 +49,14 @@ inline unsigned grid_for(u64 n, unsigned block) { return (unsigned) ((n + block 
 void pool_set_stream(cudaStream_t s); ///< stream the calling thread's allocations / frees are ordered on
 void *pool_alloc(size_t bytes);
 void pool_free(void *p);
+/// Few-word transfers on a compute stream that do not use a copy engine.  A small cudaMemcpyAsync shares the
+/// engines with the bulk copies of the host-resident step (Model::evolve_once_host keeps both directions busy for
+/// tens of ms) and waits behind them: 8 ms for 3 KB of ghost-zone boxes.  h2d_small passes the bytes as a kernel
+/// argument (2 KiB per launch; any host memory, reusable on return); d2h_small stores from a kernel into
+/// PAGE-LOCKED host memory (mapped into the device's address space: UVA), complete once the stream is
+/// synchronised.  bytes: a multiple of 4, both pointers 4-byte aligned.
+void h2d_small(cudaStream_t s, void *d_dst, const void *h_src, size_t bytes);
+void d2h_small(cudaStream_t s, void *h_pinned_dst, const void *d_src, size_t bytes);
 void pool_release_all();            ///< give every cached block back to the driver
 size_t pool_bytes_reserved();
 

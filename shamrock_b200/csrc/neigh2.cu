@@ -866,7 +866,7 @@ void search_build(
     unsigned long long *d_cursor  = reinterpret_cast<unsigned long long *>(sb.scalars.p + 4);
     unsigned long long *d_ecursor = reinterpret_cast<unsigned long long *>(sb.scalars.p + 6);
     auto read_back = [&]() {
-        SB_CUDA_CHECK(cudaMemcpyAsync(sb.h_scalars.p + 2, sb.scalars.p + 2, 5 * sizeof(u64), cudaMemcpyDeviceToHost, s));
+        d2h_small(s, sb.h_scalars.p + 2, sb.scalars.p + 2, 5 * sizeof(u64));
         SB_CUDA_CHECK(cudaStreamSynchronize(s));
         const u32 err = u32(sb.h_scalars.p[3] & 0xffffffffull);
         if (err & 1u)

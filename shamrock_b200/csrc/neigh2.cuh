@@ -49,16 +49,44 @@ struct SearchBuffers {
     DevBuf<u32> x_cnt, x_scanned, x_list;
 };
 
-/// rank-CSR view handed to the SPH loops
+/// rank-CSR view handed to the SPH loops.  A launch handles `count` real particles starting at `first`:
+/// slots [first, first + count) in Morton order (the default: neighbouring lanes share their neighbours), or —
+/// by_id — the objects with ids [first, first + count), whatever their slots: the host-resident step runs its
+/// loops over id ranges so that the outputs of a finished range (contiguous in the by-id fields) can travel to
+/// the host while the next range is computed (Model::evolve_once_host)
 struct RankCsr {
     const u32 *cnt, *off, *list; ///< by slot; entries are ranks
     const u32 *slot_rank;        ///< [N]
     const u32 *index_map;        ///< rank -> merged id
     u32 N;
+    u32 first, count;
+    bool by_id;
+    const u32 *inv_map;     ///< merged id -> rank
+    const u32 *real_prefix; ///< rank -> slot (real objects)
+    RankCsr ids(u32 id0, u32 n) const {
+        RankCsr c = *this;
+        c.first = id0, c.count = n, c.by_id = true;
+        return c;
+    }
 };
 inline RankCsr rank_csr_of(const SearchBuffers &sb, const TreeBuffers &tb) {
-    return RankCsr{sb.cnt_s.p, sb.off_s.p, sb.list_s.p, sb.slot_rank.p, tb.index_map.p, sb.N};
+    return RankCsr{sb.cnt_s.p, sb.off_s.p, sb.list_s.p, sb.slot_rank.p, tb.index_map.p, sb.N,
+                   0u,         sb.N,       false,       sb.inv_map.p,   sb.real_prefix.p};
 }
+#ifdef __CUDACC__
+/// work item k (< c.count) of a launch -> slot kk, rank r, id
+__device__ __forceinline__ void csr_item(const RankCsr &c, u32 k, u32 &kk, u32 &r, u32 &id) {
+    if (c.by_id) {
+        id = c.first + k;
+        r  = c.inv_map[id];
+        kk = c.real_prefix[r];
+    } else {
+        kk = c.first + k;
+        r  = c.slot_rank[kk];
+        id = c.index_map[r];
+    }
+}
+#endif
 
 /// SA[r] = A[index_map[r]], inv_map, real flags / slots.  A: merged (x,y,z,h) by id, N real objects first.
 void search_prepare_sorted(cudaStream_t s, const TreeBuffers &tb, SearchBuffers &sb, const Pack4 *A, u32 N);

@@ -4,7 +4,10 @@
 // carries an event the new stream waits for, so two contexts / models on one device never share a block
 // that queued work of the other still uses.
 #include "common.cuh"
+#include <algorithm>
+#include <cstring>
 #include <map>
+#include <stdexcept>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
@@ -140,5 +143,53 @@ void pool_release_all() {
 }
 
 size_t pool_bytes_reserved() { return pool().reserved; }
+
+// ---- small transfers without a copy engine (common.cuh) ---------------------------------------------------
+namespace {
+struct SmallBlob {
+    u32 w[512];
+};
+__global__ void h2d_small_kernel(u32 *__restrict__ dst, const SmallBlob b, u32 nw) {
+    for (u32 i = threadIdx.x; i < nw; i += blockDim.x)
+        dst[i] = b.w[i];
+}
+__global__ void d2h_small_kernel(u32 *__restrict__ dst, const u32 *__restrict__ src, u32 nw) {
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+} // namespace
+void h2d_small(cudaStream_t s, void *d_dst, const void *h_src, size_t bytes) {
+    if (bytes % 4 || (reinterpret_cast<uintptr_t>(d_dst) % 4) || (reinterpret_cast<uintptr_t>(h_src) % 4))
+        throw std::invalid_argument("h2d_small: 4-byte words only");
+    if (bytes > 64 * sizeof(SmallBlob)) { // not small: the copy engine after all
+        SB_CUDA_CHECK(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, s));
+        return;
+    }
+    const u32 *src = static_cast<const u32 *>(h_src);
+    u32 *dst       = static_cast<u32 *>(d_dst);
+    for (size_t w0 = 0, nw = bytes / 4; w0 < nw; w0 += 512) {
+        SmallBlob b;
+        const u32 n = u32(std::min<size_t>(512, nw - w0));
+        std::memcpy(b.w, src + w0, size_t(n) * 4);
+        h2d_small_kernel<<<1, 128, 0, s>>>(dst + w0, b, n);
+        SB_COUNT_LAUNCH();
+    }
+    SB_LAUNCH_CHECK();
+}
+void d2h_small(cudaStream_t s, void *h_pinned_dst, const void *d_src, size_t bytes) {
+    if (bytes % 4 || (reinterpret_cast<uintptr_t>(h_pinned_dst) % 4) || (reinterpret_cast<uintptr_t>(d_src) % 4))
+        throw std::invalid_argument("d2h_small: 4-byte words only");
+    if (!bytes)
+        return;
+    if (bytes > (1u << 20)) {
+        SB_CUDA_CHECK(cudaMemcpyAsync(h_pinned_dst, d_src, bytes, cudaMemcpyDeviceToHost, s));
+        return;
+    }
+    const u32 nw = u32(bytes / 4);
+    d2h_small_kernel<<<std::min<u32>(64u, (nw + 255) / 256), 256, 0, s>>>(
+        static_cast<u32 *>(h_pinned_dst), static_cast<const u32 *>(d_src), nw);
+    SB_COUNT_LAUNCH();
+    SB_LAUNCH_CHECK();
+}
 
 } // namespace sb

@@ -98,7 +98,7 @@ void Model::reset_red() {
     SB_COUNT_LAUNCH();
 }
 void Model::read_red(int n) {
-    SB_CUDA_CHECK(cudaMemcpyAsync(h_red.p, red.p, size_t(n) * sizeof(u64), cudaMemcpyDeviceToHost, s()));
+    d2h_small(s(), h_red.p, red.p, size_t(n) * sizeof(u64));
     SB_CUDA_CHECK(cudaStreamSynchronize(s()));
 }
 static f64 bits_to_f64(u64 b) {
@@ -150,7 +150,7 @@ void Model::set_box(const f64 bmin[3], const f64 bmax[3], u32 nx, u32 ny, u32 nz
             hb[6 * k + 3 + d] = patches[k].hi[d];
         }
     d_boxes.ensure(hb.size());
-    SB_CUDA_CHECK(cudaMemcpyAsync(d_boxes.p, hb.data(), hb.size() * sizeof(f64), cudaMemcpyHostToDevice, s()));
+    h2d_small(s(), d_boxes.p, hb.data(), hb.size() * sizeof(f64));
     SB_CUDA_CHECK(cudaStreamSynchronize(s()));
 }
 
@@ -305,7 +305,7 @@ void Model::keep_flagged(PatchD &p, u32 *out_kept) {
     u32 n = p.f.n;
     pos.ensure(n);
     exclusive_scan<u8>(s(), flag.p, pos.p, n, scan_tmp, red.p + 5);
-    SB_CUDA_CHECK(cudaMemcpyAsync(h_red.p + 5, red.p + 5, sizeof(u64), cudaMemcpyDeviceToHost, s()));
+    d2h_small(s(), h_red.p + 5, red.p + 5, sizeof(u64));
     SB_CUDA_CHECK(cudaStreamSynchronize(s()));
     u32 kept = u32(h_red.p[5]);
     if (out_kept)
@@ -434,9 +434,11 @@ void Model::reattribute_patch_objects() {
         SB_COUNT_LAUNCH();
     }
     {
-        std::vector<u32> hc(loc.size() * (np + 1) + 1);
-        SB_CUDA_CHECK(cudaMemcpyAsync(hc.data(), box_counts.p, hc.size() * sizeof(u32), cudaMemcpyDeviceToHost, s()));
+        const size_t nhc = loc.size() * (np + 1) + 1;
+        h_counts.ensure(nhc);
+        d2h_small(s(), h_counts.p, box_counts.p, nhc * sizeof(u32));
         SB_CUDA_CHECK(cudaStreamSynchronize(s()));
+        std::vector<u32> hc(h_counts.p, h_counts.p + nhc);
         for (size_t q = 0; q < loc.size(); q++) {
             const size_t k = loc[q];
             const u32 *h   = hc.data() + q * (np + 1);
@@ -591,7 +593,7 @@ void Model::build_ghost_cache() {
                 hb[6 * j + 3 + d] = cand[mine[sd][j]].cut_hi[d];
             }
         field_tmp.ensure(hb.size());
-        SB_CUDA_CHECK(cudaMemcpyAsync(field_tmp.p, hb.data(), hb.size() * sizeof(f64), cudaMemcpyHostToDevice, s()));
+        h2d_small(s(), field_tmp.p, hb.data(), hb.size() * sizeof(f64));
         S.st.gmask.ensure(size_t(n) * nch, 1.1);
         S.st.gblock.ensure(size_t(nblocks) * 64 * nch, 1.1);
         S.st.gtotals.ensure(64 * nch);
@@ -601,9 +603,10 @@ void Model::build_ghost_cache() {
                 s(), n, S.f.xyz.p, nbox, field_tmp.p + ch * 64 * 6, S.st.gmask.p + ch * n,
                 S.st.gblock.p + ch * 64 * size_t(nblocks), S.st.gtotals.p + ch * 64);
         }
-        std::vector<u32> hc(64 * nch);
-        SB_CUDA_CHECK(cudaMemcpyAsync(hc.data(), S.st.gtotals.p, hc.size() * sizeof(u32), cudaMemcpyDeviceToHost, s()));
+        h_counts.ensure(64 * nch);
+        d2h_small(s(), h_counts.p, S.st.gtotals.p, 64 * nch * sizeof(u32));
         SB_CUDA_CHECK(cudaStreamSynchronize(s()));
+        const u32 *hc = h_counts.p;
         for (size_t j = 0; j < mine[sd].size(); j++)
             counts[mine[sd][j]] = hc[j];
     }
@@ -624,7 +627,7 @@ void Model::build_ghost_cache() {
         }
         S.st.ids_pool.ensure(run, 1.1);
         S.st.gbase.ensure(base.size());
-        SB_CUDA_CHECK(cudaMemcpyAsync(S.st.gbase.p, base.data(), base.size() * sizeof(u64), cudaMemcpyHostToDevice, s()));
+        h2d_small(s(), S.st.gbase.p, base.data(), base.size() * sizeof(u64));
         for (size_t ch = 0; ch < nch; ch++) {
             u32 nbox = u32(std::min<size_t>(64, mine[sd].size() - ch * 64));
             ghost_select_scatter(
@@ -1036,6 +1039,13 @@ void Model::evolve_once() {
         reorder_particles();
     }
 
+    if (piped) { // are consecutive ids neighbours in space?  (pipe_slices; the search synchronises before it is read)
+        const PatchD &p = patches[pipe.ip];
+        pipe.far_dev.ensure(1);
+        pipe.far_host.ensure(1);
+        count_far_successors(s(), p.f.n, p.f.xyz.p, p.f.hpart.p, pipe.far_dev.p);
+        d2h_small(s(), pipe.far_host.p, pipe.far_dev.p, sizeof(u64));
+    }
     if (piped) { // positions (and the external acceleration) are final once the boundary has been applied: they
         static const char *const first[] = {"xyz", "axyz_ext"}; // go back while the tree and the cache are built
         pipe_download(first, 2);
@@ -1070,21 +1080,35 @@ void Model::evolve_once() {
                     p.st.alpha_updated.p, p.f.alpha_AV.p, size_t(p.st.n) * sizeof(f64), cudaMemcpyDeviceToDevice, s()));
             }
         timer.mark(s(), "divv_curlv_dtdivv");
+        // host-resident step: the two heavy loops (and the corrector behind the force loop) run over id ranges,
+        // the outputs of a finished range travel to the host while the next one is computed (pipe_slices)
+        const std::vector<std::pair<u32, u32>> slices =
+            piped && corrector_iter_cnt == 0 ? pipe_slices() : std::vector<std::pair<u32, u32>>{};
+        const bool sliced = slices.size() > 1;
+        static const char *const ops_out[] = {"divv", "curlv", "dtdivv"};
         if (has_alpha)
             for (auto &p : patches) {
                 if (!is_local(p) || !p.f.n)
                     continue;
                 PatchStep &st = p.st;
                 st.omega.ensure(st.n);
-                av_operators(
-                    s(), cfg.fp_mode, cfg.kernel, rank_csr_of(st.srch, st.tree), st.srch.SA.p, st.SB.p, st.SC.p, st.SD.p,
-                    cfg.gpart_mass, has_curl, has_dtdivv, cfg.combined_dtdiv_divcurlv_compute != 0, p.f.divv.p,
-                    p.f.curlv.p, p.f.dtdivv.p, omega_in_av_pass() ? st.omega.p : nullptr);
+                auto run = [&](const RankCsr &c) {
+                    av_operators(
+                        s(), cfg.fp_mode, cfg.kernel, c, st.srch.SA.p, st.SB.p, st.SC.p, st.SD.p, cfg.gpart_mass,
+                        has_curl, has_dtdivv, cfg.combined_dtdiv_divcurlv_compute != 0, p.f.divv.p, p.f.curlv.p,
+                        p.f.dtdivv.p, omega_in_av_pass() ? st.omega.p : nullptr);
+                };
+                const RankCsr csr = rank_csr_of(st.srch, st.tree);
+                if (sliced) // (one local patch: pipe.early_out)
+                    for (auto &sl : slices) {
+                        run(csr.ids(sl.first, sl.second));
+                        pipe_download(ops_out, 3, sl.first, sl.second);
+                    }
+                else
+                    run(csr);
             }
-        if (piped && corrector_iter_cnt == 0 && has_alpha) { // out of the operator pass: back during the EOS / forces
-            static const char *const ops[] = {"divv", "curlv", "dtdivv"};
-            pipe_download(ops, 3);
-        }
+        if (piped && corrector_iter_cnt == 0 && has_alpha && !sliced) // back during the EOS / forces
+            pipe_download(ops_out, 3);
         timer.mark(s(), "av_eos");
         if (has_alpha) {
             for (auto &p : patches)
@@ -1125,6 +1149,9 @@ void Model::evolve_once() {
         const f64 C_cour  = cfg.cfl_cour * cfl_multiplier;
         const f64 C_force = cfg.cfl_force * cfl_multiplier;
         reset_red();
+        step_sc.ensure(16);
+        h_step_sc.ensure(16);
+        SB_CUDA_CHECK(cudaMemsetAsync(step_sc.p, 0, 16 * sizeof(f64), s()));
         for (auto &p : patches) {
             if (!is_local(p) || !p.f.n)
                 continue;
@@ -1140,31 +1167,45 @@ void Model::evolve_once() {
                 spf.adiabatic_gm1 = cfg.gamma - 1;
                 spf.SG            = st.SG.p;
             }
-            force_cfl(
-                s(), cfg.fp_mode, cfg.kernel, cfg.av, rank_csr_of(st.srch, st.tree), st.srch.SA.p, st.SB.p, st.SC.p,
-                st.SE.p, st.SF.p, spf, p.f.axyz_ext.p, p.f.axyz.p, p.f.duint.p, C_cour, C_force, st.vsig.p, st.cfl_dt.p,
-                red.p + 4);
+            auto run = [&](const RankCsr &c) {
+                force_cfl(
+                    s(), cfg.fp_mode, cfg.kernel, cfg.av, c, st.srch.SA.p, st.SB.p, st.SC.p, st.SE.p, st.SF.p, spf,
+                    p.f.axyz_ext.p, p.f.axyz.p, p.f.duint.p, C_cour, C_force, st.vsig.p, st.cfl_dt.p, red.p + 4);
+            };
+            const RankCsr csr = rank_csr_of(st.srch, st.tree);
+            if (sliced) { // forces, then the corrector of the same id range, then its four fields go home
+                static const char *const done[] = {"axyz", "duint", "vxyz", "uint"};
+                for (auto &sl : slices) {
+                    const u32 i0 = sl.first, n = sl.second;
+                    run(csr.ids(i0, n));
+                    leapfrog_corrector(
+                        s(), n, dt_ / 2, p.f.vxyz.p + 3 * size_t(i0), p.f.axyz.p + 3 * size_t(i0),
+                        st.a_old.p + 3 * size_t(i0), p.f.uint_.p + i0, p.f.duint.p + i0, st.du_old.p + i0, red.p + 2,
+                        reinterpret_cast<f64 *>(red.p + 3), step_sc.p + 1);
+                    pipe_download(done, 4, i0, n);
+                }
+            } else {
+                run(csr);
+            }
         }
-        if (piped && corrector_iter_cnt == 0) { // the accelerations are final before the corrector uses them
+        if (piped && corrector_iter_cnt == 0 && !sliced) { // the accelerations are final before the corrector uses them
             static const char *const acc[] = {"axyz", "duint"};
             pipe_download(acc, 2);
         }
         timer.mark(s(), "corrector");
-        step_sc.ensure(16);
-        h_step_sc.ensure(16);
-        SB_CUDA_CHECK(cudaMemsetAsync(step_sc.p, 0, 16 * sizeof(f64), s()));
-        for (auto &p : patches)
-            if (is_local(p) && p.f.n)
-                leapfrog_corrector(
-                    s(), p.st.n, dt_ / 2, p.f.vxyz.p, p.f.axyz.p, p.st.a_old.p, p.f.uint_.p, p.f.duint.p, p.st.du_old.p,
-                    red.p + 2, reinterpret_cast<f64 *>(red.p + 3), step_sc.p + 1);
+        if (!sliced)
+            for (auto &p : patches)
+                if (is_local(p) && p.f.n)
+                    leapfrog_corrector(
+                        s(), p.st.n, dt_ / 2, p.f.vxyz.p, p.f.axyz.p, p.st.a_old.p, p.f.uint_.p, p.f.duint.p,
+                        p.st.du_old.p, red.p + 2, reinterpret_cast<f64 *>(red.p + 3), step_sc.p + 1);
         // C7 + C8 (Solver.cpp:2587, :2597, :3119) and the sums of ConservativeCheck, fused: Σ v² and the
         // conservation sums in one sum all-reduce, max eps_v² and -min dt in one max all-reduce, both queued on
         // the stream, then ONE copy and ONE synchronisation (the dt is only used if the corrector holds)
         step_scalars(s(), red.p, step_sc.p);
         comm_allreduce_f64(*this, step_sc.p, 9, 0);
         comm_allreduce_f64(*this, step_sc.p + 9, 2, 1);
-        SB_CUDA_CHECK(cudaMemcpyAsync(h_step_sc.p, step_sc.p, 11 * sizeof(f64), cudaMemcpyDeviceToHost, s()));
+        d2h_small(s(), h_step_sc.p, step_sc.p, 11 * sizeof(f64));
         SB_CUDA_CHECK(cudaStreamSynchronize(s()));
         f64 rank_veps_v = std::sqrt(h_step_sc.p[9]);
         f64 sum_vsq     = h_step_sc.p[0];
@@ -1201,8 +1242,8 @@ void Model::evolve_once() {
     if (piped) {
         // what left early is final unless the corrector pass was repeated (then it was recomputed: send it again);
         // a configuration without the CD10 fields still returns the (untouched) arrays: every field comes back
-        static const char *const tail[] = {"vxyz", "uint", "soundspeed"};
-        pipe_download(tail, 3);
+        static const char *const tail[] = {"soundspeed", "vxyz", "uint"};
+        pipe_download(tail, (pipe.sliced_out && corrector_iter_cnt == 1) ? 1 : 3); // sliced: v, u left with the ranges
         if (corrector_iter_cnt > 1) {
             static const char *const again[] = {"axyz", "duint"};
             pipe_download(again, 2);
@@ -1244,10 +1285,14 @@ static f64 *host_field(const shamb200_host_patchdata &h, const std::string &nm) 
 
 /// device -> host copies of the named fields on the download stream, ordered after the work queued so
 /// far on the main stream ("alpha_AV@updated": the new alpha before it is committed to the field)
-void Model::pipe_download(const char *const *names, int count) {
+/// first / n: the objects [first, first + n) only (n = 0xffffffff: the whole field)
+void Model::pipe_download(const char *const *names, int count, u32 first, u32 n) {
     if (!pipe.out || count <= 0)
         return;
     PatchD &p = patches[pipe.ip];
+    const bool part = n != 0xffffffffu;
+    if (part && (u64(first) + n > p.f.n))
+        throw std::logic_error("pipe_download: range past the end of the patch");
     SB_CUDA_CHECK(cudaEventRecord(pipe.ev_stage, s()));
     SB_CUDA_CHECK(cudaStreamWaitEvent(pipe.d2h, pipe.ev_stage, 0));
     for (int k = 0; k < count; k++) {
@@ -1269,10 +1314,43 @@ void Model::pipe_download(const char *const *names, int count) {
             continue;
         if (p.f.n > pipe.out_cap)
             throw std::length_error("evolve_once_host: the patch holds more objects than out->n (capacity)");
-        size_t bytes = size_t(p.f.n) * nvar * sizeof(f64);
-        SB_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, pipe.d2h));
+        const size_t o0 = part ? size_t(first) * nvar : 0;
+        size_t bytes    = size_t(part ? n : p.f.n) * nvar * sizeof(f64);
+        if (!bytes)
+            continue;
+        SB_CUDA_CHECK(cudaMemcpyAsync(dst + o0, src + o0, bytes, cudaMemcpyDeviceToHost, pipe.d2h));
         pipe.bytes_d2h += bytes;
     }
+}
+
+/// id ranges of the host-resident step's sliced loops: SHAMB200_HOST_SLICES (default 4) ranges of at least
+/// SHAMB200_HOST_SLICE_MIN (default 2^18) objects, or none — a patch whose consecutive ids are not neighbours in
+/// space (more than 1 % of the objects farther than 8 h from their successor: count_far_successors) keeps the
+/// slot-ordered launches: neighbouring lanes must share neighbours for the gathers to hit L1.  Patch data that
+/// went through ParticleReordering follows a Morton curve (of the patch box, not of the merged tree: slots and
+/// ids differ, but either order is local) and takes the ranges
+std::vector<std::pair<u32, u32>> Model::pipe_slices() {
+    std::vector<std::pair<u32, u32>> out;
+    pipe.sliced_out = false;
+    if (!pipe.active || !pipe.early_out || !pipe.out)
+        return out;
+    const char *e_k = getenv("SHAMB200_HOST_SLICES"), *e_min = getenv("SHAMB200_HOST_SLICE_MIN"); // (tests)
+    const u32 want  = e_k ? u32(std::max(1, atoi(e_k))) : 4u;
+    const u32 least = e_min ? u32(std::max(1, atoi(e_min))) : (1u << 18);
+    const PatchD &p = patches[pipe.ip];
+    const u32 n     = p.f.n;
+    const u32 k     = std::min<u32>(want, std::max<u32>(1u, n / least));
+    const char *e_far = getenv("SHAMB200_HOST_SLICE_FAR_PCT"); // (tests: 100 takes the ranges whatever the order)
+    const u64 far_pct = e_far ? u64(std::max(0, atoi(e_far))) : 1u;
+    if (k < 2 || pipe.far_host.p[0] * 100 > u64(n) * far_pct)
+        return out;
+    for (u32 q = 0; q < k; q++) {
+        const u32 i0 = u32(u64(n) * q / k), i1 = u32(u64(n) * (q + 1) / k);
+        out.emplace_back(i0, i1 - i0);
+    }
+    pipe.sliced_out = true;
+    pipe.nslices    = k;
+    return out;
 }
 
 void Model::evolve_once_host(u32 ip, const shamb200_host_patchdata *in, shamb200_host_patchdata *out) {
@@ -1299,6 +1377,8 @@ void Model::evolve_once_host(u32 ip, const shamb200_host_patchdata *in, shamb200
     pipe.ip = ip, pipe.in = in, pipe.out = out;
     pipe.out_cap = out ? out->n : 0;
     pipe.bytes_h2d = pipe.bytes_d2h = 0;
+    pipe.sliced_out = false;
+    pipe.nslices    = 0;
     SB_CUDA_CHECK(cudaStreamSynchronize(s())); // nothing of a previous call may still read the fields
     if (in && in->n != p.f.n) {                // the host owns the data: the patch takes its size
         if (in->n > 0xFFFFFFF0ull)

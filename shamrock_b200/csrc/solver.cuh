@@ -122,6 +122,7 @@ struct Model {
     DevBuf<f64> send_stage_f, recv_stage_f;
     DevBuf<u64> comm_dev;
     PinnedBuf<u64> comm_host;
+    PinnedBuf<u32> h_counts; ///< small count read-backs (d2h_small needs page-locked memory)
     DevBuf<f64> step_sc;       ///< the step's cross-rank scalars (stream_kernels.cu: step_scalars)
     PinnedBuf<f64> h_step_sc;
     /// modules::ConservativeCheck of the last step: m Σ v (3), m Σ a (3), m Σ (u + v²/2), m Σ (v·a + du/dt)
@@ -130,6 +131,10 @@ struct Model {
     /// host-resident patch data of the running step (evolve_once_host): copy streams + hand-over events
     struct HostPipe {
         bool active = false, early_out = false, defer_in2 = false;
+        bool sliced_out = false; ///< this step ran its loops over id ranges (Model::pipe_slices)
+        u32 nslices     = 0;
+        DevBuf<u64> far_dev; ///< objects whose successor by id is far away (count_far_successors) ...
+        PinnedBuf<u64> far_host; ///< ... read back with the synchronisation of the neighbour search
         u32 ip = 0;
         const shamb200_host_patchdata *in = nullptr;
         shamb200_host_patchdata *out      = nullptr;
@@ -137,7 +142,8 @@ struct Model {
         cudaEvent_t ev_in1 = nullptr, ev_in2 = nullptr, ev_stage = nullptr;
         u64 bytes_h2d = 0, bytes_d2h = 0, out_cap = 0;
     } pipe;
-    void pipe_download(const char *const *names, int count);
+    void pipe_download(const char *const *names, int count, u32 first = 0, u32 n = 0xffffffffu);
+    std::vector<std::pair<u32, u32>> pipe_slices();
 
     explicit Model(Ctx *c, const shamb200_solver_config &cf) : ctx(c), cfg(cf) {}
     /// SHAMB200_VERBOSE=1|2: progress of the prestep on stderr (sub-cycles; 2: every patch)

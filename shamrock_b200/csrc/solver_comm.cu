@@ -134,9 +134,9 @@ void comm_allreduce_host_u64(Model &m, u64 *vals, size_t n, int op) {
     m.comm_dev.ensure(n);
     m.comm_host.ensure(n);
     std::memcpy(m.comm_host.p, vals, n * sizeof(u64));
-    SB_CUDA_CHECK(cudaMemcpyAsync(m.comm_dev.p, m.comm_host.p, n * sizeof(u64), cudaMemcpyHostToDevice, m.s()));
+    h2d_small(m.s(), m.comm_dev.p, m.comm_host.p, n * sizeof(u64));
     comm_allreduce_u64(m, m.comm_dev.p, n, op);
-    SB_CUDA_CHECK(cudaMemcpyAsync(m.comm_host.p, m.comm_dev.p, n * sizeof(u64), cudaMemcpyDeviceToHost, m.s()));
+    d2h_small(m.s(), m.comm_host.p, m.comm_dev.p, n * sizeof(u64));
     SB_CUDA_CHECK(cudaStreamSynchronize(m.s()));
     std::memcpy(vals, m.comm_host.p, n * sizeof(u64));
 }
@@ -146,9 +146,9 @@ void comm_allreduce_host_f64(Model &m, f64 *vals, size_t n, int op) {
     m.comm_dev.ensure(n);
     m.comm_host.ensure(n);
     std::memcpy(m.comm_host.p, vals, n * sizeof(f64));
-    SB_CUDA_CHECK(cudaMemcpyAsync(m.comm_dev.p, m.comm_host.p, n * sizeof(f64), cudaMemcpyHostToDevice, m.s()));
+    h2d_small(m.s(), m.comm_dev.p, m.comm_host.p, n * sizeof(f64));
     comm_allreduce_f64(m, reinterpret_cast<f64 *>(m.comm_dev.p), n, op);
-    SB_CUDA_CHECK(cudaMemcpyAsync(m.comm_host.p, m.comm_dev.p, n * sizeof(f64), cudaMemcpyDeviceToHost, m.s()));
+    d2h_small(m.s(), m.comm_host.p, m.comm_dev.p, n * sizeof(f64));
     SB_CUDA_CHECK(cudaStreamSynchronize(m.s()));
     std::memcpy(vals, m.comm_host.p, n * sizeof(f64));
 }

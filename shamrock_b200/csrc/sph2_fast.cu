@@ -166,10 +166,9 @@ __global__ void __launch_bounds__(BLK) h_solve_fast_kernel(
     const u32 k   = t / G;
     const int sub = int(t % G);
     // groups past the end clamp to the last particle (their lanes must stay in the shuffles) and write nothing
-    const bool valid = k < c.N;
-    const u32 kk     = valid ? k : c.N - 1;
-    const u32 r      = c.slot_rank[kk];
-    const u32 id     = c.index_map[r];
+    const bool valid = k < c.count;
+    u32 kk, r, id;
+    csr_item(c, valid ? k : c.count - 1, kk, r, id);
     const Pack4 a    = ld4(SA + r);
     f64 h_a          = hpart[id];
     const u32 s0 = c.off[kk], s1 = s0 + c.cnt[kk];
@@ -260,10 +259,9 @@ __global__ void __launch_bounds__(BLK) av_operators_fast_kernel(
     const u32 t      = blockIdx.x * blockDim.x + threadIdx.x;
     const u32 k      = t / G;
     const int sub    = int(t % G);
-    const bool valid = k < c.N;
-    const u32 kk     = valid ? k : c.N - 1;
-    const u32 r      = c.slot_rank[kk];
-    const u32 id     = c.index_map[r];
+    const bool valid = k < c.count;
+    u32 kk, r, id;
+    csr_item(c, valid ? k : c.count - 1, kk, r, id);
     constexpr f64 Rker2 = K::Rkern * K::Rkern;
     const Pack4 pa = ld4(SA + r), va = ld4(SB + r);
     const Pack4 aa = MAT ? ld4(SD + r) : Pack4{0, 0, 0, 0};
@@ -457,10 +455,9 @@ __global__ void __launch_bounds__(BLK) force_cfl_fast_kernel(
     const u32 t      = blockIdx.x * blockDim.x + threadIdx.x;
     const u32 k      = t / G;
     const int sub    = int(t % G);
-    const bool valid = k < c.N;
-    const u32 kk     = valid ? k : c.N - 1;
-    const u32 r      = c.slot_rank[kk];
-    const u32 id     = c.index_map[r];
+    const bool valid = k < c.count;
+    u32 kk, r, id;
+    csr_item(c, valid ? k : c.count - 1, kk, r, id);
     constexpr f64 Rker2 = K::Rkern * K::Rkern;
     constexpr bool DISC = (AV == AVK_DISC);
     const Pack4 pa = ld4(SE + r), va = ld4(SB + r), fa = ld4(SF + r);
@@ -620,9 +617,9 @@ static int lanes_override() {
 void h_solve_fast(
     cudaStream_t s, int kernel, RankCsr c, const Pack4 *SA, const f64 *h_old, f64 *hpart, f64 *eps, f64 *omega,
     f64 pmass, f64 h_evol_max, f64 h_evol_iter_max, u32 max_sweeps, bool do_iter, bool do_omega, u64 *red) {
-    if (!c.N)
+    if (!c.N || !c.count)
         return;
-    SB_KDG(kernel, (h_solve_fast_kernel<KT, G><<<grid_groups<G>(c.N), BLK, 0, s>>>(
+    SB_KDG(kernel, (h_solve_fast_kernel<KT, G><<<grid_groups<G>(c.count), BLK, 0, s>>>(
                        c, SA, h_old, hpart, eps, omega, pmass, h_evol_max, h_evol_iter_max, max_sweeps, do_iter,
                        do_omega, red)));
 }
@@ -630,10 +627,10 @@ void h_solve_fast(
 void av_operators_fast(
     cudaStream_t s, int kernel, RankCsr c, const Pack4 *SA, const Pack4 *SB, const Pack4 *SC, const Pack4 *SD,
     f64 pmass, bool want_curl, bool want_dtdivv, bool combined, f64 *divv, f64 *curlv, f64 *dtdivv, f64 *omega_out) {
-    if (!c.N)
+    if (!c.N || !c.count)
         return;
 #define AVOP2(S_, C_, M_, CB_, OM_)                                                              \
-    SB_KDG(kernel, (av_operators_fast_kernel<KT, G, S_, C_, M_, CB_, OM_><<<grid_groups<G>(c.N), BLK, 0, s>>>( \
+    SB_KDG(kernel, (av_operators_fast_kernel<KT, G, S_, C_, M_, CB_, OM_><<<grid_groups<G>(c.count), BLK, 0, s>>>( \
                        c, SA, SB, SC, SD, pmass, divv, curlv, dtdivv, omega_out)))
 #define AVOP(S_, C_, M_, CB_)                                                                    \
     do {                                                                                         \
@@ -678,15 +675,15 @@ void force_cfl_fast(
     cudaStream_t s, int kernel, int av, RankCsr c, const Pack4 *SA, const Pack4 *SB, const Pack4 *SE, const Pack4 *SF,
     const Pack4 *SC, SphParams p, const f64 *axyz_ext, f64 *axyz, f64 *duint, f64 C_cour, f64 C_force, f64 *vsig,
     f64 *cfl_dt, u64 *red_min) {
-    if (!c.N)
+    if (!c.N || !c.count)
         return;
 #define FRC(AV_)                                                                                 \
     do {                                                                                         \
         if (p.SG && p.adiabatic_gm1 != 0)                                                        \
-            SB_KDG(kernel, (force_cfl_fast_kernel<KT, AV_, G, true><<<grid_groups<G>(c.N), BLK, 0, s>>>(  \
+            SB_KDG(kernel, (force_cfl_fast_kernel<KT, AV_, G, true><<<grid_groups<G>(c.count), BLK, 0, s>>>(  \
                                c, SA, SB, SE, SF, SC, p, axyz_ext, axyz, duint, C_cour, C_force, vsig, cfl_dt, red_min))); \
         else                                                                                     \
-            SB_KDG(kernel, (force_cfl_fast_kernel<KT, AV_, G><<<grid_groups<G>(c.N), BLK, 0, s>>>(   \
+            SB_KDG(kernel, (force_cfl_fast_kernel<KT, AV_, G><<<grid_groups<G>(c.count), BLK, 0, s>>>(   \
                                c, SA, SB, SE, SF, SC, p, axyz_ext, axyz, duint, C_cour, C_force, vsig, cfl_dt, red_min))); \
     } while (0)
     switch (av) {

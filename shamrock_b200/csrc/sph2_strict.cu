@@ -26,13 +26,13 @@ __global__ void __launch_bounds__(BLK) h_solve_kernel(
     f64 *__restrict__ eps, f64 *__restrict__ omega, f64 part_mass, f64 h_max_tot_max_evol, f64 h_max_evol_p,
     u32 max_sweeps, bool do_iter, bool do_omega, u64 *red) {
     using Kn   = Kern<K>;
-    u32 k      = blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = k < c.N;
+    u32 k0     = blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = k0 < c.count;
     f64 e_out  = 0;
     u32 sweeps = 0;
     if (valid) {
-        u32 r   = c.slot_rank[k];
-        u32 id  = c.index_map[r];
+        u32 k, r, id;
+        csr_item(c, k0, k, r, id);
         Pack4 a = ld4(SA + r);
         f64 h_a = hpart[id];
         u32 s0 = c.off[k], s1 = s0 + c.cnt[k];
@@ -162,11 +162,11 @@ __global__ void __launch_bounds__(BLK) av_operators_kernel(
     const Pack4 *__restrict__ SD, f64 pmass, f64 *__restrict__ divv, f64 *__restrict__ curlv,
     f64 *__restrict__ dtdivv) {
     using Kn = Kern<K>;
-    u32 k    = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= c.N)
+    u32 k0   = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k0 >= c.count)
         return;
-    u32 r  = c.slot_rank[k];
-    u32 id = c.index_map[r];
+    u32 k, r, id;
+    csr_item(c, k0, k, r, id);
     constexpr f64 Rker2 = Kn::Rkern * Kn::Rkern;
     Pack4 pa = ld4(SA + r), va = ld4(SB + r);
     Pack4 aa = MAT ? ld4(SD + r) : Pack4{0, 0, 0, 0};
@@ -264,12 +264,12 @@ __global__ void __launch_bounds__(BLK) force_cfl_kernel(
     SphParams p, const f64 *__restrict__ axyz_ext, f64 *__restrict__ axyz, f64 *__restrict__ duint, f64 C_cour,
     f64 C_force, f64 *__restrict__ vsig_out, f64 *__restrict__ cfl_out, u64 *red_min) {
     using Kn   = Kern<K>;
-    u32 k      = blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = k < c.N;
+    u32 k0     = blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = k0 < c.count;
     f64 dt_out = f64(INFINITY);
     if (valid) {
-        u32 r  = c.slot_rank[k];
-        u32 id = c.index_map[r];
+        u32 k, r, id;
+        csr_item(c, k0, k, r, id);
         constexpr f64 Rker2 = Kn::Rkern * Kn::Rkern;
         constexpr bool VARY = (AV == AVK_MM97 || AV == AVK_CD10);
         constexpr bool DISC = (AV == AVK_DISC);
@@ -390,9 +390,9 @@ __global__ void __launch_bounds__(BLK) force_cfl_kernel(
 void h_solve_strict(
     cudaStream_t s, int kernel, RankCsr c, const Pack4 *SA, const f64 *h_old, f64 *hpart, f64 *eps, f64 *omega,
     f64 pmass, f64 h_evol_max, f64 h_evol_iter_max, u32 max_sweeps, bool do_iter, bool do_omega, u64 *red) {
-    if (!c.N)
+    if (!c.N || !c.count)
         return;
-    SB_KD(kernel, (h_solve_kernel<KT><<<grid_for(c.N, BLK), BLK, 0, s>>>(
+    SB_KD(kernel, (h_solve_kernel<KT><<<grid_for(c.count, BLK), BLK, 0, s>>>(
                       c, SA, h_old, hpart, eps, omega, pmass, h_evol_max, h_evol_iter_max, max_sweeps, do_iter,
                       do_omega, red)));
 }
@@ -400,9 +400,9 @@ void h_solve_strict(
 void av_operators_strict(
     cudaStream_t s, int kernel, RankCsr c, const Pack4 *SA, const Pack4 *SB, const Pack4 *SC, const Pack4 *SD,
     f64 pmass, bool want_curl, bool want_dtdivv, bool combined, f64 *divv, f64 *curlv, f64 *dtdivv) {
-    if (!c.N)
+    if (!c.N || !c.count)
         return;
-    unsigned g = grid_for(c.N, BLK);
+    unsigned g = grid_for(c.count, BLK);
 #define AVOP(S_, C_, M_, CB_)                                                                    \
     SB_KD(kernel, (av_operators_kernel<KT, S_, C_, M_, CB_><<<g, BLK, 0, s>>>(c, SA, SB, SC, SD, pmass, divv, curlv, dtdivv)))
     if (want_dtdivv) {
@@ -424,9 +424,9 @@ void av_operators_strict(
 void force_cfl_strict(
     cudaStream_t s, int kernel, int av, RankCsr c, const Pack4 *SA, const Pack4 *SB, const Pack4 *SC, SphParams p,
     const f64 *axyz_ext, f64 *axyz, f64 *duint, f64 C_cour, f64 C_force, f64 *vsig, f64 *cfl_dt, u64 *red_min) {
-    if (!c.N)
+    if (!c.N || !c.count)
         return;
-    unsigned g = grid_for(c.N, BLK);
+    unsigned g = grid_for(c.count, BLK);
 #define FRC(AV_)                                                                                 \
     SB_KD(kernel, (force_cfl_kernel<KT, AV_><<<g, BLK, 0, s>>>(                                  \
                       c, SA, SB, SC, p, axyz_ext, axyz, duint, C_cour, C_force, vsig, cfl_dt, red_min)))

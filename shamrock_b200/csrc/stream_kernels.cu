@@ -134,6 +134,32 @@ void leapfrog_corrector(
     SB_LAUNCH_CHECK();
 }
 
+// ---- do consecutive ids lie next to each other? ---------------------------------------------------
+/// counts the objects whose successor by id lies farther away than 8 h: a handful per thousand when the patch
+/// data follows a space-filling curve (ParticleReordering: the jumps of the curve), nearly all of them otherwise
+__global__ void __launch_bounds__(256) far_successor_kernel(
+    u32 n, const f64 *__restrict__ xyz, const f64 *__restrict__ h, unsigned long long *__restrict__ out) {
+    u32 i    = blockIdx.x * blockDim.x + threadIdx.x;
+    bool far = false;
+    if (i + 1 < n) {
+        f64 dx = xyz[3 * u64(i) + 3] - xyz[3 * u64(i)], dy = xyz[3 * u64(i) + 4] - xyz[3 * u64(i) + 1],
+            dz = xyz[3 * u64(i) + 5] - xyz[3 * u64(i) + 2];
+        f64 hh = h[i];
+        far    = dx * dx + dy * dy + dz * dz > 64. * hh * hh;
+    }
+    const u32 b = __ballot_sync(0xffffffffu, far);
+    if (b && (threadIdx.x & 31) == 0)
+        atomicAdd(out, (unsigned long long) __popc(b));
+}
+void count_far_successors(cudaStream_t s, u32 n, const f64 *xyz, const f64 *h, u64 *out) {
+    SB_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(u64), s));
+    if (n < 2)
+        return;
+    far_successor_kernel<<<grid_for(n, 256), 256, 0, s>>>(n, xyz, h, reinterpret_cast<unsigned long long *>(out));
+    SB_COUNT_LAUNCH();
+    SB_LAUNCH_CHECK();
+}
+
 /// the scalars a step reduces over the ranks, gathered into one f64 vector on the device:
 /// sc[0] = Σ v² and sc[1..8] (the conservation sums, already there) are summed; sc[9] = max eps_v²,
 /// sc[10] = -min dt are maximised — two back-to-back NCCL all-reduces and ONE host synchronisation

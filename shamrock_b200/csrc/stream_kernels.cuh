@@ -34,4 +34,6 @@ void pack_alpha(cudaStream_t s, u32 cnt, const u32 *ids, const f64 *alpha, Pack4
 void unpack_cs(cudaStream_t s, u32 n, const Pack4 *C, f64 *cs, const u32 *src_map = nullptr);
 void unpack_comp(cudaStream_t s, u32 n, const Pack4 *P, int first, int nc, f64 *out, const u32 *src_map = nullptr);
 void max_reduce(cudaStream_t s, u32 n, const f64 *v, u64 *red);
+/// *out = number of objects whose successor by id lies farther away than 8 h (locality of the id order)
+void count_far_successors(cudaStream_t s, u32 n, const f64 *xyz, const f64 *h, u64 *out);
 } // namespace sb

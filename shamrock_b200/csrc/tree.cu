@@ -801,7 +801,7 @@ void morton_sort_permutation(
     f64 hb[6] = {bmin[0], bmin[1], bmin[2], bmax[0], bmax[1], bmax[2]};
     f64 *hp   = reinterpret_cast<f64 *>(t.h_scalars.p + 8);
     std::memcpy(hp, hb, sizeof(hb));
-    SB_CUDA_CHECK(cudaMemcpyAsync(t.bbox.p, hp, sizeof(hb), cudaMemcpyHostToDevice, s));
+    h2d_small(s, t.bbox.p, hp, sizeof(hb));
     t.morton.ensure(t.P2);
     t.index_map.ensure(t.P2);
     morton_kernel<<<grid_for(t.P2, 256), 256, 0, s>>>(d_xyz, stride, M, t.P2, t.bbox.p, t.morton.p, t.index_map.p);
@@ -842,7 +842,7 @@ void tree_build(
         f64 hb[6] = {bmin[0], bmin[1], bmin[2], bmax[0], bmax[1], bmax[2]};
         f64 *hp   = reinterpret_cast<f64 *>(t.h_scalars.p + 8);
         std::memcpy(hp, hb, sizeof(hb));
-        SB_CUDA_CHECK(cudaMemcpyAsync(t.bbox.p, hp, sizeof(hb), cudaMemcpyHostToDevice, s));
+        h2d_small(s, t.bbox.p, hp, sizeof(hb));
     }
     t.morton.ensure(t.P2);
     t.index_map.ensure(t.P2);
@@ -877,8 +877,8 @@ void tree_build(
         t.morton.p, M, cur, t.scan_out.p, t.scalars.p, t.reduc_index_map.p, t.reduced_morton.p);
     SB_COUNT_LAUNCH();
     // the leaf count (and the bbox) are needed on the host
-    SB_CUDA_CHECK(cudaMemcpyAsync(t.h_scalars.p, t.scalars.p, sizeof(u64), cudaMemcpyDeviceToHost, s));
-    SB_CUDA_CHECK(cudaMemcpyAsync(t.h_scalars.p + 1, t.bbox.p, 6 * sizeof(f64), cudaMemcpyDeviceToHost, s));
+    d2h_small(s, t.h_scalars.p, t.scalars.p, sizeof(u64));
+    d2h_small(s, t.h_scalars.p + 1, t.bbox.p, 6 * sizeof(f64));
     SB_CUDA_CHECK(cudaStreamSynchronize(s));
     t.L = u32(t.h_scalars.p[0]);
     std::memcpy(t.bmin, t.h_scalars.p + 1, 3 * sizeof(f64));

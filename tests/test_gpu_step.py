@@ -337,6 +337,77 @@ def test_evolve_once_host_matches_device_resident(scenario):
         assert m.state()["dt"] == ref.state()["dt"]
 
 
+@pytest.mark.parametrize("fp_mode", FP_MODES)
+@pytest.mark.parametrize("av", ["cd10", "constant"])
+def test_evolve_once_host_sliced(av, fp_mode, monkeypatch):
+    """The host step with its operator / force / corrector passes cut into id ranges (whose outputs travel while
+    the next range is computed): bit-identical fields to the device-resident step, ids in arbitrary order."""
+    monkeypatch.setenv("SHAMB200_HOST_SLICES", "3")
+    monkeypatch.setenv("SHAMB200_HOST_SLICE_MIN", "1000")
+    monkeypatch.setenv("SHAMB200_HOST_SLICE_FAR_PCT", "100")  # lattice order: rows of 19, every row end is a jump
+    sc = S.periodic_box(7000, "M4", av, jitter=0.1)
+    ref = S.make_cuda(sc, fp_mode=fp_mode, keep_step_data=False)
+    m = S.make_cuda(sc, fp_mode=fp_mode, keep_step_data=False)
+    n = m.patch_size(0)
+    host = {nm: torch.zeros(n * nv, dtype=torch.float64).pin_memory() for nm, nv in _capi.HOST_FIELDS}
+    for nm in ALL_FIELDS:
+        host[nm].numpy()[:] = m.get(0, nm).reshape(-1)
+    in_names = ["xyz", "vxyz", "axyz", "hpart", "uint", "duint"] + (["alpha_AV", "soundspeed"] if av == "cd10" else [])
+    for step in range(3):
+        ref.evolve_once()
+        for nm in ALL_FIELDS:  # every output must arrive: poison the host copy of what is not an input
+            if nm not in in_names:
+                host[nm].numpy()[:] = np.nan
+        n_new = m.evolve_once_host(0, n, {nm: host[nm].data_ptr() for nm in in_names},
+                                   {nm: host[nm].data_ptr() for nm in ALL_FIELDS})
+        assert n_new == n
+        assert m.host_step_info(0)[0] == 3
+        up, down = m.host_traffic()
+        assert down >= n * 22 * 8
+        for nm in ALL_FIELDS:
+            got, want = host[nm].numpy(), ref.get(0, nm).reshape(-1)
+            assert np.array_equal(got, want, equal_nan=True), f"step {step} {nm}"
+        assert m.state()["dt"] == ref.state()["dt"]
+
+
+def test_host_step_slices_need_morton_order():
+    """Ranges of ids are only used when consecutive ids are neighbours in space (neighbouring lanes must share
+    neighbours): a shuffled patch reports its far successors and keeps the slot-ordered launches; after
+    ParticleReordering the ranges are used.  Same fields either way."""
+    import os
+    os.environ["SHAMB200_HOST_SLICE_MIN"] = "4096"
+    try:
+        sc = S.periodic_box(40000, "M4", "cd10", jitter=0.1)
+        rng = np.random.default_rng(5)
+        perm = rng.permutation(len(sc["hpart"]))
+        for k in ("xyz", "vxyz", "hpart", "uint"):
+            sc[k] = np.ascontiguousarray(sc[k][perm])
+        ref = S.make_cuda(sc, fp_mode="fast", keep_step_data=False)
+        m = S.make_cuda(sc, fp_mode="fast", keep_step_data=False)
+        n = m.patch_size(0)
+        host = {nm: torch.zeros(n * nv, dtype=torch.float64).pin_memory() for nm, nv in _capi.HOST_FIELDS}
+
+        def step_and_compare():
+            for nm in ALL_FIELDS:
+                host[nm].numpy()[:] = m.get(0, nm).reshape(-1)
+            ref.evolve_once()
+            ptrs = {nm: host[nm].data_ptr() for nm in ALL_FIELDS}
+            m.evolve_once_host(0, n, ptrs, ptrs)
+            for nm in ALL_FIELDS:
+                assert np.array_equal(host[nm].numpy(), ref.get(0, nm).reshape(-1), equal_nan=True), nm
+
+        step_and_compare()
+        k, far = m.host_step_info(0)
+        assert k == 0 and far > n // 2
+        ref.reorder_particles()
+        m.reorder_particles()
+        step_and_compare()
+        k, far = m.host_step_info(0)
+        assert k == 4 and far * 100 <= n
+    finally:
+        del os.environ["SHAMB200_HOST_SLICE_MIN"]
+
+
 def test_bench_path_fields_match_oracle():
     """The configuration bench.py times (fast fp, keep_step_data = 0) against the oracle: every main-layout
     field within 1e-10 after three steps."""

@@ -1323,7 +1323,7 @@ void Model::pipe_download(const char *const *names, int count, u32 first, u32 n)
     }
 }
 
-/// id ranges of the host-resident step's sliced loops: SHAMB200_HOST_SLICES (default 4) ranges of at least
+/// id ranges of the host-resident step's sliced loops: SHAMB200_HOST_SLICES (default 8) ranges of at least
 /// SHAMB200_HOST_SLICE_MIN (default 2^18) objects, or none — a patch whose consecutive ids are not neighbours in
 /// space (more than 1 % of the objects farther than 8 h from their successor: count_far_successors) keeps the
 /// slot-ordered launches: neighbouring lanes must share neighbours for the gathers to hit L1.  Patch data that
@@ -1335,7 +1335,7 @@ std::vector<std::pair<u32, u32>> Model::pipe_slices() {
     if (!pipe.active || !pipe.early_out || !pipe.out)
         return out;
     const char *e_k = getenv("SHAMB200_HOST_SLICES"), *e_min = getenv("SHAMB200_HOST_SLICE_MIN"); // (tests)
-    const u32 want  = e_k ? u32(std::max(1, atoi(e_k))) : 4u;
+    const u32 want  = e_k ? u32(std::max(1, atoi(e_k))) : 8u;
     const u32 least = e_min ? u32(std::max(1, atoi(e_min))) : (1u << 18);
     const PatchD &p = patches[pipe.ip];
     const u32 n     = p.f.n;

@@ -403,7 +403,7 @@ def test_host_step_slices_need_morton_order():
         m.reorder_particles()
         step_and_compare()
         k, far = m.host_step_info(0)
-        assert k == 4 and far * 100 <= n
+        assert k == 8 and far * 100 <= n
     finally:
         del os.environ["SHAMB200_HOST_SLICE_MIN"]
 

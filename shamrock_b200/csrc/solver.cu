@@ -379,10 +379,11 @@ void Model::compute_ext_forces_indep_v() {
 
 /// Solver::apply_position_boundary (Solver.cpp:938-981)
 void Model::apply_position_boundary() {
-    if (cfg.bc == SHAMB200_BC_PERIODIC)
+    if (cfg.bc == SHAMB200_BC_PERIODIC && !wrapped_in_drift)
         for (auto &p : patches)
             if (is_local(p) && p.f.n)
                 periodic_wrap(s(), p.f.n, p.f.xyz.p, box_min, box_max);
+    wrapped_in_drift = false;
     reattribute_patch_objects();
 }
 
@@ -717,12 +718,14 @@ void Model::merge_position_ghost() {
 void Model::build_merged_pos_trees() {
     for (auto &p : patches)
         if (is_local(p) && p.f.n)
-            tree_build(
+            tree_build( // ... and the interaction radius of every node (compute_presteps_rint) in its AABB pass
                 s(), p.st.tree, reinterpret_cast<const f64 *>(p.st.A.p), 4, p.st.m, nullptr, nullptr, true,
-                cfg.tree_reduction_level, cfg.sort_mode);
+                cfg.tree_reduction_level, cfg.sort_mode, cfg.htol_up_coarse_cycle, &p.st.rint);
 }
 /// Solver::compute_presteps_rint (Solver.cpp:1322-1356)
 void Model::compute_presteps_rint() {
+    if (!no_fused_rint())
+        return; // build_merged_pos_trees left it in p.st.rint (same maxima, same scale)
     for (auto &p : patches)
         if (is_local(p) && p.f.n) {
             p.st.rint.ensure(size_t(p.st.tree.I) + p.st.tree.L);
@@ -1018,12 +1021,17 @@ void Model::evolve_once() {
     point_mass_accrete_particles();
     // host-resident patch data (evolve_once_host): copies overlap the kernels
     const bool piped_in = pipe.active && pipe.defer_in2, piped = pipe.active && pipe.early_out;
+    // periodic box and nothing that reads the positions between the drift and the position boundary (kill
+    // spheres, point-mass force): the wrap of apply_position_boundary rides in the drift kernel (same arithmetic)
+    wrapped_in_drift = cfg.bc == SHAMB200_BC_PERIODIC && cfg.n_kill_spheres == 0 && !cfg.has_point_mass;
+    const f64 *wmin = wrapped_in_drift ? box_min : nullptr, *wmax = wrapped_in_drift ? box_max : nullptr;
     for (auto &p : patches)
         if (is_local(p) && p.f.n) {
             if (piped_in) // uint / duint are still uploading: drift the positions now, u after the prestep
-                leapfrog_predictor_pos(s(), p.f.n, dt_, p.f.xyz.p, p.f.vxyz.p, p.f.axyz.p);
+                leapfrog_predictor_pos(s(), p.f.n, dt_, p.f.xyz.p, p.f.vxyz.p, p.f.axyz.p, wmin, wmax);
             else
-                leapfrog_predictor(s(), p.f.n, dt_, p.f.xyz.p, p.f.vxyz.p, p.f.axyz.p, p.f.uint_.p, p.f.duint.p);
+                leapfrog_predictor(
+                    s(), p.f.n, dt_, p.f.xyz.p, p.f.vxyz.p, p.f.axyz.p, p.f.uint_.p, p.f.duint.p, wmin, wmax);
         }
     kill_particles();
     compute_ext_forces_indep_v();

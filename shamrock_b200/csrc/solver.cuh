@@ -215,6 +215,12 @@ struct Model {
     bool omega_in_av_pass() const {
         return cfg.fp_mode == SHAMB200_FP_FAST && (cfg.av == SHAMB200_AV_MM97 || cfg.av == SHAMB200_AV_CD10);
     }
+    /// SHAMB200_FUSED_RINT=0: the interaction radii in their own tree pass (A / B runs)
+    static bool no_fused_rint() {
+        const char *e = getenv("SHAMB200_FUSED_RINT");
+        return e && atoi(e) == 0;
+    }
+    bool wrapped_in_drift = false; ///< this step's predictor already applied the periodic wrap
     void reset_red();
     void read_red(int n);
 };

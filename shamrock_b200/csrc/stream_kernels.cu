@@ -15,15 +15,37 @@
 namespace sb {
 
 // ---- leapfrog predictor: v+=½dt a ; u+=½dt du ; x+=dt v ; v+=½dt a ; u+=½dt du -----------------
+/// periodic wrap of one coordinate into [lo, hi) (BasicSPHGhosts / apply_position_boundary of the reference)
+__device__ __forceinline__ f64 wrap_coord(f64 x, f64 lo, f64 hi) {
+    f64 delt = hi - lo;
+    f64 r    = x - lo;
+    r        = fmod(r, delt);
+    r += delt;
+    r = fmod(r, delt);
+    r += lo;
+    return r;
+}
+struct WrapBox {
+    f64 lo[3], hi[3];
+};
+/// WRAP: the periodic position boundary applied to the drifted position in the same pass (nothing reads the
+/// positions between the drift and the wrap in such a step: Model::evolve_once)
+template<bool WRAP>
 __global__ void __launch_bounds__(256) predictor_kernel(
     u32 n_pos, u32 n_u, f64 dt, f64 dt_half, f64 *__restrict__ xyz, f64 *__restrict__ vxyz,
-    const f64 *__restrict__ axyz, f64 *__restrict__ uint_, const f64 *__restrict__ duint) {
+    const f64 *__restrict__ axyz, f64 *__restrict__ uint_, const f64 *__restrict__ duint, WrapBox wb) {
     u64 i = u64(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < u64(n_pos) * 3) {
         f64 a  = axyz[i];
         f64 v  = vxyz[i];
         v      = v + dt_half * a;
-        xyz[i] = xyz[i] + dt * v;
+        f64 x  = xyz[i] + dt * v;
+        if (WRAP) {
+            const int c = int(i % 3);
+            x = wrap_coord(x, c == 0 ? wb.lo[0] : (c == 1 ? wb.lo[1] : wb.lo[2]),
+                           c == 0 ? wb.hi[0] : (c == 1 ? wb.hi[1] : wb.hi[2]));
+        }
+        xyz[i] = x;
         v      = v + dt_half * a;
         vxyz[i] = v;
     }
@@ -35,26 +57,46 @@ __global__ void __launch_bounds__(256) predictor_kernel(
         uint_[i] = u;
     }
 }
-void leapfrog_predictor(cudaStream_t s, u32 n, f64 dt, f64 *xyz, f64 *vxyz, const f64 *axyz, f64 *uint_, const f64 *duint) {
+static WrapBox wrap_box(const f64 *bmin, const f64 *bmax) {
+    WrapBox wb{{0, 0, 0}, {0, 0, 0}};
+    for (int d = 0; bmin && d < 3; d++)
+        wb.lo[d] = bmin[d], wb.hi[d] = bmax[d];
+    return wb;
+}
+void leapfrog_predictor(
+    cudaStream_t s, u32 n, f64 dt, f64 *xyz, f64 *vxyz, const f64 *axyz, f64 *uint_, const f64 *duint,
+    const f64 *wrap_min, const f64 *wrap_max) {
     if (!n)
         return;
-    predictor_kernel<<<grid_for(u64(n) * 3, 256), 256, 0, s>>>(n, n, dt, dt / 2, xyz, vxyz, axyz, uint_, duint);
+    if (wrap_min)
+        predictor_kernel<true><<<grid_for(u64(n) * 3, 256), 256, 0, s>>>(
+            n, n, dt, dt / 2, xyz, vxyz, axyz, uint_, duint, wrap_box(wrap_min, wrap_max));
+    else
+        predictor_kernel<false><<<grid_for(u64(n) * 3, 256), 256, 0, s>>>(
+            n, n, dt, dt / 2, xyz, vxyz, axyz, uint_, duint, wrap_box(nullptr, nullptr));
     SB_COUNT_LAUNCH();
     SB_LAUNCH_CHECK();
 }
 /// the two halves of the predictor on their own (host-resident patch data: `uint` may still be in flight
 /// while the positions are already being drifted; the updates are independent element by element)
-void leapfrog_predictor_pos(cudaStream_t s, u32 n, f64 dt, f64 *xyz, f64 *vxyz, const f64 *axyz) {
+void leapfrog_predictor_pos(
+    cudaStream_t s, u32 n, f64 dt, f64 *xyz, f64 *vxyz, const f64 *axyz, const f64 *wrap_min, const f64 *wrap_max) {
     if (!n)
         return;
-    predictor_kernel<<<grid_for(u64(n) * 3, 256), 256, 0, s>>>(n, 0, dt, dt / 2, xyz, vxyz, axyz, nullptr, nullptr);
+    if (wrap_min)
+        predictor_kernel<true><<<grid_for(u64(n) * 3, 256), 256, 0, s>>>(
+            n, 0, dt, dt / 2, xyz, vxyz, axyz, nullptr, nullptr, wrap_box(wrap_min, wrap_max));
+    else
+        predictor_kernel<false><<<grid_for(u64(n) * 3, 256), 256, 0, s>>>(
+            n, 0, dt, dt / 2, xyz, vxyz, axyz, nullptr, nullptr, wrap_box(nullptr, nullptr));
     SB_COUNT_LAUNCH();
     SB_LAUNCH_CHECK();
 }
 void leapfrog_predictor_u(cudaStream_t s, u32 n, f64 dt, f64 *uint_, const f64 *duint) {
     if (!n)
         return;
-    predictor_kernel<<<grid_for(n, 256), 256, 0, s>>>(0, n, dt, dt / 2, nullptr, nullptr, nullptr, uint_, duint);
+    predictor_kernel<false><<<grid_for(n, 256), 256, 0, s>>>(
+        0, n, dt, dt / 2, nullptr, nullptr, nullptr, uint_, duint, wrap_box(nullptr, nullptr));
     SB_COUNT_LAUNCH();
     SB_LAUNCH_CHECK();
 }
@@ -184,13 +226,7 @@ __global__ void __launch_bounds__(256) wrap_kernel(u32 n, f64 *__restrict__ xyz,
     int c    = int(i % 3);
     f64 lo   = c == 0 ? b0x : (c == 1 ? b0y : b0z);
     f64 hi   = c == 0 ? b1x : (c == 1 ? b1y : b1z);
-    f64 delt = hi - lo;
-    f64 r    = xyz[i] - lo;
-    r        = fmod(r, delt);
-    r += delt;
-    r = fmod(r, delt);
-    r += lo;
-    xyz[i] = r;
+    xyz[i] = wrap_coord(xyz[i], lo, hi);
 }
 void periodic_wrap(cudaStream_t s, u32 n, f64 *xyz, const f64 bmin[3], const f64 bmax[3]) {
     if (!n)

@@ -3,8 +3,13 @@
 #include "sph.cuh"
 
 namespace sb {
-void leapfrog_predictor(cudaStream_t s, u32 n, f64 dt, f64 *xyz, f64 *vxyz, const f64 *axyz, f64 *uint_, const f64 *duint);
-void leapfrog_predictor_pos(cudaStream_t s, u32 n, f64 dt, f64 *xyz, f64 *vxyz, const f64 *axyz);
+/// wrap_min / wrap_max (optional): the periodic box the drifted positions are wrapped into in the same pass
+void leapfrog_predictor(
+    cudaStream_t s, u32 n, f64 dt, f64 *xyz, f64 *vxyz, const f64 *axyz, f64 *uint_, const f64 *duint,
+    const f64 *wrap_min = nullptr, const f64 *wrap_max = nullptr);
+void leapfrog_predictor_pos(
+    cudaStream_t s, u32 n, f64 dt, f64 *xyz, f64 *vxyz, const f64 *axyz, const f64 *wrap_min = nullptr,
+    const f64 *wrap_max = nullptr);
 void leapfrog_predictor_u(cudaStream_t s, u32 n, f64 dt, f64 *uint_, const f64 *duint);
 void leapfrog_corrector(cudaStream_t s, u32 n, f64 hdt, f64 *vxyz, const f64 *axyz, const f64 *axyz_old, f64 *uint_,
                         const f64 *duint, const f64 *duint_old, u64 *red_max, f64 *red_sum, f64 *cons = nullptr);

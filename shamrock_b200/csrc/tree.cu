@@ -693,16 +693,21 @@ __global__ void __launch_bounds__(256) karras_kernel(
 // AABB (K11-K12) and max-field (K13): one bottom-up pass with arrival counters.  min/max are exact,
 // so this equals the reference's 32 brute-force passes (KarrasRadixTreeAABB.cpp:33-74).
 // =============================================================================================
+/// FIELD: the objects are (x, y, z, f) records and the pass also reduces fout[node] = fscale * max f, exactly as
+/// leaf_field_max_propagate_kernel would afterwards (the solver's interaction radius: compute_presteps_rint)
+template<bool FIELD>
 __global__ void __launch_bounds__(128) leaf_aabb_propagate_kernel(
     const f64 *__restrict__ xyz, size_t stride, const u32 *__restrict__ index_map,
     const u32 *__restrict__ reduc_index_map, u32 L, u32 I, const u32 *__restrict__ lchild,
     const u32 *__restrict__ rchild, const u8 *__restrict__ lflag, const u8 *__restrict__ rflag,
-    const u32 *__restrict__ parent, u32 *__restrict__ counters, f64 *aabb_min, f64 *aabb_max) {
+    const u32 *__restrict__ parent, u32 *__restrict__ counters, f64 *aabb_min, f64 *aabb_max, f64 fscale,
+    f64 *fout) {
     u32 leaf = blockIdx.x * blockDim.x + threadIdx.x;
     if (leaf >= L)
         return;
     const f64 big = 1.7976931348623157e308;
     f64 mn[3] = {big, big, big}, mx[3] = {-big, -big, -big};
+    f64 fm = -big;
     u32 a = reduc_index_map[leaf], b = reduc_index_map[leaf + 1];
     for (u32 sidx = a; sidx < b; sidx++) {
         u32 id = index_map[sidx];
@@ -712,6 +717,8 @@ __global__ void __launch_bounds__(128) leaf_aabb_propagate_kernel(
             mn[c] = fmin(mn[c], v);
             mx[c] = fmax(mx[c], v);
         }
+        if (FIELD)
+            fm = fmax(fm, xyz[u64(id) * stride + 3]);
     }
     u32 node = I + leaf;
 #pragma unroll
@@ -719,6 +726,8 @@ __global__ void __launch_bounds__(128) leaf_aabb_propagate_kernel(
         aabb_min[u64(node) * 3 + c] = mn[c];
         aabb_max[u64(node) * 3 + c] = mx[c];
     }
+    if (FIELD)
+        fout[node] = fm * fscale;
     if (I == 0)
         return;
     node = parent[node];
@@ -736,6 +745,8 @@ __global__ void __launch_bounds__(128) leaf_aabb_propagate_kernel(
             aabb_min[u64(node) * 3 + c] = fmin(a0, a1);
             aabb_max[u64(node) * 3 + c] = fmax(b0, b1);
         }
+        if (FIELD)
+            fout[node] = fmax(__ldcg(&fout[l]), __ldcg(&fout[r]));
         if (node == 0)
             return;
         node = parent[node];
@@ -821,7 +832,7 @@ void morton_sort_permutation(
 
 void tree_build(
     cudaStream_t s, TreeBuffers &t, const f64 *d_xyz, size_t stride, u32 M, const f64 *bmin,
-    const f64 *bmax, bool auto_bbox, u32 reduction_level, int sort_mode) {
+    const f64 *bmax, bool auto_bbox, u32 reduction_level, int sort_mode, f64 field_scale, DevBuf<f64> *field_out) {
     if (M == 0)
         throw std::invalid_argument("obj_cnt is 0, cannot build a CompressedLeafBVH");
     t.M  = M;
@@ -903,9 +914,18 @@ void tree_build(
     size_t tot = size_t(t.I) + t.L;
     t.aabb_min.ensure(tot * 3);
     t.aabb_max.ensure(tot * 3);
-    leaf_aabb_propagate_kernel<<<grid_for(t.L, 128), 128, 0, s>>>(
-        d_xyz, stride, t.index_map.p, t.reduc_index_map.p, t.L, t.I, t.lchild.p, t.rchild.p, t.lflag.p,
-        t.rflag.p, t.parent.p, t.counters.p, t.aabb_min.p, t.aabb_max.p);
+    if (field_out) {
+        if (stride < 4)
+            throw std::invalid_argument("tree_build: the fused field maximum needs (x, y, z, f) records");
+        field_out->ensure(tot);
+        leaf_aabb_propagate_kernel<true><<<grid_for(t.L, 128), 128, 0, s>>>(
+            d_xyz, stride, t.index_map.p, t.reduc_index_map.p, t.L, t.I, t.lchild.p, t.rchild.p, t.lflag.p,
+            t.rflag.p, t.parent.p, t.counters.p, t.aabb_min.p, t.aabb_max.p, field_scale, field_out->p);
+    } else {
+        leaf_aabb_propagate_kernel<false><<<grid_for(t.L, 128), 128, 0, s>>>(
+            d_xyz, stride, t.index_map.p, t.reduc_index_map.p, t.L, t.I, t.lchild.p, t.rchild.p, t.lflag.p,
+            t.rflag.p, t.parent.p, t.counters.p, t.aabb_min.p, t.aabb_max.p, 0., nullptr);
+    }
     SB_COUNT_LAUNCH();
     SB_LAUNCH_CHECK();
 }

@@ -31,7 +31,10 @@ enum SortMode { SORT_BITONIC = 0, SORT_RADIX = 1 };
 /// d_bbox (device, 6 doubles: bmin, bmax) may be null → bmin/bmax host values are used.
 void tree_build(
     cudaStream_t s, TreeBuffers &t, const f64 *d_xyz, size_t stride_dbl, u32 M, const f64 *bmin,
-    const f64 *bmax, bool auto_bbox, u32 reduction_level, int sort_mode);
+    const f64 *bmax, bool auto_bbox, u32 reduction_level, int sort_mode, f64 field_scale = 0.,
+    DevBuf<f64> *field_out = nullptr);
+// field_out (optional; stride_dbl >= 4): the objects are (x, y, z, f) records and the AABB pass also leaves
+// field_out[node] = field_scale * max f of the node's objects ([I+L]) — tree_field_max without its own pass
 
 /// Morton codes over [bmin, bmax] + sort only: t.index_map[0..M) = Morton order of the objects
 void morton_sort_permutation(

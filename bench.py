@@ -146,10 +146,10 @@ def workload(npart_per_gpu, n_gpus, kernel="M4", rank=0, count_reduce=None):
 # M merged, N real, K = sum of list lengths, K_acc ~ K / htol^3 pairs inside the kernel support, L leaves.
 # Flop convention: FMA = 2, div / sqrt = 1; candidate test 10, density pair 39, div+curl+dtdivv 175,
 # force + v_sig 155 per accepted pair.
-def alg_work(stage, N, M, K, L, sweeps, tests=0, omega_in_av=True):
+def alg_work(stage, N, M, K, L, sweeps, tests=0, omega_in_av=True, list_tol=1.1):
     """omega_in_av: fast fp + CD10 / MM97 — the Ω sum (one density-type pass, 39 flop per pair) is evaluated inside
     the CD10 operator pass instead of after the h iteration"""
-    K_acc = K / 1.1**3
+    K_acc = K / list_tol**3  # K counts the lists as built: radius R h list_tol (shamb200_model_list_tolerance)
     h_passes = sweeps + (0 if omega_in_av else 1)
     return {
         # the search = one tree walk per group of 8 leaves + the accept / fill kernel; SURVEY.md §8d's figure
@@ -218,7 +218,7 @@ def run_reference(args):
                                    f"OpenMP), {args.steps} dt=0 replays"},
         "e2e": {"value": v, "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def rel_err(a, b):
@@ -345,6 +345,25 @@ def parity_check(args, rank, world, local, ctx, dist, torch, _capi):
     return out
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries ONE JSON line: whatever libraries print there (NCCL's version banner, torchrun chatter of the
+    children) is sent to stderr; the line itself goes to the original descriptor."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    claim_stdout()
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -364,6 +383,7 @@ def main():
     ap.add_argument("--no-reorder", action="store_true",
                     help="keep the generation order of the lattice (the reference's apply_setup reorders by default)")
     args = ap.parse_args()
+    claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
     if args.impl == "reference":
@@ -532,12 +552,14 @@ def main():
         # (h_solve / av_operators / force_cfl) or the search kernels.  Roof = slower of HBM and FP64 pipe.
         N, K = n_local, int(st["K_local"])
         tests = m.search_stats()[1]
+        ltol_info = m.list_tolerance()
+        ltol = ltol_info["last"] or 1.1
         M, L = int(N * 1.0), int(N / 3.6)  # ~3.6 objects per leaf at reduction level 3 on the HCP lattice
         sweeps = int(st["h_iters_last"]) + 1
         per_stage = {k: v / args.steps for k, v in stage_acc.items()}
         table = {}
         for k, ms_k in per_stage.items():
-            w = alg_work(k, N, M, K, L, sweeps, tests)
+            w = alg_work(k, N, M, K, L, sweeps, tests, list_tol=ltol)
             if not w:
                 continue
             t_hbm, t_fp = w[0] / (hbm_peak * 1e9), (w[1] / (fp64_peak * 1e12) if fp64_peak else 0.0)
@@ -576,9 +598,14 @@ def main():
                     "achieved": tt["TFLOP/s"] if tt["bound"] == "fp64" else tt["GB/s"],
                     "peak": fp64_peak if tt["bound"] == "fp64" else hbm_peak,
                     "unit": "TFLOP/s" if tt["bound"] == "fp64" else "GB/s", "frac": tt["frac"], "traffic": traffic, "traffic_source": traffic_src,
-                    "algorithmic_bytes": alg_work(top, N, M, K, L, sweeps, tests)[0],
-                    "algorithmic_flops": alg_work(top, N, M, K, L, sweeps, tests)[1],
+                    "algorithmic_bytes": alg_work(top, N, M, K, L, sweeps, tests, list_tol=ltol)[0],
+                    "algorithmic_flops": alg_work(top, N, M, K, L, sweeps, tests, list_tol=ltol)[1],
                     "accept_tests_per_particle": tests / max(N, 1),
+                    "neighbours_per_particle": K / max(N, 1),
+                    # the lists of the timed steps were built with the radius R h list_tolerance.last instead of the
+                    # reference's R h 1.1: the h growth of the previous step (dt = 0 replays: none) decides, a step
+                    # whose h outgrows its lists is redone with 1.1 (shamb200_model_list_tolerance)
+                    "list_tolerance": ltol_info,
                     "peak_source": {"hbm_gbs": hbm_peak, "hbm": peak_src, "fp64_tflops": fp64_peak,
                                     "fp64": "measured here: FP64 FMA chains (shamb200_microbench), FMA = 2 flop",
                                     "copy_gbs_here": copy_bw,
@@ -626,7 +653,7 @@ def main():
             if cpus_before:
                 os.sched_setaffinity(0, cpus_before)
             line["cpu_baseline"] = cpu_baseline(args, ctx)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

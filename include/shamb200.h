@@ -430,6 +430,16 @@ int shamb200_host_unregister(void *p);
 int shamb200_model_search_stats(shamb200_model *m, uint64_t out[2]);
 /* bytes moved by the last shamb200_model_evolve_once_host: out[0] host->device, out[1] device->host */
 int shamb200_model_host_traffic(shamb200_model *m, uint64_t out[2]);
+/* Neighbour-list tolerance of the model's own step (not of shamb200_neigh_cache_build, which takes the caller's).
+ * The reference builds the lists of a step with the radius R h htol, htol = htol_up_coarse_cycle = 1.1
+ * (Solver.cpp:1322-1386, NeighbourCache.cpp:482-520), so that h may grow inside the step.  With fp_mode FAST the
+ * step builds them with a tolerance fitted to the h growth of the previous step, verifies after the h iteration
+ * that no h_iterate / h_old exceeded it (then the loops saw every pair inside a kernel support: same sums as with
+ * the full lists) and otherwise redoes the sub-cycle with htol.  STRICT mode, keep_step_data and epsilon_h != 1e-6
+ * always use htol.  out = {tolerance of the last step's lists, largest h_iterate / h_old of the last step (all
+ * ranks), tolerance the next step will start with, number of steps that had to fall back so far}.
+ * Environment: SHAMB200_LIST_TOL=0 always htol; a value in (1, htol] fixes the starting tolerance. */
+int shamb200_model_list_tolerance(shamb200_model *m, double out[4]);
 /* how the last shamb200_model_evolve_once_host ran: out[0] = number of id ranges its operator / force / corrector
  * passes were cut into so that finished ranges travel to the host while the next is computed (0: one launch per
  * pass), out[1] = objects of the patch whose successor by id lay farther away than 8 h — above 1 % of the patch the

@@ -89,7 +89,7 @@ SYMBOLS = [
     "shamb200_model_set_field", "shamb200_model_reorder_particles", "shamb200_model_evolve_once",
     "shamb200_model_evolve_once_host",
     "shamb200_host_register", "shamb200_host_unregister", "shamb200_model_host_traffic",
-    "shamb200_model_host_step_info",
+    "shamb200_model_host_step_info", "shamb200_model_list_tolerance",
     "shamb200_model_search_stats", "shamb200_model_state", "shamb200_model_conservation",
     "shamb200_model_add_lattice_hcp", "shamb200_model_add_disc_lattice", "shamb200_model_add_disc_mc", "shamb200_model_set_value_in_a_box",
     "shamb200_model_set_value_in_sphere", "shamb200_model_add_kernel_value", "shamb200_model_get_sum",
@@ -558,6 +558,12 @@ class Model:
         o = (C.c_uint64 * 2)()
         check(lib().shamb200_model_host_traffic(self.h, o))
         return int(o[0]), int(o[1])
+
+    def list_tolerance(self):
+        """neighbour-list tolerance of the model's step: dict(last, growth, next, fallbacks)"""
+        o = (C.c_double * 4)()
+        check(lib().shamb200_model_list_tolerance(self.h, o))
+        return dict(last=float(o[0]), growth=float(o[1]), next=float(o[2]), fallbacks=int(o[3]))
 
     def host_step_info(self, ip=0):
         """(id ranges the last host step was cut into, objects stored far from their Morton position)"""

@@ -702,6 +702,15 @@ int shamb200_model_host_traffic(shamb200_model *m, uint64_t out[2]) {
         out[1] = m->m.pipe.bytes_d2h;
     });
 }
+int shamb200_model_list_tolerance(shamb200_model *m, double out[4]) {
+    return guard([&] {
+        need_live(m);
+        out[0] = m->m.list_tol_last;
+        out[1] = m->m.h_growth_last;
+        out[2] = m->m.list_tol_next > 1. ? m->m.list_tol_next : m->m.cfg.htol_up_coarse_cycle;
+        out[3] = double(m->m.list_fallbacks);
+    });
+}
 int shamb200_model_host_step_info(shamb200_model *m, uint32_t ip, uint64_t out[2]) {
     return guard([&] {
         need_live(m);

@@ -715,27 +715,26 @@ void Model::merge_position_ghost() {
 }
 
 /// modules::BuildTrees::build_merged_pos_trees (BuildTrees.cpp:26-66)
-void Model::build_merged_pos_trees() {
+void Model::build_merged_pos_trees(f64 tol) {
     for (auto &p : patches)
         if (is_local(p) && p.f.n)
             tree_build( // ... and the interaction radius of every node (compute_presteps_rint) in its AABB pass
                 s(), p.st.tree, reinterpret_cast<const f64 *>(p.st.A.p), 4, p.st.m, nullptr, nullptr, true,
-                cfg.tree_reduction_level, cfg.sort_mode, cfg.htol_up_coarse_cycle, &p.st.rint);
+                cfg.tree_reduction_level, cfg.sort_mode, tol, &p.st.rint);
 }
 /// Solver::compute_presteps_rint (Solver.cpp:1322-1356)
-void Model::compute_presteps_rint() {
+void Model::compute_presteps_rint(f64 tol) {
     if (!no_fused_rint())
         return; // build_merged_pos_trees left it in p.st.rint (same maxima, same scale)
     for (auto &p : patches)
         if (is_local(p) && p.f.n) {
             p.st.rint.ensure(size_t(p.st.tree.I) + p.st.tree.L);
             tree_field_max(
-                s(), p.st.tree, reinterpret_cast<const f64 *>(p.st.A.p) + 3, cfg.htol_up_coarse_cycle,
-                p.st.rint.p, 4);
+                s(), p.st.tree, reinterpret_cast<const f64 *>(p.st.A.p) + 3, tol, p.st.rint.p, 4);
         }
 }
 /// Solver::start_neighbors_cache (Solver.cpp:1364-1386): Morton-sorted storage + the B200 search
-void Model::start_neighbors_cache() {
+void Model::start_neighbors_cache(f64 tol) {
     const f64 Rkern = cfg.kernel == SHAMB200_KERNEL_M4 ? 2.0 : 3.0;
     if (verbose())
         fprintf(stderr, "[shamb200 rank %d] neighbour cache: %zu interfaces\n", rank, ifaces.size());
@@ -745,8 +744,7 @@ void Model::start_neighbors_cache() {
         if (is_local(p) && p.f.n) {
             search_prepare_sorted(s(), p.st.tree, p.st.srch, p.st.A.p, p.st.n);
             search_build(
-                s(), p.st.tree, p.st.srch, p.st.rint.p, Rkern, cfg.htol_up_coarse_cycle,
-                [&](const char *name) { timer.mark(s(), name); });
+                s(), p.st.tree, p.st.srch, p.st.rint.p, Rkern, tol, [&](const char *name) { timer.mark(s(), name); });
             K_local += p.st.srch.K;
             pair_tests_local += p.st.srch.pair_tests;
             if (verbose() > 1)
@@ -757,7 +755,27 @@ void Model::start_neighbors_cache() {
 }
 
 /// Solver::sph_prestep (Solver.cpp:1060-1304)
+///
+/// List tolerance.  The reference builds its neighbour lists with the radius R h htol (htol_up_coarse_cycle = 1.1)
+/// so that h may grow by 10 % inside the step without a new search; a third of the entries of such a list lie
+/// outside every kernel support when h barely moves — the usual case.  The fast fp mode builds its lists with a
+/// tolerance tol <= htol fitted to what the previous step needed (h_growth_last) and checks afterwards what this
+/// step needed: the h iteration reports the largest h_iterate / h_old of any particle and sweep.  If that stayed
+/// below tol, every density sum and every later loop saw all the pairs inside its supports (the entries left out
+/// contribute exactly nothing) and the step is the one the full lists would have given; if not, h is restored
+/// and the sub-cycle is redone with the reference's tolerance (list_fallbacks).  Ghost zones always use htol.
+/// The strict mode, keep_step_data (the lists can be exported) and epsilon_h != 1e-6 keep htol.
 void Model::sph_prestep() {
+    const f64 htol = cfg.htol_up_coarse_cycle;
+    f64 tol        = htol;
+    if (cfg.fp_mode == SHAMB200_FP_FAST && !cfg.keep_step_data && cfg.epsilon_h == 1e-6) {
+        const f64 ov = list_tol_override();
+        if (ov < 0)
+            tol = list_tol_next > 1. ? std::min(list_tol_next, htol) : htol;
+        else if (ov > 1.)
+            tol = std::min(ov, htol);
+    }
+    f64 growth_step = 1.;
     u32 hstep_cnt = 0;
     for (; hstep_cnt < cfg.h_max_subcycles_count; hstep_cnt++) {
         timer.mark(s(), "ghost_cache");
@@ -765,11 +783,11 @@ void Model::sph_prestep() {
         timer.mark(s(), "merge_position_ghost");
         merge_position_ghost();
         timer.mark(s(), "build_trees");
-        build_merged_pos_trees();
+        build_merged_pos_trees(tol);
         timer.mark(s(), "rint");
-        compute_presteps_rint();
+        compute_presteps_rint(tol);
         timer.mark(s(), "neigh_prepare"); // sorted storage + packed nodes; then "neigh_walk", "neigh_lists"
-        start_neighbors_cache();
+        start_neighbors_cache(tol);
         timer.mark(s(), "h_iteration");
         if (cfg.gpart_mass == 0)
             throw std::runtime_error(
@@ -804,7 +822,7 @@ void Model::sph_prestep() {
                         p.f.hpart.p, st.eps.p, st.omega.p, cfg.gpart_mass, cfg.htol_up_coarse_cycle,
                         cfg.htol_up_fine_cycle, cfg.h_iter_per_subcycles, true, !omega_later, red.p);
                 }
-            read_red(3);
+            read_red(7);
             local_max_eps = ordered_to_f64(h_red.p[0]);
             local_min_eps = ordered_to_f64(h_red.p[1]);
             u32 sweeps    = u32(h_red.p[2]); // slot 2 doubles as the sweep counter during the h iteration
@@ -835,14 +853,43 @@ void Model::sph_prestep() {
         bool should_rerun_gz = local_min_eps < 0;
         bool below_tol       = local_max_eps < cfg.epsilon_h;
         bool converged       = below_tol && !should_rerun_gz;
-        u64 all_conv         = converged ? 1 : 0; // are_all_rank_true (LoopSmoothingLengthIter.cpp:63-64)
-        comm_allreduce_host_u64(*this, &all_conv, 1, 2);
-        converged = all_conv != 0;
+        // are_all_rank_true (LoopSmoothingLengthIter.cpp:63-64) and the largest h growth of any rank in one
+        // min all-reduce (the ordered encoding is monotonic: min of the complement = complement of the max)
+        const u64 growth_enc = (fused && cfg.fp_mode == SHAMB200_FP_FAST) ? h_red.p[6] : 0;
+        u64 agree[2]         = {converged ? 1ull : 0ull, ~growth_enc};
+        comm_allreduce_host_u64(*this, agree, 2, 2);
+        converged        = agree[0] != 0;
+        const f64 growth = ~agree[1] ? ordered_to_f64(~agree[1]) : 1.;
+        if (tol < htol && !(growth <= tol * (1. - 1e-12))) {
+            // some h outgrew the lists (a ghost's h grows on the rank that owns it: every rank sees the same
+            // maximum): back to the h of before the iteration, once more with the reference's tolerance
+            for (auto &p : patches)
+                if (is_local(p) && p.f.n)
+                    SB_CUDA_CHECK(cudaMemcpyAsync(
+                        p.f.hpart.p, p.st.h_old.p, size_t(p.st.n) * sizeof(f64), cudaMemcpyDeviceToDevice, s()));
+            if (verbose())
+                fprintf(stderr, "[shamb200 rank %d] h grew by %.4f > list tolerance %.4f: sub-cycle redone with %.2f\n",
+                        rank, growth, tol, htol);
+            tol = htol;
+            list_fallbacks++;
+            hstep_cnt--;
+            continue;
+        }
+        growth_step = std::max(growth_step, growth);
         if (!converged)
             continue;
         break;
     }
-    h_subcycles = hstep_cnt + 1;
+    h_subcycles   = hstep_cnt + 1;
+    list_tol_last = tol;
+    h_growth_last = growth_step;
+    // next step: 2.5 x the growth this one needed + 0.3 %, at least 0.5 %; close to htol there is nothing to gain
+    {
+        const f64 want = 1. + 2.5 * (growth_step - 1.) + 0.003;
+        list_tol_next  = std::max(1.005, want);
+        if (!(list_tol_next < 1. + 0.8 * (htol - 1.)))
+            list_tol_next = htol;
+    }
     if (cfg.epsilon_h != 1e-6 && !omega_in_av_pass()) {
         timer.mark(s(), "omega");
         for (auto &p : patches)

@@ -204,9 +204,9 @@ struct Model {
     void reattribute_patch_objects();
     void build_ghost_cache();
     void merge_position_ghost();
-    void build_merged_pos_trees();
-    void compute_presteps_rint();
-    void start_neighbors_cache();
+    void build_merged_pos_trees(f64 tol);
+    void compute_presteps_rint(f64 tol);
+    void start_neighbors_cache(f64 tol);
     void sph_prestep();
     void communicate_merge_ghosts_fields();
     void exchange_alpha_ghosts(bool with_omega);
@@ -214,6 +214,17 @@ struct Model {
     /// costing a pass of its own after the h iteration (sph2_fast.cu: av_operators_fast_kernel<..., OMEGA>)
     bool omega_in_av_pass() const {
         return cfg.fp_mode == SHAMB200_FP_FAST && (cfg.av == SHAMB200_AV_MM97 || cfg.av == SHAMB200_AV_CD10);
+    }
+    // ---- list tolerance of the fast fp mode (solver.cu: Model::sph_prestep) ----
+    f64 list_tol_next  = 0;  ///< tolerance the next step's lists are built with (0: htol_up_coarse_cycle)
+    f64 list_tol_last  = 0;  ///< what the last step's lists were built with
+    f64 h_growth_last  = 1;  ///< max over all ranks, particles and sweeps of h_iterate / h_old in the last step
+    u64 list_fallbacks = 0;  ///< steps whose h outgrew the tight lists and were redone with the reference's tolerance
+    /// SHAMB200_LIST_TOL: 0 = always the reference's tolerance; a value in (1, htol]: that tolerance in every step
+    /// (still with the fallback); unset: adaptive
+    static f64 list_tol_override() {
+        const char *e = getenv("SHAMB200_LIST_TOL");
+        return e ? atof(e) : -1.;
     }
     /// SHAMB200_FUSED_RINT=0: the interaction radii in their own tree pass (A / B runs)
     static bool no_fused_rint() {

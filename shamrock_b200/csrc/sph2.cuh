@@ -17,7 +17,8 @@ namespace sb {
 
 enum { FP_STRICT = 0, FP_FAST = 1 };
 
-/// red: [0] max eps (ordered), [1] min eps (ordered), [2] max sweep count (u64)
+/// red: [0] max eps (ordered), [1] min eps (ordered), [2] max sweep count (u64); fast fp mode also [6] = max over
+/// the particles and sweeps of h_iterate / h_old (ordered): the list tolerance this iteration needed (solver.cu)
 void h_solve(
     cudaStream_t s, int fp_mode, int kernel, RankCsr c, const Pack4 *SA, const f64 *h_old, f64 *hpart, f64 *eps,
     f64 *omega, f64 pmass, f64 h_evol_max, f64 h_evol_iter_max, u32 max_sweeps, bool do_iter, bool do_omega,

@@ -175,9 +175,11 @@ __global__ void __launch_bounds__(BLK) h_solve_fast_kernel(
     constexpr f64 hf3 = K::hfactd * K::hfactd * K::hfactd;
     f64 e_out  = 0;
     u32 sweeps = 0;
+    f64 growth = 0; // largest h_iterate / h_old of this particle (red[6]: how much list tolerance the step needed)
     if (do_iter) {
         f64 e            = eps[id];
         const f64 ha_0   = h_old[id];
+        f64 h_top        = h_a;
         const f64 h_max_evol_m = 1 / h_max_evol_p;
         while (sweeps < max_sweeps && e > 1e-6) {
             f64 sf, sg;
@@ -201,9 +203,11 @@ __global__ void __launch_bounds__(BLK) h_solve_fast_kernel(
                 h_a = ha_0 * h_max_tot_max_evol;
                 e   = -1;
             }
+            h_top = fmax(h_top, h_a);
             sweeps++;
         }
-        e_out = e;
+        e_out  = e;
+        growth = h_top / ha_0;
         if (valid && sub == 0) {
             eps[id]   = e;
             hpart[id] = h_a;
@@ -217,9 +221,10 @@ __global__ void __launch_bounds__(BLK) h_solve_fast_kernel(
             omega[id] = 1 - (K::norm_3d / (3 * hf3)) * sg;
     }
     if (do_iter) {
-        __shared__ f64 smax[BLK / 32], smin[BLK / 32];
+        __shared__ f64 smax[BLK / 32], smin[BLK / 32], sgr[BLK / 32];
         __shared__ u32 ssw[BLK / 32];
         const bool mine = valid && sub == 0;
+        f64 vgr  = warp_max(mine ? growth : 0.);
         f64 vmax = warp_max(mine ? e_out : -f64(INFINITY));
         f64 vmin = warp_min(mine ? e_out : f64(INFINITY));
         u32 sw   = mine ? sweeps : 0u;
@@ -229,18 +234,21 @@ __global__ void __launch_bounds__(BLK) h_solve_fast_kernel(
         if ((threadIdx.x & 31) == 0) {
             smax[threadIdx.x >> 5] = vmax;
             smin[threadIdx.x >> 5] = vmin;
+            sgr[threadIdx.x >> 5]  = vgr;
             ssw[threadIdx.x >> 5]  = sw;
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            f64 x = smax[0], y = smin[0];
+            f64 x = smax[0], y = smin[0], g = sgr[0];
             u32 z = ssw[0];
 #pragma unroll
             for (int q = 1; q < BLK / 32; q++) {
                 x = fmax(x, smax[q]);
                 y = fmin(y, smin[q]);
+                g = fmax(g, sgr[q]);
                 z = max(z, ssw[q]);
             }
+            atomicMax((unsigned long long *) &red[6], (unsigned long long) f64_to_ordered(g));
             atomicMax((unsigned long long *) &red[0], (unsigned long long) f64_to_ordered(x));
             atomicMin((unsigned long long *) &red[1], (unsigned long long) f64_to_ordered(y));
             atomicMax((unsigned long long *) &red[2], (unsigned long long) z);

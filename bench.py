@@ -260,7 +260,12 @@ def cpu_baseline(args, ctx):
         sm = m.evolve_once()
     errs = {nm: rel_err(m.get(0, nm), o.get(0, nm)) for nm in CHECK_FIELDS}
     errs["dt"] = abs(sm["dt"] - so["dt"]) / abs(so["dt"])
-    cnt_equal = bool(np.array_equal(m.get(0, "cache.cnt_neigh"), o.get(0, "cache.cnt_neigh")))
+    # the model's lists are built with the radius R h tol, tol <= the reference's 1.1 (shamb200_model_list_tolerance):
+    # equal counts when tol = 1.1, otherwise every list is a subset of the reference's
+    cm, co = m.get(0, "cache.cnt_neigh"), o.get(0, "cache.cnt_neigh")
+    ltol = m.list_tolerance()
+    cnt_equal = bool(np.array_equal(cm, co))
+    cnt_subset = bool(cm.shape == co.shape and (cm <= co).all())
     m.close()
     return {"value": n * k / dt, "unit": "particles/s", "cores": ncores, "kind": "port",
             "sample": f"{n} particles of the same periodic box, 1 warm-up + {k} dt=0 replays, oracle (C++/OpenMP port "
@@ -273,7 +278,9 @@ def cpu_baseline(args, ctx):
                 # time derivative are sums that cancel to round-off away from the blast, alpha is a ratio of them
                 "max_rel_err_av_switch": max(errs[f] for f in ("alpha_AV", "divv", "dtdivv", "curlv", "soundspeed")),
                 "per_field": {f: float(f"{e:.3e}") for f, e in errs.items()},
-                "neighbour_counts_equal": cnt_equal}}
+                "list_tolerance": ltol["last"], "list_fallbacks": ltol["fallbacks"],
+                "neighbour_counts_equal": cnt_equal, "neighbour_counts_subset_of_reference": cnt_subset,
+                "neighbours_per_particle": [float(cm.mean()), float(co.mean())]}}
 
 
 def parity_check(args, rank, world, local, ctx, dist, torch, _capi):

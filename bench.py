@@ -300,9 +300,12 @@ def parity_check(args, rank, world, local, ctx, dist, torch, _capi):
         ids = [_capi.nccl_unique_id() if rank == 0 else None]
         if world > 1:
             dist.broadcast_object_list(ids, src=0)
-        m = S.make_cuda(sc, ctx=ctx, keep_step_data=True, rank=rank, world=world, nccl_id=ids[0], fp_mode=fp_mode)
+        # the fast run is the configuration the bench times (keep_step_data off: adaptive list tolerance, §4c)
+        m = S.make_cuda(sc, ctx=ctx, keep_step_data=(fp_mode == "strict"), rank=rank, world=world, nccl_id=ids[0],
+                        fp_mode=fp_mode)
         for _ in range(2):
             sm = m.evolve_once()
+        ltol = m.list_tolerance()["last"]
         names = CHECK_FIELDS + (INT_NAMES if fp_mode == "strict" else [])
         mine = {ip: {nm: m.get(ip, nm) for nm in names} for ip in range(m.patch_count)
                 if m.patch_is_local(ip) and m.patch_size(ip)}
@@ -338,7 +341,8 @@ def parity_check(args, rank, world, local, ctx, dist, torch, _capi):
         if e_dt > worst:
             worst, worst_nm = e_dt, "dt"
         return {"n": len(sc["xyz"]), "max_rel_err": worst, "worst": worst_nm, "ints_exact": ints_ok,
-                "fields_bit_identical": bits_ok, "h_subcycles": sm["h_subcycles"] == so["h_subcycles"]}
+                "fields_bit_identical": bits_ok, "h_subcycles": sm["h_subcycles"] == so["h_subcycles"],
+                "list_tolerance": ltol}
 
     fast = run(args.fp, "radix")
     strict = run("strict", "bitonic")
@@ -346,7 +350,7 @@ def parity_check(args, rank, world, local, ctx, dist, torch, _capi):
         return None
     out.update(n=fast["n"], max_rel_err=fast["max_rel_err"], worst=fast["worst"],
                ints_exact=strict["ints_exact"], strict_fields_bit_identical=strict["fields_bit_identical"],
-               strict_max_rel_err=strict["max_rel_err"],
+               strict_max_rel_err=strict["max_rel_err"], list_tolerance_second_step=fast["list_tolerance"],
                config={"bench_mode": f"fp {args.fp}, radix sort", "exact_mode": "fp strict, bitonic sort (reference tie order)",
                        "tolerance": "1e-10 relative per particle, |d| <= tol * max(|x|, mean|x|), no floors"})
     return out

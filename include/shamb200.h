@@ -329,6 +329,37 @@ int shamb200_model_push_particles(shamb200_model *m, uint64_t n, const double *x
  * SerializeHelper byte stream.  Collective: every rank calls it with the same file name (shared file system). */
 int shamb200_model_dump(shamb200_model *m, const char *fname);
 int shamb200_model_load_dump(shamb200_model *m, const char *fname);
+/* ---- Phantom dumps and legacy VTK files ---------------------------------------------------------
+ * phantom_dump = Model::make_phantom_dump().save_dump(fname) (shammodels/sph/src/Model.cpp:1491-1638,
+ *   io/PhantomDump.cpp:276-316): the Fortran-record container of PhantomDump::gen_file with the reference's header
+ *   tables (same tags, types and order) and block 0 = fort_real x y z vx vy vz u, f32 h [alpha divv].  Sinks are
+ *   outside this library: nptmass = 0, no block 1.  The reference leaves isink / polyk2 (and polyk / RK2 for the
+ *   adiabatic EOS) of its EOS header uninitialised; 0 is written here.  Collective; one file, every rank writes
+ *   its particles (rank by rank, patch by patch).
+ * init_from_phantom_dump = Model::init_from_phantom_dump(dump, hpart_fact_load) (Model.cpp:1225-1429): box from
+ *   xmin..zmax of the header, else the positions' bounding box grown by 1.2; time from the header; every particle
+ *   of block 0 with h >= 0 goes to the patch that contains it (xyz vxyz hpart * hpart_fact_load, uint, alpha_AV).
+ *   Every rank reads the file; *kept = particles inside the box with h >= 0.  A model without a box gets one patch.
+ * phantom_gen_config = Model::gen_config_from_phantom_dump (Model.cpp:1203-1222, io/Phantom2Shamrock.cpp:27-67,
+ *   :128-136, :186-197): gpart_mass = massoftype[0], C_cour, C_force, ieos 1 / 2 / 3 -> isothermal / adiabatic /
+ *   LP07 (other values: error unless bypass_error), CD10 viscosity (0, 1, 0.1, alphau, 2), periodic iff xmin is in
+ *   the header.  Fields of *cfg it does not name are left as they are.  No device needed.
+ * phantom_copy = PhantomDump::from_file + gen_file + write_to_file (the reference's own test of its reader /
+ *   writer, src/tests/phantom_read_test.cpp:20-34: the copy must be byte-identical).  phantom_header_* =
+ *   PhantomDump::read_header_float / read_header_int / has_header_entry; phantom_compare = compare_phantom_dumps
+ *   (number of header entries that differ, are missing or extra).
+ * vtk_dump = Model::do_vtk_dump(fname, add_patch_world_id) (modules/io/VTKDump.cpp:36-178,
+ *   shamrock/include/shamrock/io/LegacyVtkWriter.hpp): legacy BINARY unstructured grid, points + one FIELD section
+ *   ([patchid world_rank] h u v a [alpha_AV divv] [dtdivv curlv] [soundspeed] rho), every value big-endian f32 /
+ *   i32, converted on the device.  Collective. */
+int shamb200_model_phantom_dump(shamb200_model *m, const char *fname);
+int shamb200_model_init_from_phantom_dump(shamb200_model *m, const char *fname, double hpart_fact_load, uint64_t *kept);
+int shamb200_model_vtk_dump(shamb200_model *m, const char *fname, int add_patch_world_id);
+int shamb200_phantom_gen_config(const char *fname, int bypass_error, shamb200_solver_config *cfg);
+int shamb200_phantom_copy(const char *fname_in, const char *fname_out);
+int shamb200_phantom_header_float(const char *fname, const char *key, double *out, int *found);
+int shamb200_phantom_header_int(const char *fname, const char *key, int64_t *out, int *found);
+int shamb200_phantom_compare(const char *fname_a, const char *fname_b, uint64_t *offenses);
 /* ---- patch scheduler ---------------------------------------------------------------------
  * PatchScheduler (shamrock/src/scheduler/PatchScheduler.cpp:308-500): patches on the 2^21 integer grid are split
  * into their eight children above crit_split objects, an octet of sibling leaves is merged below crit_merge,

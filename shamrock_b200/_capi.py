@@ -94,7 +94,10 @@ SYMBOLS = [
     "shamb200_model_add_lattice_hcp", "shamb200_model_add_disc_lattice", "shamb200_model_add_disc_mc", "shamb200_model_set_value_in_a_box",
     "shamb200_model_set_value_in_sphere", "shamb200_model_add_kernel_value", "shamb200_model_get_sum",
     "shamb200_model_total_part_count", "shamb200_model_set_particle_mass",
-    "shamb200_model_dump", "shamb200_model_load_dump", "shamb200_model_init_scheduler", "shamb200_model_scheduler_step", "shamb200_model_split_patch",
+    "shamb200_model_dump", "shamb200_model_load_dump",
+    "shamb200_model_phantom_dump", "shamb200_model_init_from_phantom_dump", "shamb200_model_vtk_dump",
+    "shamb200_phantom_gen_config", "shamb200_phantom_copy", "shamb200_phantom_header_float",
+    "shamb200_phantom_header_int", "shamb200_phantom_compare", "shamb200_model_init_scheduler", "shamb200_model_scheduler_step", "shamb200_model_split_patch",
     "shamb200_model_merge_patches", "shamb200_model_migrate_patch", "shamb200_model_patch_info",
     "shamb200_model_scheduler_log",
     "shamb200_model_set_next_dt", "shamb200_model_set_time", "shamb200_model_set_cfl_multiplier",
@@ -412,6 +415,19 @@ class Model:
     def load_dump(self, fname):
         check(lib().shamb200_model_load_dump(self.h, str(fname).encode()))
 
+    # -- Phantom dumps / legacy VTK (io_formats.cu)
+    def phantom_dump(self, fname):
+        check(lib().shamb200_model_phantom_dump(self.h, str(fname).encode()))
+
+    def init_from_phantom_dump(self, fname, hpart_fact_load=1.0):
+        kept = C.c_uint64(0)
+        check(lib().shamb200_model_init_from_phantom_dump(self.h, str(fname).encode(), C.c_double(hpart_fact_load),
+                                                          C.byref(kept)))
+        return kept.value
+
+    def vtk_dump(self, fname, add_patch_world_id=True):
+        check(lib().shamb200_model_vtk_dump(self.h, str(fname).encode(), C.c_int(1 if add_patch_world_id else 0)))
+
     # -- patch scheduler (scheduler.cu)
     def init_scheduler(self, crit_split, crit_merge, step_freq=0):
         check(lib().shamb200_model_init_scheduler(self.h, C.c_uint64(int(crit_split)), C.c_uint64(int(crit_merge)),
@@ -594,6 +610,36 @@ class Model:
         check(lib().shamb200_model_stage_times(self.h, C.byref(names), C.byref(ms), C.byref(cnt)))
         ns = names.value.decode().split(";") if names.value else []
         return {n: ms[i] for i, n in enumerate(ns[: cnt.value])}
+
+
+# ---- Phantom dump files (io_formats.cu; host only, no device needed) ----
+def phantom_gen_config(fname, cfg=None, bypass_error=False):
+    """Model::gen_config_from_phantom_dump: fills the fields the dump defines into cfg (default configuration if None)"""
+    cfg = default_config() if cfg is None else cfg
+    check(lib().shamb200_phantom_gen_config(str(fname).encode(), C.c_int(1 if bypass_error else 0), C.byref(cfg)))
+    return cfg
+
+
+def phantom_copy(fname_in, fname_out):
+    check(lib().shamb200_phantom_copy(str(fname_in).encode(), str(fname_out).encode()))
+
+
+def phantom_header_float(fname, key):
+    out, found = C.c_double(0), C.c_int(0)
+    check(lib().shamb200_phantom_header_float(str(fname).encode(), key.encode(), C.byref(out), C.byref(found)))
+    return out.value if found.value else None
+
+
+def phantom_header_int(fname, key):
+    out, found = C.c_int64(0), C.c_int(0)
+    check(lib().shamb200_phantom_header_int(str(fname).encode(), key.encode(), C.byref(out), C.byref(found)))
+    return out.value if found.value else None
+
+
+def phantom_compare(fname_a, fname_b):
+    out = C.c_uint64(0)
+    check(lib().shamb200_phantom_compare(str(fname_a).encode(), str(fname_b).encode(), C.byref(out)))
+    return out.value
 
 
 def plan_patch_grid(bmin, bmax, grid, world=1):

@@ -33,6 +33,7 @@ SOURCES = {
     "setup.cu": ["-fmad=false"],
     "scheduler.cu": ["-fmad=false"],
     "dump.cu": ["-fmad=false"],
+    "io_formats.cu": ["-fmad=false"],
     "solver_comm.cu": ["-fmad=false"],
     "capi.cu": ["-fmad=false"],
     "capi_stages.cu": ["-fmad=false"],

@@ -524,6 +524,69 @@ int shamb200_model_load_dump(shamb200_model *m, const char *fname) {
         m->m.load_dump(fname);
     });
 }
+int shamb200_model_phantom_dump(shamb200_model *m, const char *fname) {
+    return guard([&] {
+        need_live(m);
+        if (!fname)
+            throw std::invalid_argument("null file name");
+        m->m.phantom_dump(fname);
+    });
+}
+int shamb200_model_init_from_phantom_dump(shamb200_model *m, const char *fname, double hpart_fact_load, uint64_t *kept) {
+    return guard([&] {
+        need_live(m);
+        if (!fname)
+            throw std::invalid_argument("null file name");
+        const uint64_t k = m->m.init_from_phantom_dump(fname, hpart_fact_load);
+        if (kept)
+            *kept = k;
+    });
+}
+int shamb200_model_vtk_dump(shamb200_model *m, const char *fname, int add_patch_world_id) {
+    return guard([&] {
+        need_live(m);
+        if (!fname)
+            throw std::invalid_argument("null file name");
+        m->m.vtk_dump(fname, add_patch_world_id != 0);
+    });
+}
+int shamb200_phantom_gen_config(const char *fname, int bypass_error, shamb200_solver_config *cfg) {
+    return guard([&] {
+        if (!fname || !cfg)
+            throw std::invalid_argument("null argument");
+        sb::phantom_gen_config(fname, bypass_error != 0, *cfg);
+    });
+}
+int shamb200_phantom_copy(const char *fname_in, const char *fname_out) {
+    return guard([&] {
+        if (!fname_in || !fname_out)
+            throw std::invalid_argument("null file name");
+        sb::phantom_copy(fname_in, fname_out);
+    });
+}
+int shamb200_phantom_header_float(const char *fname, const char *key, double *out, int *found) {
+    return guard([&] {
+        if (!fname || !key || !out || !found)
+            throw std::invalid_argument("null argument");
+        int64_t dummy = 0;
+        *found        = sb::phantom_header(fname, key, 0, out, &dummy);
+    });
+}
+int shamb200_phantom_header_int(const char *fname, const char *key, int64_t *out, int *found) {
+    return guard([&] {
+        if (!fname || !key || !out || !found)
+            throw std::invalid_argument("null argument");
+        double dummy = 0;
+        *found       = sb::phantom_header(fname, key, 1, &dummy, out);
+    });
+}
+int shamb200_phantom_compare(const char *fname_a, const char *fname_b, uint64_t *offenses) {
+    return guard([&] {
+        if (!fname_a || !fname_b || !offenses)
+            throw std::invalid_argument("null argument");
+        *offenses = sb::phantom_compare(fname_a, fname_b);
+    });
+}
 int shamb200_model_init_scheduler(shamb200_model *m, uint64_t crit_split, uint64_t crit_merge, uint32_t step_freq) {
     return guard([&] {
         need_live(m);

@@ -154,7 +154,7 @@ void Model::set_box(const f64 bmin[3], const f64 bmax[3], u32 nx, u32 ny, u32 nz
     SB_CUDA_CHECK(cudaStreamSynchronize(s()));
 }
 
-void Model::push_particles(u64 n, const f64 *xyz, const f64 *vxyz, const f64 *h, const f64 *u) {
+void Model::push_particles(u64 n, const f64 *xyz, const f64 *vxyz, const f64 *h, const f64 *u, const f64 *alpha) {
     if (patches.empty())
         throw std::runtime_error("the box size is not set, please resize the box to the domain size");
     // host-side binning (setup path, not the hot path)
@@ -207,6 +207,8 @@ void Model::push_particles(u64 n, const f64 *xyz, const f64 *vxyz, const f64 *h,
                 src = h;
             else if (nm == "uint")
                 src = u;
+            else if (nm == "alpha_AV")
+                src = alpha;
             up(*r.buf, r.nvar, src);
         }
         p.f.n = newn;

@@ -158,7 +158,7 @@ struct Model {
     bool is_local(const PatchD &p) const { return p.owner == rank; }
 
     void set_box(const f64 bmin[3], const f64 bmax[3], u32 nx, u32 ny, u32 nz);
-    void push_particles(u64 n, const f64 *xyz, const f64 *vxyz, const f64 *h, const f64 *u);
+    void push_particles(u64 n, const f64 *xyz, const f64 *vxyz, const f64 *h, const f64 *u, const f64 *alpha = nullptr);
     // patch scheduler (scheduler.cu): PatchScheduler::scheduler_step and its pieces
     u64 next_patch_id = 0;            ///< SchedulerPatchList::_next_patch_id
     u64 crit_split = 0, crit_merge = 0; ///< Model::init_scheduler(crit_split, crit_merge); 0 = never
@@ -179,6 +179,10 @@ struct Model {
     // checkpoint / restart (dump.cu): write_shamrock_dump / load_shamrock_dump container
     void dump(const std::string &fname);
     void load_dump(const std::string &fname);
+    // Phantom dumps and legacy VTK files (io_formats.cu)
+    void phantom_dump(const std::string &fname);                             ///< make_phantom_dump + save_dump
+    u64 init_from_phantom_dump(const std::string &fname, f64 hpart_fact_load); ///< returns the particles kept (all ranks' input)
+    void vtk_dump(const std::string &fname, bool add_patch_world_id);        ///< Model::do_vtk_dump
     void evolve_once();
     void evolve_once_host(u32 ip, const shamb200_host_patchdata *in, shamb200_host_patchdata *out);
     int64_t get(u32 ip, const std::string &name, void *out, int64_t cap);
@@ -237,6 +241,12 @@ struct Model {
 };
 
 f64 microbench(Ctx &c, int what); ///< microbench.cu
+
+// Phantom dump files (io_formats.cu; host only)
+void phantom_gen_config(const std::string &fname, bool bypass_error, shamb200_solver_config &cfg);
+void phantom_copy(const std::string &in, const std::string &out); ///< from_file + gen_file + write_to_file
+int phantom_header(const std::string &fname, const std::string &key, int want_int, f64 *fval, i64 *ival);
+u64 phantom_compare(const std::string &fa, const std::string &fb); ///< compare_phantom_dumps: number of offenses
 
 // NCCL plumbing (solver_comm.cu)
 void comm_unique_id(void *out128);

@@ -13,7 +13,10 @@ modules/AnalysisSodTube.cpp (analysis).
 
 Setup is host work (numpy), as in the reference; the patch data moves to the GPU at the first timestep and
 lives there.  One process drives one GPU; there is no CPU fallback (the step needs libshamb200 and a device).
-Not mirrored: dumps, plots, sinks, the solver-graph introspection (`get_solver_tex` / `get_solver_dot_graph`
+Phantom dumps (`load_phantom_dump`, `PhantomDump`, `compare_phantom_dumps`, `model.make_phantom_dump`,
+`gen_config_from_phantom_dump`, `init_from_phantom_dump`: shammodels/sph/src/pyPhantomDump.cpp:24-58,
+pySPHModel.cpp:1352-1379) and `model.do_vtk_dump` go through libshamb200's csrc/io_formats.cu.
+Not mirrored: plots, sinks, the solver-graph introspection (`get_solver_tex` / `get_solver_dot_graph`
 return a short placeholder so that scripts printing them keep running).
 """
 import math as _math
@@ -620,6 +623,48 @@ class Model:
                 break
         return n
 
+    # -- Phantom dumps / VTK (pySPHModel.cpp:1352-1379)
+    def do_vtk_dump(self, filename, add_patch_world_id):
+        if getattr(self, "_dirty", True) or self._dev is None:
+            self._push()
+        self._dev.vtk_dump(filename, add_patch_world_id)
+
+    def make_phantom_dump(self):
+        """a PhantomDump of the current state (held in a temporary file until save_dump copies it)"""
+        import tempfile
+
+        if getattr(self, "_dirty", True) or self._dev is None:
+            self._push()
+        tmp = tempfile.NamedTemporaryFile(prefix="shamb200_", suffix=".phdump", delete=False)
+        tmp.close()
+        self._dev.phantom_dump(tmp.name)
+        return PhantomDump(tmp.name, owned=True)
+
+    def gen_config_from_phantom_dump(self, dump, bypass_error=False):
+        c = _capi.phantom_gen_config(dump._fname, bypass_error=bypass_error)
+        cfg = SolverConfig(self._kernel)
+        cfg._c.update(eos=c.eos, gamma=c.gamma, cs0=c.cs0, eos_q=c.eos_q, eos_r0=c.eos_r0, av=c.av,
+                      alpha_min=c.alpha_min, alpha_max=c.alpha_max, sigma_decay=c.sigma_decay, alpha_u=c.alpha_u,
+                      beta_AV=c.beta_AV, bc=c.bc, gpart_mass=c.gpart_mass)
+        cfg._cfl = (c.cfl_cour, c.cfl_force)
+        return cfg
+
+    def init_from_phantom_dump(self, dump, hpart_fact_load=1.0):
+        """particles, box and time of the dump; call after set_solver_config + init_scheduler like the reference"""
+        if self._dev is not None:
+            raise RuntimeError("init_from_phantom_dump needs a model that has not started")
+        if hasattr(self._cfg, "_cfl") and not self._cfl_cour:
+            self._cfl_cour, self._cfl_force = self._cfg._cfl
+        if not self._pmass:
+            self._pmass = self._cfg._c.get("gpart_mass", 0.0)
+        self._bmin, self._bmax = (0.0, 0.0, 0.0), (1.0, 1.0, 1.0)  # replaced by the dump's box
+        self._make_device_model()
+        self._dev.init_from_phantom_dump(dump._fname, hpart_fact_load)
+        info = self._dev.patch_info(0)
+        self._bmin, self._bmax = info["lo"], info["hi"]
+        self._dirty, self._on_device, self._host_fresh = False, True, False
+        self._pull()
+
     # -- checkpoint / restart (Model::dump / Model::load_from_dump, Model.hpp:906-995)
     def dump(self, fname):
         if getattr(self, "_dirty", True) or self._dev is None:
@@ -652,6 +697,52 @@ class Model:
 
     def make_analysis_sodtube(self, sod, direction, time_val, x_ref, x_min, x_max):
         return AnalysisSodTube(self, sod, direction, time_val, x_ref, x_min, x_max)
+
+
+class PhantomDump:
+    """shamrock.PhantomDump (pyPhantomDump.cpp:29-46): a dump file on disk, read through libshamb200"""
+
+    def __init__(self, fname, owned=False):
+        self._fname, self._owned = str(fname), owned
+
+    def __del__(self):
+        if getattr(self, "_owned", False):
+            import os
+
+            try:
+                os.unlink(self._fname)
+            except OSError:
+                pass
+
+    def save_dump(self, fname):
+        _capi.phantom_copy(self._fname, fname)  # from_file + gen_file + write_to_file
+
+    def read_header_float(self, s):
+        v = _capi.phantom_header_float(self._fname, s)
+        if v is None:
+            raise RuntimeError("the entry cannot be found : " + s)
+        return v
+
+    def read_header_int(self, s):
+        v = _capi.phantom_header_int(self._fname, s)
+        if v is None:
+            raise RuntimeError("the entry cannot be found")
+        return v
+
+    def print_state(self):
+        print("--- dump state ---")
+        print("file =", self._fname, " nparttot =", _capi.phantom_header_int(self._fname, "nparttot"))
+        print("------------------")
+
+
+def load_phantom_dump(fname):
+    d = PhantomDump(fname)
+    d.read_header_int("nparttot")  # parses the file: a damaged dump fails here, as in the reference
+    return d
+
+
+def compare_phantom_dumps(dump_1, dump_2):
+    return _capi.phantom_compare(dump_1._fname, dump_2._fname) == 0
 
 
 def get_Model_SPH(context, vector_type="f64_3", sph_kernel="M4", device=0, fp_mode="strict", sort_mode="bitonic"):

@@ -124,7 +124,7 @@ class PhantomDump:
     def array(self, iblock, name):
         k = pad16(name)
         out = [np.asarray(v, dtype=np.float64) for t in TYPES for tag, v in self.blocks[iblock]["arrays"].get(t, [])
-               if tag == k]
+               if pad16(tag) == k]
         return np.concatenate(out) if out else np.zeros(0)
 
 

@@ -828,9 +828,25 @@ __global__ void __launch_bounds__(S2_WARPS * 32, 4) neigh_lists_kernel(
     }
 }
 
-void search_build(
-    cudaStream_t s, const TreeBuffers &tb, SearchBuffers &sb, const f64 *d_rint, f64 Rkern, f64 h_tolerance,
-    const std::function<void(const char *)> &mark) {
+// The search of one patch in three pieces, so that a model with many patches can enqueue the searches of all
+// of them and synchronise ONCE (Model::start_neighbors_cache): setup (packed nodes, buffers), one attempt
+// (walk + cull + lists + the read-back of the cursors, no synchronisation), and the check of an attempt after the
+// stream has been synchronised (true: a capacity was exceeded, the exact need is known, run another attempt).
+namespace {
+constexpr u32 OVER_CAP = 1u << 16;
+using ListsKernel = void (*)(
+    const NodePack *, u32, u32, const Pack4 *, const u8 *, const u32 *, const uint2 *, const u64 *, const u32 *,
+    const u32 *, f64, f64, u64, unsigned long long *, u32 *, u32 *, u32 *);
+ListsKernel lists_kernel_choice() { // SHAMB200_NL = 0 selects the first version of the list kernel (tuning runs)
+    const char *nl_env = getenv("SHAMB200_NL");
+    return (nl_env && atoi(nl_env) == 0) ? neigh_lists_kernel<0> : neigh_lists_kernel<1>;
+}
+u32 *search_flags(SearchBuffers &sb) { return reinterpret_cast<u32 *>(sb.scalars.p + 2); } // [0] groups over the frontier, [2] errors
+unsigned long long *search_cursor(SearchBuffers &sb) { return reinterpret_cast<unsigned long long *>(sb.scalars.p + 4); }
+unsigned long long *search_ecursor(SearchBuffers &sb) { return reinterpret_cast<unsigned long long *>(sb.scalars.p + 6); }
+constexpr size_t s2_bytes = sizeof(WarpScratch) * S2_WARPS;
+
+void search_setup(cudaStream_t s, const TreeBuffers &tb, SearchBuffers &sb, const f64 *d_rint) {
     const u32 I = tb.I, L = tb.L;
     sb.nodes.ensure(size_t(I) + L, 1.1);
     pack_nodes_kernel<<<grid_for(size_t(I) + L, 256), 256, 0, s>>>(
@@ -842,9 +858,7 @@ void search_build(
     sb.gc_off.ensure(G, 1.1);
     sb.cnt_s.ensure(sb.N, 1.1);
     sb.off_s.ensure(sb.N, 1.1);
-    const f64 Rker2 = Rkern * Rkern;
     static bool attr_set = false;
-    const size_t s2_bytes = sizeof(WarpScratch) * S2_WARPS;
     if (!attr_set) {
         SB_CUDA_CHECK(cudaFuncSetAttribute(neigh_lists_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(s2_bytes)));
         SB_CUDA_CHECK(cudaFuncSetAttribute(neigh_lists_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(s2_bytes)));
@@ -860,100 +874,151 @@ void search_build(
         sb.list_s.ensure(size_t(sb.N) * 96 + 1024);
     if (sb.gcand.cap == 0)
         sb.gcand.ensure(size_t(L) * 24 + 4096);
-    constexpr u32 OVER_CAP = 1u << 16;
+    // head room: a search that outgrows an array runs twice.  Lists grow from step to step while a system
+    // relaxes (h grows by several per cent per step in a fresh disc), so an array the last search filled to more
+    // than 85 % is replaced before this one starts (the old lists are not needed any more).
+    if (sb.K && double(sb.K) > 0.85 * double(sb.list_s.cap))
+        sb.list_s.ensure(size_t(double(sb.K) * 1.4));
+    if (sb.entries_last && double(sb.entries_last) > 0.85 * double(sb.gcand.cap))
+        sb.gcand.ensure(size_t(double(sb.entries_last) * 1.4));
     sb.over_list.ensure(OVER_CAP);
-    u32 *d_flags = reinterpret_cast<u32 *>(sb.scalars.p + 2); // [0] groups over the frontier, [2] errors
-    unsigned long long *d_cursor  = reinterpret_cast<unsigned long long *>(sb.scalars.p + 4);
-    unsigned long long *d_ecursor = reinterpret_cast<unsigned long long *>(sb.scalars.p + 6);
-    auto read_back = [&]() {
+    // tuning knobs (scripts/tune.py): shared-memory frontier entries per walk and the walk kernel's shared-memory
+    // carve-out (per cent of the SM's unified L1 / shared array); both bound the resident walks per SM
+    if (const char *e = getenv("SHAMB200_WALK_F"))
+        sb.frontier_cap = std::max(64, atoi(e));
+    if (const char *e = getenv("SHAMB200_WALK_CARVE"))
+        SB_CUDA_CHECK(cudaFuncSetAttribute(
+            group_walk_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, std::min(100, std::max(0, atoi(e)))));
+}
+
+/// walk + cull + lists of every group and the read-back of the cursors; no synchronisation
+void search_attempt(
+    cudaStream_t s, const TreeBuffers &tb, SearchBuffers &sb, f64 Rkern, f64 h_tolerance,
+    const std::function<void(const char *)> &mark) {
+    const u32 I = tb.I, L = tb.L, G = (L + GL - 1) / GL;
+    const f64 Rker2       = Rkern * Rkern;
+    const size_t per_warp = sizeof(LeafBox) * (GL + 1) + size_t(2) * sb.frontier_cap * sizeof(uint2);
+    const u64 ecap        = sb.gcand.cap;
+    SB_CUDA_CHECK(cudaMemsetAsync(sb.scalars.p + 2, 0, 5 * sizeof(u64), s));
+    if (mark)
+        mark("neigh_walk");
+    const u32 SUPER = top_cfg().super, TOP_CAP = top_cfg().cap;
+    const u32 S = (G + SUPER - 1) / SUPER;
+    sb.top_front.ensure(size_t(S) * TOP_CAP, 1.1);
+    sb.top_count.ensure(S, 1.1);
+    top_walk_kernel<<<S, 32, 0, s>>>(sb.nodes.p, I, L, sb.real_prefix.p, Rkern, SUPER, TOP_CAP, sb.top_front.p, sb.top_count.p);
+    SB_COUNT_LAUNCH();
+    group_walk_kernel<false><<<grid_for(G, WALK_WARPS), WALK_WARPS * 32, per_warp * WALK_WARPS, s>>>(
+        sb.nodes.p, I, L, sb.real_prefix.p, Rkern, sb.frontier_cap, SUPER, TOP_CAP, sb.top_front.p, sb.top_count.p, ecap,
+        search_ecursor(sb), sb.gcand.p, sb.gc_off.p, sb.gcount.p, search_flags(sb), sb.over_list.p, OVER_CAP, nullptr);
+    SB_COUNT_LAUNCH();
+    euclid_cull_kernel<<<grid_for(G, 4), 128, 0, s>>>(
+        sb.nodes.p, I, L, Rkern, sb.gcand.p, sb.gc_off.p, sb.gcount.p, nullptr, G);
+    SB_COUNT_LAUNCH();
+    if (mark)
+        mark("neigh_lists");
+    lists_kernel_choice()<<<G, S2_WARPS * 32, s2_bytes, s>>>(
+        sb.nodes.p, I, L, sb.SA.p, sb.real_flag.p, sb.real_prefix.p, sb.gcand.p, sb.gc_off.p, sb.gcount.p, nullptr,
+        Rker2, h_tolerance, u64(sb.list_s.cap), search_cursor(sb), sb.cnt_s.p, sb.off_s.p, sb.list_s.p);
+    SB_COUNT_LAUNCH();
+    d2h_small(s, sb.h_scalars.p + 2, sb.scalars.p + 2, 5 * sizeof(u64));
+}
+
+void search_errors(const SearchBuffers &sb) {
+    const u32 err = u32(sb.h_scalars.p[3] & 0xffffffffull);
+    if (err & 1u)
+        throw std::runtime_error("neighbour search: a tree leaf holds 2^24 or more objects");
+    if (err & 2u)
+        throw std::runtime_error("neighbour search: internal error, a global-memory frontier overflowed");
+}
+
+/// after the synchronisation that follows an attempt: true = run another attempt (capacities adjusted)
+bool search_check(
+    cudaStream_t s, const TreeBuffers &tb, SearchBuffers &sb, f64 Rkern, f64 h_tolerance, int attempt) {
+    const u32 I = tb.I, L = tb.L, G = (L + GL - 1) / GL;
+    const f64 Rker2 = Rkern * Rkern;
+    const u64 ecap  = sb.gcand.cap;
+    search_errors(sb);
+    u32 n_over = u32(sb.h_scalars.p[2] & 0xffffffffull);
+    bool redo  = false;
+    // many groups over the frontier: a larger shared-memory frontier for everybody; a few (the
+    // surroundings of a particle with a very large h): those groups again with a frontier in global memory
+    if (n_over > OVER_CAP || (n_over > G / 64 && sb.frontier_cap < 2048)) {
+        if (sb.frontier_cap >= 8192)
+            throw std::runtime_error("neighbour search: too many leaf groups need a very large tree-walk frontier");
+        // x 1.4 in multiples of 64 entries (320, 448, 640, 896, ...): the frontier is what bounds the resident
+        // walks per SM, and doubling overshoots (17 M particles: 448 entries suffice, walk 5.5 -> 5.1 ms)
+        sb.frontier_cap = (sb.frontier_cap * 7 / 5 + 63) / 64 * 64;
+        redo = true;
+    } else if (n_over > 0 && sb.h_scalars.p[6] <= ecap) {
+        const u64 budget = 4ull << 30; // scratch for the global frontiers, groups in batches
+        const u32 batch  = u32(std::max<u64>(1, std::min<u64>(n_over, budget / (u64(2) * L * sizeof(uint2)))));
+        sb.big_scratch.ensure(size_t(batch) * 2 * L);
+        for (u32 b0 = 0; b0 < n_over; b0 += batch) {
+            const u32 nb = std::min(batch, n_over - b0);
+            group_walk_kernel<true><<<nb, WALK_WARPS * 32, sizeof(LeafBox) * (GL + 1), s>>>(
+                sb.nodes.p, I, L, sb.real_prefix.p, Rkern, L, top_cfg().super, top_cfg().cap, sb.top_front.p, sb.top_count.p, ecap,
+                search_ecursor(sb), sb.gcand.p, sb.gc_off.p, sb.gcount.p, search_flags(sb), sb.over_list.p + b0, OVER_CAP,
+                sb.big_scratch.p);
+            SB_COUNT_LAUNCH();
+            euclid_cull_kernel<<<grid_for(nb, 4), 128, 0, s>>>(
+                sb.nodes.p, I, L, Rkern, sb.gcand.p, sb.gc_off.p, sb.gcount.p, sb.over_list.p + b0, nb);
+            SB_COUNT_LAUNCH();
+            lists_kernel_choice()<<<nb, S2_WARPS * 32, s2_bytes, s>>>(
+                sb.nodes.p, I, L, sb.SA.p, sb.real_flag.p, sb.real_prefix.p, sb.gcand.p, sb.gc_off.p, sb.gcount.p,
+                sb.over_list.p + b0, Rker2, h_tolerance, u64(sb.list_s.cap), search_cursor(sb), sb.cnt_s.p, sb.off_s.p,
+                sb.list_s.p);
+            SB_COUNT_LAUNCH();
+        }
         d2h_small(s, sb.h_scalars.p + 2, sb.scalars.p + 2, 5 * sizeof(u64));
         SB_CUDA_CHECK(cudaStreamSynchronize(s));
-        const u32 err = u32(sb.h_scalars.p[3] & 0xffffffffull);
-        if (err & 1u)
-            throw std::runtime_error("neighbour search: a tree leaf holds 2^24 or more objects");
-        if (err & 2u)
-            throw std::runtime_error("neighbour search: internal error, a global-memory frontier overflowed");
-    };
-    // SHAMB200_NL = 0 selects the first version of the list kernel (tuning runs)
-    const char *nl_env      = getenv("SHAMB200_NL");
-    const auto lists_kernel = (nl_env && atoi(nl_env) == 0) ? neigh_lists_kernel<0> : neigh_lists_kernel<1>;
+        search_errors(sb);
+    }
+    const u64 need_e = sb.h_scalars.p[6];
+    sb.entries_last  = need_e;
+    sb.K             = sb.h_scalars.p[4];
+    sb.pair_tests    = sb.h_scalars.p[5];
+    if (need_e > ecap) { // the candidate-entry array is too small
+        sb.gcand.ensure(need_e, 1.25);
+        redo = true;
+    }
+    if (!redo && sb.K > 0xFFFFFFFFull)
+        throw std::overflow_error(
+            "neighbour count overflows u32 (sum_neigh_cnt is u32 in the reference, TreeTraversal.hpp:378): "
+            "use more / smaller patches");
+    if (!redo && sb.K > sb.list_s.cap) {
+        sb.list_s.ensure(sb.K, 1.25); // lists grow while a system relaxes: room for a few steps, not for one
+        redo = true;
+    }
+    sb.attempts_last    = u32(attempt) + 1;
+    sb.over_groups_last = n_over;
+    if (redo && attempt >= 8)
+        throw std::runtime_error("neighbour search: capacity retry failed");
+    return redo;
+}
+} // namespace
+
+void search_build(
+    cudaStream_t s, const TreeBuffers &tb, SearchBuffers &sb, const f64 *d_rint, f64 Rkern, f64 h_tolerance,
+    const std::function<void(const char *)> &mark) {
+    search_setup(s, tb, sb, d_rint);
     for (int attempt = 0;; attempt++) {
-        const size_t per_warp = sizeof(LeafBox) * (GL + 1) + size_t(2) * sb.frontier_cap * sizeof(uint2);
-        const u64 ecap        = sb.gcand.cap;
-        SB_CUDA_CHECK(cudaMemsetAsync(sb.scalars.p + 2, 0, 5 * sizeof(u64), s));
-        if (mark)
-            mark("neigh_walk");
-        const u32 SUPER = top_cfg().super, TOP_CAP = top_cfg().cap;
-        const u32 S = (G + SUPER - 1) / SUPER;
-        sb.top_front.ensure(size_t(S) * TOP_CAP, 1.1);
-        sb.top_count.ensure(S, 1.1);
-        top_walk_kernel<<<S, 32, 0, s>>>(sb.nodes.p, I, L, sb.real_prefix.p, Rkern, SUPER, TOP_CAP, sb.top_front.p, sb.top_count.p);
-        SB_COUNT_LAUNCH();
-        group_walk_kernel<false><<<grid_for(G, WALK_WARPS), WALK_WARPS * 32, per_warp * WALK_WARPS, s>>>(
-            sb.nodes.p, I, L, sb.real_prefix.p, Rkern, sb.frontier_cap, SUPER, TOP_CAP, sb.top_front.p, sb.top_count.p, ecap, d_ecursor,
-            sb.gcand.p, sb.gc_off.p, sb.gcount.p, d_flags, sb.over_list.p, OVER_CAP, nullptr);
-        SB_COUNT_LAUNCH();
-        euclid_cull_kernel<<<grid_for(G, 4), 128, 0, s>>>(
-            sb.nodes.p, I, L, Rkern, sb.gcand.p, sb.gc_off.p, sb.gcount.p, nullptr, G);
-        SB_COUNT_LAUNCH();
-        if (mark)
-            mark("neigh_lists");
-        lists_kernel<<<G, S2_WARPS * 32, s2_bytes, s>>>(
-            sb.nodes.p, I, L, sb.SA.p, sb.real_flag.p, sb.real_prefix.p, sb.gcand.p, sb.gc_off.p, sb.gcount.p, nullptr,
-            Rker2, h_tolerance, u64(sb.list_s.cap), d_cursor, sb.cnt_s.p, sb.off_s.p, sb.list_s.p);
-        SB_COUNT_LAUNCH();
-        read_back();
-        u32 n_over = u32(sb.h_scalars.p[2] & 0xffffffffull);
-        bool redo  = false;
-        // many groups over the frontier: a larger shared-memory frontier for everybody; a few (the
-        // surroundings of a particle with a very large h): those groups again with a frontier in global memory
-        if (n_over > OVER_CAP || (n_over > G / 64 && sb.frontier_cap < 2048)) {
-            if (sb.frontier_cap >= 8192)
-                throw std::runtime_error("neighbour search: too many leaf groups need a very large tree-walk frontier");
-            sb.frontier_cap *= 2;
-            redo = true;
-        } else if (n_over > 0 && sb.h_scalars.p[6] <= ecap) {
-            const u64 budget = 4ull << 30; // scratch for the global frontiers, groups in batches
-            const u32 batch  = u32(std::max<u64>(1, std::min<u64>(n_over, budget / (u64(2) * L * sizeof(uint2)))));
-            sb.big_scratch.ensure(size_t(batch) * 2 * L);
-            for (u32 b0 = 0; b0 < n_over; b0 += batch) {
-                const u32 nb = std::min(batch, n_over - b0);
-                group_walk_kernel<true><<<nb, WALK_WARPS * 32, sizeof(LeafBox) * (GL + 1), s>>>(
-                    sb.nodes.p, I, L, sb.real_prefix.p, Rkern, L, top_cfg().super, top_cfg().cap, sb.top_front.p, sb.top_count.p, ecap, d_ecursor,
-                    sb.gcand.p, sb.gc_off.p, sb.gcount.p, d_flags, sb.over_list.p + b0, OVER_CAP, sb.big_scratch.p);
-                SB_COUNT_LAUNCH();
-                euclid_cull_kernel<<<grid_for(nb, 4), 128, 0, s>>>(
-                    sb.nodes.p, I, L, Rkern, sb.gcand.p, sb.gc_off.p, sb.gcount.p, sb.over_list.p + b0, nb);
-                SB_COUNT_LAUNCH();
-                lists_kernel<<<nb, S2_WARPS * 32, s2_bytes, s>>>(
-                    sb.nodes.p, I, L, sb.SA.p, sb.real_flag.p, sb.real_prefix.p, sb.gcand.p, sb.gc_off.p, sb.gcount.p,
-                    sb.over_list.p + b0, Rker2, h_tolerance, u64(sb.list_s.cap), d_cursor, sb.cnt_s.p, sb.off_s.p,
-                    sb.list_s.p);
-                SB_COUNT_LAUNCH();
-            }
-            read_back();
-        }
-        const u64 need_e = sb.h_scalars.p[6];
-        sb.K             = sb.h_scalars.p[4];
-        sb.pair_tests    = sb.h_scalars.p[5];
-        if (need_e > ecap) { // the candidate-entry array is too small
-            sb.gcand.ensure(need_e, 1.25);
-            redo = true;
-        }
-        if (!redo && sb.K > 0xFFFFFFFFull)
-            throw std::overflow_error(
-                "neighbour count overflows u32 (sum_neigh_cnt is u32 in the reference, TreeTraversal.hpp:378): "
-                "use more / smaller patches");
-        if (!redo && sb.K > sb.list_s.cap) {
-            sb.list_s.ensure(sb.K, 1.1);
-            redo = true;
-        }
-        sb.attempts_last    = u32(attempt) + 1;
-        sb.over_groups_last = n_over;
-        if (!redo)
+        search_attempt(s, tb, sb, Rkern, h_tolerance, mark);
+        SB_CUDA_CHECK(cudaStreamSynchronize(s));
+        if (!search_check(s, tb, sb, Rkern, h_tolerance, attempt))
             break;
-        if (attempt >= 8)
-            throw std::runtime_error("neighbour search: capacity retry failed");
+    }
+    SB_LAUNCH_CHECK();
+}
+void search_enqueue(
+    cudaStream_t s, const TreeBuffers &tb, SearchBuffers &sb, const f64 *d_rint, f64 Rkern, f64 h_tolerance) {
+    search_setup(s, tb, sb, d_rint);
+    search_attempt(s, tb, sb, Rkern, h_tolerance, nullptr);
+}
+void search_finish(cudaStream_t s, const TreeBuffers &tb, SearchBuffers &sb, f64 Rkern, f64 h_tolerance) {
+    for (int attempt = 0; search_check(s, tb, sb, Rkern, h_tolerance, attempt); attempt++) {
+        search_attempt(s, tb, sb, Rkern, h_tolerance, nullptr);
+        SB_CUDA_CHECK(cudaStreamSynchronize(s));
     }
     SB_LAUNCH_CHECK();
 }

@@ -23,6 +23,7 @@ struct SearchBuffers {
     u32 N = 0, M = 0, L = 0, I = 0;
     u64 K        = 0; ///< total neighbour count
     u64 pair_tests = 0; ///< (particle, candidate) accept tests of the last search
+    u64 entries_last = 0; ///< candidate entries the last search needed
     u32 frontier_cap = 320; ///< walk frontier entries per group in shared memory (doubled on demand)
     // how the last search went (shamb200_neigh_cache_stats): attempts (1 = every capacity was large enough),
     // groups that were walked with a frontier in global memory
@@ -100,6 +101,11 @@ void search_prepare_sorted_strided(
 void search_build(
     cudaStream_t s, const TreeBuffers &tb, SearchBuffers &sb, const f64 *d_rint, f64 Rkern, f64 h_tolerance,
     const std::function<void(const char *)> &mark = {});
+/// the same around ONE stream synchronisation of the caller (several patches: enqueue all, synchronise once,
+/// finish all).  `finish` repeats the search of a patch whose capacities were exceeded (synchronising itself).
+void search_enqueue(
+    cudaStream_t s, const TreeBuffers &tb, SearchBuffers &sb, const f64 *d_rint, f64 Rkern, f64 h_tolerance);
+void search_finish(cudaStream_t s, const TreeBuffers &tb, SearchBuffers &sb, f64 Rkern, f64 h_tolerance);
 /// ObjectCache layout of the reference (cnt / scanned by id, ids).  Synchronises.
 void export_object_cache(cudaStream_t s, const TreeBuffers &tb, SearchBuffers &sb);
 

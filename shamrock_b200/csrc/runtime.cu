@@ -60,8 +60,12 @@ void *pool_alloc(size_t bytes) {
     SB_CUDA_CHECK(cudaGetDevice(&dev));
     {
         std::lock_guard<std::mutex> g(P.mu);
-        auto range = P.free_blocks.equal_range(sz);
-        for (auto it = range.first; it != range.second; ++it) {
+        // best fit: the smallest cached block that holds the request and is at most twice as large (64 KiB
+        // for small requests) — the sizes of per-step scratch (objects that change patch, ghost counts) differ
+        // from step to step, and an exact-size cache would go back to cudaMalloc (a device synchronisation) for
+        // nearly every one of them
+        const size_t limit = std::max<size_t>(2 * sz, size_t(64) << 10);
+        for (auto it = P.free_blocks.lower_bound(sz); it != P.free_blocks.end() && it->first <= limit; ++it) {
             void *p  = it->second;
             Block &b = P.live[p];
             if (b.device == dev) {

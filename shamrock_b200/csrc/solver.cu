@@ -302,11 +302,42 @@ int64_t Model::get(u32 ip, const std::string &name, void *out, int64_t cap) {
 // ---------------------------------------------------------------------------------------------
 // particle removal / migration (order preserving)
 // ---------------------------------------------------------------------------------------------
-/// keep the particles whose `flag` is set, in order (PatchDataLayer::keep_ids semantics)
-void Model::keep_flagged(PatchD &p, u32 *out_kept) {
+/// doubles per object of the main layout (Σ nvar of PatchFields::all())
+constexpr int kRowDoubles = 22;
+/// one f64 block holding every field of `cnt` rows, field after field (field r starts at cnt * Σ nvar before it)
+static RowTable fields_to_block(PatchFields &f, f64 *block, u32 cnt) {
+    RowTable t{};
+    size_t o = 0;
+    int k    = 0;
+    for (auto &r : f.all()) {
+        t.src[k] = r.buf->p, t.dst[k] = block + o, t.nvar[k] = r.nvar;
+        o += size_t(cnt) * r.nvar;
+        k++;
+    }
+    t.nf = k;
+    return t;
+}
+static RowTable block_to_fields(const f64 *block, u32 cnt, PatchFields &f) {
+    RowTable t{};
+    size_t o = 0;
+    int k    = 0;
+    for (auto &r : f.all()) {
+        t.src[k] = block + o, t.dst[k] = r.buf->p, t.nvar[k] = r.nvar;
+        o += size_t(cnt) * r.nvar;
+        k++;
+    }
+    t.nf = k;
+    return t;
+}
+
+/// keep the particles whose flag is set, in order (PatchDataLayer::keep_ids semantics); flg: the patch's flags
+/// (default: the shared scratch `flag`)
+void Model::keep_flagged(PatchD &p, u32 *out_kept, const u8 *flg) {
     u32 n = p.f.n;
+    if (!flg)
+        flg = flag.p;
     pos.ensure(n);
-    exclusive_scan<u8>(s(), flag.p, pos.p, n, scan_tmp, red.p + 5);
+    exclusive_scan<u8>(s(), flg, pos.p, n, scan_tmp, red.p + 5);
     d2h_small(s(), h_red.p + 5, red.p + 5, sizeof(u64));
     SB_CUDA_CHECK(cudaStreamSynchronize(s()));
     u32 kept = u32(h_red.p[5]);
@@ -315,14 +346,55 @@ void Model::keep_flagged(PatchD &p, u32 *out_kept) {
     if (kept == n)
         return;
     owner_tmp.ensure(n);
-    scatter_ids(s(), n, flag.p, pos.p, owner_tmp.p);
-    for (auto &r : p.f.all()) {
-        field_tmp.ensure(size_t(kept) * r.nvar + 1);
-        gather_field(s(), kept, r.nvar, owner_tmp.p, r.buf->p, field_tmp.p);
-        SB_CUDA_CHECK(cudaMemcpyAsync(
-            r.buf->p, field_tmp.p, size_t(kept) * r.nvar * sizeof(f64), cudaMemcpyDeviceToDevice, s()));
-    }
+    scatter_ids(s(), n, flg, pos.p, owner_tmp.p);
+    // all fields in two launches: kept rows -> one block -> back to the front of the fields
+    field_tmp.ensure(size_t(kept) * kRowDoubles + 1);
+    rows_gather(s(), kept, owner_tmp.p, fields_to_block(p.f, field_tmp.p, kept), 0, 0);
+    rows_gather(s(), kept, nullptr, block_to_fields(field_tmp.p, kept, p.f), 0, 0);
     p.f.n = kept;
+}
+
+/// number of cleared flags of a patch, added to *out
+__global__ void __launch_bounds__(256) count_cleared_kernel(u32 n, const u8 *__restrict__ flag, u32 *__restrict__ out) {
+    u32 c = 0;
+    for (u64 i = u64(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += u64(gridDim.x) * blockDim.x)
+        c += flag[i] ? 0u : 1u;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c)
+        atomicAdd(out, c);
+}
+
+/// sphere removals of every local patch (accretion / kill spheres) with ONE synchronisation: the flags of all
+/// patches are set and counted first; only a patch that really loses objects is compacted (keep_flagged)
+void Model::remove_in_sphere(const f64 center[3], f64 radius, int mode) {
+    std::vector<size_t> loc;
+    std::vector<u64> off;
+    u64 total = 0;
+    for (size_t k = 0; k < patches.size(); k++)
+        if (is_local(patches[k]) && patches[k].f.n) {
+            loc.push_back(k);
+            off.push_back(total);
+            total += (u64(patches[k].f.n) + 15) / 16 * 16;
+        }
+    if (loc.empty())
+        return;
+    flag.ensure(total);
+    box_counts.ensure(loc.size() + 1);
+    SB_CUDA_CHECK(cudaMemsetAsync(box_counts.p, 0, (loc.size() + 1) * sizeof(u32), s()));
+    for (size_t q = 0; q < loc.size(); q++) {
+        PatchD &p = patches[loc[q]];
+        flag_sphere(s(), p.f.n, p.f.xyz.p, center, radius, mode, flag.p + off[q]);
+        const unsigned nb = (unsigned) std::min<u64>(u64(kNumSM) * 4, (u64(p.f.n) + 255) / 256);
+        count_cleared_kernel<<<nb, 256, 0, s()>>>(p.f.n, flag.p + off[q], box_counts.p + q);
+        SB_COUNT_LAUNCH();
+    }
+    h_counts.ensure(loc.size() + 1);
+    d2h_small(s(), h_counts.p, box_counts.p, loc.size() * sizeof(u32));
+    SB_CUDA_CHECK(cudaStreamSynchronize(s()));
+    std::vector<u32> gone(h_counts.p, h_counts.p + loc.size());
+    for (size_t q = 0; q < loc.size(); q++)
+        if (gone[q])
+            keep_flagged(patches[loc[q]], nullptr, flag.p + off[q]);
 }
 
 /// modules::ParticleReordering::reorder_particles (shammodels/sph/src/modules/ParticleReordering.cpp:22-51):
@@ -349,24 +421,12 @@ void Model::point_mass_accrete_particles() {
     if (!cfg.has_point_mass)
         return;
     const f64 c[3] = {0, 0, 0};
-    for (auto &p : patches) {
-        if (!is_local(p) || !p.f.n)
-            continue;
-        flag.ensure(p.f.n);
-        flag_sphere(s(), p.f.n, p.f.xyz.p, c, cfg.pm_racc, 0, flag.p);
-        keep_flagged(p);
-    }
+    remove_in_sphere(c, cfg.pm_racc, 0);
 }
 /// "part killing step" (Solver.cpp:526-578)
 void Model::kill_particles() {
     for (int k = 0; k < cfg.n_kill_spheres; k++)
-        for (auto &p : patches) {
-            if (!is_local(p) || !p.f.n)
-                continue;
-            flag.ensure(p.f.n);
-            flag_sphere(s(), p.f.n, p.f.xyz.p, cfg.kill_center[k], cfg.kill_radius[k], 1, flag.p);
-            keep_flagged(p);
-        }
+        remove_in_sphere(cfg.kill_center[k], cfg.kill_radius[k], 1);
 }
 /// ExternalForces::compute_ext_forces_indep_v (ExternalForces.cpp:49-323)
 void Model::compute_ext_forces_indep_v() {
@@ -458,10 +518,13 @@ void Model::reattribute_patch_objects() {
         any = any || v;
     if (!any)
         return;
-    // 2. stage the migrants of the local senders (all fields) before compacting the sources
+    // 2. per local sender that loses objects: ids of those that stay / leave (one scan), the leavers of every
+    //    receiver staged as ONE block holding all fields, then the sender compacted — its new size is known from
+    //    the counts, no read-back.  (A launch per field and pair, and a scan per pair, cost 30 launches per pair:
+    //    28 ms per step for 44 patches of a disc; now 2 per pair + 9 per sender.)
     struct Mig {
-        u32 src, dst, count;
-        std::vector<DevBuf<f64>> f; // staged rows (local sender only)
+        u32 src, dst, count, dst_off = 0;
+        DevBuf<f64> blk; ///< [field 0 of all rows | field 1 ...] (local sender: staged rows; remote sender: received)
     };
     std::vector<Mig> migs;
     for (size_t k = 0; k < np; k++)
@@ -473,34 +536,36 @@ void Model::reattribute_patch_objects() {
                 m.count = u32(cm[k * np + d]);
                 migs.push_back(std::move(m));
             }
-    for (auto &m : migs) {
-        PatchD &src = patches[m.src];
-        if (!is_local(src))
-            continue;
-        flag_equal(s(), src.f.n, owners[m.src].p, m.dst, flag.p);
-        pos.ensure(src.f.n);
-        exclusive_scan<u8>(s(), flag.p, pos.p, src.f.n, scan_tmp, red.p + 5);
-        owner_tmp.ensure(m.count);
-        scatter_ids(s(), src.f.n, flag.p, pos.p, owner_tmp.p);
-        auto refs = src.f.all();
-        m.f.resize(refs.size());
-        for (size_t r = 0; r < refs.size(); r++) {
-            m.f[r].ensure(size_t(m.count) * refs[r].nvar);
-            gather_field(s(), m.count, refs[r].nvar, owner_tmp.p, refs[r].buf->p, m.f[r].p);
-        }
-    }
-    // 3. compact the sources
-    for (size_t k = 0; k < np; k++) {
+    DevBuf<u32> leave_ids, sel_ids;
+    for (size_t k = 0, im = 0; k < np; k++) {
+        size_t im_end = im;
+        u64 out       = 0;
+        while (im_end < migs.size() && migs[im_end].src == k)
+            out += migs[im_end++].count;
         PatchD &p = patches[k];
-        if (!is_local(p) || !p.f.n)
-            continue;
-        u64 out = 0;
-        for (size_t d = 0; d < np; d++)
-            out += cm[k * np + d];
-        if (!out)
-            continue;
-        flag_equal(s(), p.f.n, owners[k].p, u32(k), flag.p);
-        keep_flagged(p);
+        if (out && is_local(p)) {
+            const u32 n = p.f.n, kept = u32(n - out);
+            flag.ensure(n);
+            pos.ensure(n);
+            owner_tmp.ensure(n);
+            leave_ids.ensure(out);
+            flag_equal(s(), n, owners[k].p, u32(k), flag.p);
+            exclusive_scan<u8>(s(), flag.p, pos.p, n, scan_tmp, red.p + 5);
+            split_ids(s(), n, flag.p, pos.p, owner_tmp.p, leave_ids.p);
+            for (size_t q = im; q < im_end; q++) {
+                Mig &m = migs[q];
+                sel_ids.ensure(m.count);
+                select_equal(s(), u32(out), leave_ids.p, owners[k].p, m.dst, sel_ids.p);
+                m.blk.ensure(size_t(m.count) * kRowDoubles);
+                rows_gather(s(), m.count, sel_ids.p, fields_to_block(p.f, m.blk.p, m.count), 0, 0);
+            }
+            // 3. compact the sender (order preserving)
+            field_tmp.ensure(size_t(kept) * kRowDoubles + 1);
+            rows_gather(s(), kept, owner_tmp.p, fields_to_block(p.f, field_tmp.p, kept), 0, 0);
+            rows_gather(s(), kept, nullptr, block_to_fields(field_tmp.p, kept, p.f), 0, 0);
+            p.f.n = kept;
+        }
+        im = im_end;
     }
     // 4. append at the destinations: (sender, receiver) ascending
     // (a destination may receive from several senders: reserve once for the sum of the incoming counts)
@@ -515,28 +580,36 @@ void Model::reattribute_patch_objects() {
             throw std::overflow_error("patch object count overflows u32 after the reattribution");
         dst.f.reserve(u32(dst.f.n + incoming[d]), s());
     }
+    // rows that cross ranks travel as one message per pair (the staged block)
+    bool remote = false;
+    for (auto &m : migs)
+        if (is_local(patches[m.dst]) && !is_local(patches[m.src]))
+            m.blk.ensure(size_t(m.count) * kRowDoubles);
     comm_group_start(*this);
     for (auto &m : migs) {
         PatchD &src = patches[m.src];
         PatchD &dst = patches[m.dst];
-        auto refs   = dst.f.all();
+        const size_t bytes = size_t(m.count) * kRowDoubles * sizeof(f64);
         if (is_local(dst)) {
-            for (size_t r = 0; r < refs.size(); r++) {
-                f64 *tail    = refs[r].buf->p + size_t(dst.f.n) * refs[r].nvar;
-                size_t bytes = size_t(m.count) * refs[r].nvar * sizeof(f64);
-                if (is_local(src))
-                    SB_CUDA_CHECK(cudaMemcpyAsync(tail, m.f[r].p, bytes, cudaMemcpyDeviceToDevice, s()));
-                else
-                    comm_recv(*this, tail, bytes, src.owner);
-            }
+            m.dst_off = dst.f.n;
             dst.f.n += m.count;
+            if (!is_local(src)) {
+                comm_recv(*this, m.blk.p, bytes, src.owner);
+                remote = true;
+            }
         } else if (is_local(src)) {
-            for (size_t r = 0; r < refs.size(); r++)
-                comm_send(*this, m.f[r].p, size_t(m.count) * refs[r].nvar * sizeof(f64), dst.owner);
+            comm_send(*this, m.blk.p, bytes, dst.owner);
+            remote = true;
         }
     }
     comm_group_end(*this);
-    comm_wait(*this);
+    if (remote)
+        comm_wait(*this);
+    for (auto &m : migs) {
+        PatchD &dst = patches[m.dst];
+        if (is_local(dst))
+            rows_gather(s(), m.count, nullptr, block_to_fields(m.blk.p, m.count, dst.f), 0, m.dst_off);
+    }
     SB_CUDA_CHECK(cudaStreamSynchronize(s()));
 }
 
@@ -583,6 +656,16 @@ void Model::build_ghost_cache() {
     std::vector<std::vector<size_t>> mine(np);
     for (size_t q = 0; q < cand.size(); q++)
         mine[cand[q].sender].push_back(q);
+    std::vector<size_t> hc_off(np, 0); // slots of every local sender in the pinned count read-back
+    {
+        size_t run = 0;
+        for (size_t sd = 0; sd < np; sd++)
+            if (is_local(patches[sd]) && patches[sd].f.n && !mine[sd].empty()) {
+                hc_off[sd] = run;
+                run += 64 * ((mine[sd].size() + 63) / 64);
+            }
+        h_counts.ensure(run + 64);
+    }
     for (size_t sd = 0; sd < np; sd++) {
         PatchD &S = patches[sd];
         if (!is_local(S) || !S.f.n || mine[sd].empty())
@@ -606,10 +689,14 @@ void Model::build_ghost_cache() {
                 s(), n, S.f.xyz.p, nbox, field_tmp.p + ch * 64 * 6, S.st.gmask.p + ch * n,
                 S.st.gblock.p + ch * 64 * size_t(nblocks), S.st.gtotals.p + ch * 64);
         }
-        h_counts.ensure(64 * nch);
-        d2h_small(s(), h_counts.p, S.st.gtotals.p, 64 * nch * sizeof(u32));
-        SB_CUDA_CHECK(cudaStreamSynchronize(s()));
-        const u32 *hc = h_counts.p;
+        d2h_small(s(), h_counts.p + hc_off[sd], S.st.gtotals.p, 64 * nch * sizeof(u32));
+    }
+    SB_CUDA_CHECK(cudaStreamSynchronize(s())); // ONE read-back for all senders
+    for (size_t sd = 0; sd < np; sd++) {
+        PatchD &S = patches[sd];
+        if (!is_local(S) || !S.f.n || mine[sd].empty())
+            continue;
+        const u32 *hc = h_counts.p + hc_off[sd];
         for (size_t j = 0; j < mine[sd].size(); j++)
             counts[mine[sd][j]] = hc[j];
     }
@@ -682,11 +769,16 @@ void Model::merge_position_ghost() {
     // the ghosts that leave this rank first: gather into the staging, hand the messages to the communication
     // stream, and build the local part of the merged positions while they travel
     send_stage.ensure(send_total, 1.1);
-    for (auto &itf : ifaces) {
-        PatchD &R = patches[itf.receiver];
-        PatchD &S = patches[itf.sender];
-        if (is_local(S) && !is_local(R)) // C1: positions + h of the ghosts, 32 B each, straight from the gather
-            ghost_xyzh(s(), itf.count, itf.ids, S.f.xyz.p, S.f.hpart.p, itf.offset, send_stage.p + itf.stage_off);
+    {
+        Batcher<GhostXyzhJob> bt(s()); // one launch per BATCH_JOBS interfaces (stream_kernels.cuh)
+        for (auto &itf : ifaces) {
+            PatchD &R = patches[itf.receiver];
+            PatchD &S = patches[itf.sender];
+            if (is_local(S) && !is_local(R)) // C1: positions + h of the ghosts, 32 B each, straight from the gather
+                bt.add({itf.ids, S.f.xyz.p, S.f.hpart.p, send_stage.p + itf.stage_off, itf.offset[0], itf.offset[1],
+                        itf.offset[2], itf.count});
+        }
+        bt.flush();
     }
     comm_group_start(*this);
     for (auto &itf : ifaces) {
@@ -698,14 +790,19 @@ void Model::merge_position_ghost() {
             comm_recv(*this, R.st.A.p + R.st.n + itf.dst_off, size_t(itf.count) * sizeof(Pack4), S.owner);
     }
     comm_group_end(*this);
-    for (auto &p : patches)
-        if (is_local(p) && p.f.n)
-            pack_xyzh(s(), p.st.n, p.f.xyz.p, p.f.hpart.p, p.st.A.p);
-    for (auto &itf : ifaces) {
-        PatchD &R = patches[itf.receiver];
-        PatchD &S = patches[itf.sender];
-        if (is_local(R) && is_local(S))
-            ghost_xyzh(s(), itf.count, itf.ids, S.f.xyz.p, S.f.hpart.p, itf.offset, R.st.A.p + R.st.n + itf.dst_off);
+    {
+        Batcher<GhostXyzhJob> bt(s());
+        for (auto &p : patches)
+            if (is_local(p) && p.f.n)
+                bt.add({nullptr, p.f.xyz.p, p.f.hpart.p, p.st.A.p, 0., 0., 0., p.st.n});
+        for (auto &itf : ifaces) {
+            PatchD &R = patches[itf.receiver];
+            PatchD &S = patches[itf.sender];
+            if (is_local(R) && is_local(S))
+                bt.add({itf.ids, S.f.xyz.p, S.f.hpart.p, R.st.A.p + R.st.n + itf.dst_off, itf.offset[0], itf.offset[1],
+                        itf.offset[2], itf.count});
+        }
+        bt.flush();
     }
     comm_wait(*this);
     if (cfg.keep_step_data)
@@ -718,11 +815,17 @@ void Model::merge_position_ghost() {
 
 /// modules::BuildTrees::build_merged_pos_trees (BuildTrees.cpp:26-66)
 void Model::build_merged_pos_trees(f64 tol) {
+    // all trees up to their leaf counts, ONE synchronisation, then the Karras trees and the boxes
+    // ... and the interaction radius of every node (compute_presteps_rint) in the AABB pass
     for (auto &p : patches)
         if (is_local(p) && p.f.n)
-            tree_build( // ... and the interaction radius of every node (compute_presteps_rint) in its AABB pass
+            tree_build_begin(
                 s(), p.st.tree, reinterpret_cast<const f64 *>(p.st.A.p), 4, p.st.m, nullptr, nullptr, true,
-                cfg.tree_reduction_level, cfg.sort_mode, tol, &p.st.rint);
+                cfg.tree_reduction_level, cfg.sort_mode);
+    SB_CUDA_CHECK(cudaStreamSynchronize(s()));
+    for (auto &p : patches)
+        if (is_local(p) && p.f.n)
+            tree_build_finish(s(), p.st.tree, reinterpret_cast<const f64 *>(p.st.A.p), 4, tol, &p.st.rint);
 }
 /// Solver::compute_presteps_rint (Solver.cpp:1322-1356)
 void Model::compute_presteps_rint(f64 tol) {
@@ -742,11 +845,28 @@ void Model::start_neighbors_cache(f64 tol) {
         fprintf(stderr, "[shamb200 rank %d] neighbour cache: %zu interfaces\n", rank, ifaces.size());
     K_local         = 0;
     pair_tests_local = 0;
+    size_t nloc = 0;
+    for (auto &p : patches)
+        nloc += is_local(p) && p.f.n;
+    if (nloc > 1) { // the searches of all patches, ONE synchronisation, then the (rare) capacity retries
+        for (auto &p : patches)
+            if (is_local(p) && p.f.n)
+                search_prepare_sorted(s(), p.st.tree, p.st.srch, p.st.A.p, p.st.n);
+        timer.mark(s(), "neigh_walk"); // walks and lists of the patches alternate: one stage for both
+        for (auto &p : patches)
+            if (is_local(p) && p.f.n)
+                search_enqueue(s(), p.st.tree, p.st.srch, p.st.rint.p, Rkern, tol);
+        SB_CUDA_CHECK(cudaStreamSynchronize(s()));
+    }
     for (auto &p : patches)
         if (is_local(p) && p.f.n) {
-            search_prepare_sorted(s(), p.st.tree, p.st.srch, p.st.A.p, p.st.n);
-            search_build(
-                s(), p.st.tree, p.st.srch, p.st.rint.p, Rkern, tol, [&](const char *name) { timer.mark(s(), name); });
+            if (nloc > 1) {
+                search_finish(s(), p.st.tree, p.st.srch, Rkern, tol);
+            } else {
+                search_prepare_sorted(s(), p.st.tree, p.st.srch, p.st.A.p, p.st.n);
+                search_build(
+                    s(), p.st.tree, p.st.srch, p.st.rint.p, Rkern, tol, [&](const char *name) { timer.mark(s(), name); });
+            }
             K_local += p.st.srch.K;
             pair_tests_local += p.st.srch.pair_tests;
             if (verbose() > 1)
@@ -927,20 +1047,25 @@ void Model::communicate_merge_ghosts_fields() {
     // interfaces are packed while they travel.
     const size_t nblk = has_a ? 4 : 3;
     send_stage.ensure(send_total * nblk, 1.1);
-    for (auto &itf : ifaces) {
-        PatchD &R = patches[itf.receiver];
-        PatchD &S = patches[itf.sender];
-        if (is_local(S) && !is_local(R)) {
-            Pack4 *sA = send_stage.p + itf.stage_off * nblk;
-            Pack4 *sB = sA + itf.count, *sC = sB + itf.count, *sD = has_a ? sC + itf.count : nullptr;
-            ghost_xyzh(s(), itf.count, itf.ids, S.f.xyz.p, S.f.hpart.p, itf.offset, sA);
-            pack_fields(
-                s(), itf.count, itf.ids, S.f.hpart.p, S.f.vxyz.p, S.f.uint_.p, S.st.omega.p,
-                has_a ? S.f.axyz.p : nullptr, sA, sB, sC, sD);
-        } else if (is_local(R) && !is_local(S)) {
-            recv_plan.push_back({&itf, recv_total});
-            recv_total += size_t(itf.count) * nblk;
+    {
+        Batcher<GhostXyzhJob> bx(s());
+        Batcher<PackFieldsJob> bf(s());
+        for (auto &itf : ifaces) {
+            PatchD &R = patches[itf.receiver];
+            PatchD &S = patches[itf.sender];
+            if (is_local(S) && !is_local(R)) {
+                Pack4 *sA = send_stage.p + itf.stage_off * nblk;
+                Pack4 *sB = sA + itf.count, *sC = sB + itf.count, *sD = has_a ? sC + itf.count : nullptr;
+                bx.add({itf.ids, S.f.xyz.p, S.f.hpart.p, sA, itf.offset[0], itf.offset[1], itf.offset[2], itf.count});
+                bf.add({itf.ids, nullptr, S.f.hpart.p, S.f.vxyz.p, S.f.uint_.p, S.st.omega.p,
+                        has_a ? S.f.axyz.p : nullptr, sA, sB, sC, sD, itf.count});
+            } else if (is_local(R) && !is_local(S)) {
+                recv_plan.push_back({&itf, recv_total});
+                recv_total += size_t(itf.count) * nblk;
+            }
         }
+        bx.flush(); // positions first: pack_fields overwrites A.d of the same records
+        bf.flush();
     }
     recv_stage.ensure(recv_total, 1.1);
     comm_group_start(*this);
@@ -954,35 +1079,40 @@ void Model::communicate_merge_ghosts_fields() {
         comm_recv(*this, recv_stage.p + rp.second, size_t(rp.first->count) * nblk * sizeof(Pack4),
                   patches[rp.first->sender].owner);
     comm_group_end(*this);
-    for (auto &p : patches) {
-        if (!is_local(p) || !p.f.n)
-            continue;
-        PatchStep &st = p.st;
-        pack_fields(
-            s(), st.n, nullptr, p.f.hpart.p, p.f.vxyz.p, p.f.uint_.p, st.omega.p, has_a ? p.f.axyz.p : nullptr,
-            st.srch.SA.p, st.SB.p, st.SC.p, st.SD.p, st.srch.inv_map.p);
-    }
-    for (auto &itf : ifaces) {
-        PatchD &R = patches[itf.receiver];
-        PatchD &S = patches[itf.sender];
-        if (is_local(R) && is_local(S)) {
-            u32 o = R.st.n + itf.dst_off;
-            pack_fields(
-                s(), itf.count, itf.ids, S.f.hpart.p, S.f.vxyz.p, S.f.uint_.p, S.st.omega.p,
-                has_a ? S.f.axyz.p : nullptr, R.st.srch.SA.p, R.st.SB.p, R.st.SC.p, has_a ? R.st.SD.p : nullptr,
-                R.st.srch.inv_map.p + o);
+    {
+        Batcher<PackFieldsJob> bf(s());
+        for (auto &p : patches) {
+            if (!is_local(p) || !p.f.n)
+                continue;
+            PatchStep &st = p.st;
+            bf.add({nullptr, st.srch.inv_map.p, p.f.hpart.p, p.f.vxyz.p, p.f.uint_.p, st.omega.p,
+                    has_a ? p.f.axyz.p : nullptr, st.srch.SA.p, st.SB.p, st.SC.p, st.SD.p, st.n});
         }
+        for (auto &itf : ifaces) {
+            PatchD &R = patches[itf.receiver];
+            PatchD &S = patches[itf.sender];
+            if (is_local(R) && is_local(S)) {
+                u32 o = R.st.n + itf.dst_off;
+                bf.add({itf.ids, R.st.srch.inv_map.p + o, S.f.hpart.p, S.f.vxyz.p, S.f.uint_.p, S.st.omega.p,
+                        has_a ? S.f.axyz.p : nullptr, R.st.srch.SA.p, R.st.SB.p, R.st.SC.p, has_a ? R.st.SD.p : nullptr,
+                        itf.count});
+            }
+        }
+        bf.flush();
     }
     comm_wait(*this);
-    for (auto &rp : recv_plan) {
-        const Iface &itf = *rp.first;
-        PatchD &R        = patches[itf.receiver];
-        u32 o            = R.st.n + itf.dst_off;
-        const Pack4 *sA  = recv_stage.p + rp.second;
-        const Pack4 *sB = sA + itf.count, *sC = sB + itf.count, *sD = has_a ? sC + itf.count : nullptr;
-        unpack_ghost_fields(
-            s(), itf.count, sA, sB, sC, sD, R.st.srch.SA.p, R.st.SB.p, R.st.SC.p, has_a ? R.st.SD.p : nullptr,
-            R.st.srch.inv_map.p + o);
+    {
+        Batcher<UnpackGhostJob> bu(s());
+        for (auto &rp : recv_plan) {
+            const Iface &itf = *rp.first;
+            PatchD &R        = patches[itf.receiver];
+            u32 o            = R.st.n + itf.dst_off;
+            const Pack4 *sA  = recv_stage.p + rp.second;
+            const Pack4 *sB = sA + itf.count, *sC = sB + itf.count, *sD = has_a ? sC + itf.count : nullptr;
+            bu.add({sA, sB, sC, sD, R.st.srch.inv_map.p + o, R.st.srch.SA.p, R.st.SB.p, R.st.SC.p,
+                    has_a ? R.st.SD.p : nullptr, itf.count});
+        }
+        bu.flush();
     }
 }
 
@@ -1021,27 +1151,35 @@ void Model::exchange_alpha_ghosts(bool with_omega) {
         }
     }
     comm_group_end(*this);
-    for (auto &p : patches)
-        if (is_local(p) && p.f.n)
-            pack_alpha(s(), p.st.n, nullptr, p.st.alpha_updated.p, p.st.SC.p, p.st.srch.inv_map.p,
-                       with_omega ? p.st.omega.p : nullptr);
-    for (auto &itf : ifaces) {
-        PatchD &R = patches[itf.receiver];
-        PatchD &S = patches[itf.sender];
-        if (is_local(R) && is_local(S))
-            pack_alpha(s(), itf.count, itf.ids, S.st.alpha_updated.p, R.st.SC.p, R.st.srch.inv_map.p + R.st.n + itf.dst_off,
-                       with_omega ? S.st.omega.p : nullptr);
+    {
+        Batcher<PackAlphaJob> ba(s());
+        for (auto &p : patches)
+            if (is_local(p) && p.f.n)
+                ba.add({nullptr, p.st.srch.inv_map.p, p.st.alpha_updated.p, with_omega ? p.st.omega.p : nullptr,
+                        p.st.SC.p, p.st.n});
+        for (auto &itf : ifaces) {
+            PatchD &R = patches[itf.receiver];
+            PatchD &S = patches[itf.sender];
+            if (is_local(R) && is_local(S))
+                ba.add({itf.ids, R.st.srch.inv_map.p + R.st.n + itf.dst_off, S.st.alpha_updated.p,
+                        with_omega ? S.st.omega.p : nullptr, R.st.SC.p, itf.count});
+        }
+        ba.flush();
     }
     comm_wait(*this);
-    roff = 0;
-    for (auto &itf : ifaces) {
-        PatchD &R = patches[itf.receiver];
-        if (is_local(R) && !is_local(patches[itf.sender])) {
-            const f64 *stg = recv_stage_f.p + roff;
-            pack_alpha(s(), itf.count, nullptr, stg, R.st.SC.p, R.st.srch.inv_map.p + R.st.n + itf.dst_off,
-                       with_omega ? stg + itf.count : nullptr);
-            roff += size_t(itf.count) * nv;
+    {
+        Batcher<PackAlphaJob> ba(s());
+        roff = 0;
+        for (auto &itf : ifaces) {
+            PatchD &R = patches[itf.receiver];
+            if (is_local(R) && !is_local(patches[itf.sender])) {
+                const f64 *stg = recv_stage_f.p + roff;
+                ba.add({nullptr, R.st.srch.inv_map.p + R.st.n + itf.dst_off, stg, with_omega ? stg + itf.count : nullptr,
+                        R.st.SC.p, itf.count});
+                roff += size_t(itf.count) * nv;
+            }
         }
+        ba.flush();
     }
 }
 

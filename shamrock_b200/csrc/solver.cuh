@@ -199,7 +199,8 @@ struct Model {
     u64 total_part_count();
 
     // pieces of the step (names follow the reference's Solver methods)
-    void keep_flagged(PatchD &p, u32 *out_kept = nullptr);
+    void keep_flagged(PatchD &p, u32 *out_kept = nullptr, const u8 *flg = nullptr);
+    void remove_in_sphere(const f64 center[3], f64 radius, int mode);
     void point_mass_accrete_particles();
     void kill_particles();
     void compute_ext_forces_indep_v();

@@ -517,6 +517,86 @@ void gather_field(cudaStream_t s, u32 cnt, int nvar, const u32 *ids, const f64 *
     SB_LAUNCH_CHECK();
 }
 
+__global__ void __launch_bounds__(256) rows_gather_kernel(u32 cnt, const u32 *__restrict__ ids, RowTable t, u32 src_off, u32 dst_off) {
+    u64 q = u64(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (q >= u64(cnt) * t.nf)
+        return;
+    const u32 k = u32(q / t.nf);
+    const int f = int(q % t.nf);
+    const u64 i = ids ? u64(ids[k]) : u64(src_off) + k;
+    const int nv = t.nvar[f];
+    const f64 *a = t.src[f] + i * nv;
+    f64 *b       = t.dst[f] + (u64(dst_off) + k) * nv;
+    for (int c = 0; c < nv; c++)
+        b[c] = a[c];
+}
+void rows_gather(cudaStream_t s, u32 cnt, const u32 *ids, const RowTable &t, u32 src_off, u32 dst_off) {
+    if (!cnt)
+        return;
+    rows_gather_kernel<<<grid_for(u64(cnt) * t.nf, 256), 256, 0, s>>>(cnt, ids, t, src_off, dst_off);
+    SB_COUNT_LAUNCH();
+    SB_LAUNCH_CHECK();
+}
+
+__global__ void __launch_bounds__(256) split_ids_kernel(
+    u32 n, const u8 *__restrict__ flag, const u32 *__restrict__ pos, u32 *__restrict__ set_ids, u32 *__restrict__ cleared_ids) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    if (flag[i])
+        set_ids[pos[i]] = i;
+    else
+        cleared_ids[i - pos[i]] = i;
+}
+void split_ids(cudaStream_t s, u32 n, const u8 *flag, const u32 *pos, u32 *set_ids, u32 *cleared_ids) {
+    if (!n)
+        return;
+    split_ids_kernel<<<grid_for(n, 256), 256, 0, s>>>(n, flag, pos, set_ids, cleared_ids);
+    SB_COUNT_LAUNCH();
+    SB_LAUNCH_CHECK();
+}
+__global__ void __launch_bounds__(1024) select_equal_kernel(
+    u32 n, const u32 *__restrict__ ids, const u32 *__restrict__ key, u32 val, u32 *__restrict__ out) {
+    __shared__ u32 wsum[32];
+    __shared__ u32 tile_total;
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32 base = 0;
+    for (u32 t0 = 0; t0 < n; t0 += 1024) {
+        const u32 j  = t0 + threadIdx.x;
+        const u32 id = j < n ? ids[j] : 0u;
+        const bool f = j < n && key[id] == val;
+        const u32 b  = __ballot_sync(0xffffffffu, f);
+        if (lane == 0)
+            wsum[warp] = __popc(b);
+        __syncthreads();
+        if (warp == 0) {
+            const u32 v = wsum[lane];
+            u32 inc     = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                u32 t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= u32(o))
+                    inc += t;
+            }
+            wsum[lane] = inc - v;
+            if (lane == 31)
+                tile_total = inc;
+        }
+        __syncthreads();
+        if (f)
+            out[base + wsum[warp] + __popc(b & ((1u << lane) - 1u))] = id;
+        base += tile_total;
+        __syncthreads();
+    }
+}
+void select_equal(cudaStream_t s, u32 n, const u32 *ids, const u32 *key, u32 val, u32 *out) {
+    if (!n)
+        return;
+    select_equal_kernel<<<1, 1024, 0, s>>>(n, ids, key, val, out);
+    SB_COUNT_LAUNCH();
+    SB_LAUNCH_CHECK();
+}
+
 // ---- packs ---------------------------------------------------------------------------------------------
 /// A[i] = (xyz_i, h_i) for the real particles
 __global__ void __launch_bounds__(256) pack_xyzh_kernel(u32 n, const f64 *__restrict__ xyz, const f64 *__restrict__ h, Pack4 *__restrict__ A) {
@@ -549,6 +629,105 @@ void ghost_xyzh(cudaStream_t s, u32 cnt, const u32 *ids, const f64 *xyz, const f
     SB_COUNT_LAUNCH();
     SB_LAUNCH_CHECK();
 }
+
+// ---- batched interface kernels (stream_kernels.cuh) ----------------------------------------------------
+template<class Job>
+__device__ __forceinline__ int batch_job_of_block(const JobBatch<Job> &b, u32 blk) {
+    int lo = 0, hi = b.n - 1; // last job whose first block is <= blk
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (b.first_block[mid] <= blk)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    return lo;
+}
+__global__ void __launch_bounds__(256) ghost_xyzh_batch_kernel(const __grid_constant__ JobBatch<GhostXyzhJob> b) {
+    const int j           = batch_job_of_block(b, blockIdx.x);
+    const GhostXyzhJob &J = b.job[j];
+    const u32 k           = (blockIdx.x - b.first_block[j]) * 256 + threadIdx.x;
+    if (k >= J.count)
+        return;
+    if (J.ids) {
+        const u32 id = J.ids[k];
+        J.dst[k] = Pack4{J.xyz[3 * u64(id)] + J.ox, J.xyz[3 * u64(id) + 1] + J.oy, J.xyz[3 * u64(id) + 2] + J.oz, J.h[id]};
+    } else { // the patch's own objects (pack_xyzh): no offset arithmetic, not even + 0
+        J.dst[k] = Pack4{J.xyz[3 * u64(k)], J.xyz[3 * u64(k) + 1], J.xyz[3 * u64(k) + 2], J.h[k]};
+    }
+}
+__global__ void __launch_bounds__(256) pack_fields_batch_kernel(const __grid_constant__ JobBatch<PackFieldsJob> b) {
+    const int j            = batch_job_of_block(b, blockIdx.x);
+    const PackFieldsJob &J = b.job[j];
+    const u32 k            = (blockIdx.x - b.first_block[j]) * 256 + threadIdx.x;
+    if (k >= J.count)
+        return;
+    const u32 id = J.ids ? J.ids[k] : k;
+    const u32 o  = J.dst_map ? J.dst_map[k] : k;
+    J.A[o].d = J.h[id];
+    J.B[o]   = Pack4{J.vxyz[3 * u64(id)], J.vxyz[3 * u64(id) + 1], J.vxyz[3 * u64(id) + 2], J.uint_[id]};
+    J.C[o].b = J.omega[id];
+    if (J.axyz)
+        J.D[o] = Pack4{J.axyz[3 * u64(id)], J.axyz[3 * u64(id) + 1], J.axyz[3 * u64(id) + 2], 0.};
+}
+__global__ void __launch_bounds__(256) pack_alpha_batch_kernel(const __grid_constant__ JobBatch<PackAlphaJob> b) {
+    const int j           = batch_job_of_block(b, blockIdx.x);
+    const PackAlphaJob &J = b.job[j];
+    const u32 k           = (blockIdx.x - b.first_block[j]) * 256 + threadIdx.x;
+    if (k >= J.count)
+        return;
+    const u32 src = J.ids ? J.ids[k] : k;
+    Pack4 &c      = J.C[J.dst_map ? J.dst_map[k] : k];
+    c.d           = J.alpha[src];
+    if (J.omega)
+        c.b = J.omega[src];
+}
+__global__ void __launch_bounds__(256) unpack_ghost_batch_kernel(const __grid_constant__ JobBatch<UnpackGhostJob> b) {
+    const int j             = batch_job_of_block(b, blockIdx.x);
+    const UnpackGhostJob &J = b.job[j];
+    const u32 k             = (blockIdx.x - b.first_block[j]) * 256 + threadIdx.x;
+    if (k >= J.count)
+        return;
+    const u32 o = J.dst_map ? J.dst_map[k] : k;
+    J.A[o].d = J.sA[k].d;
+    J.B[o]   = J.sB[k];
+    J.C[o].b = J.sC[k].b;
+    if (J.sD)
+        J.D[o] = J.sD[k];
+}
+template<class Job>
+static void launch_batch(cudaStream_t s, const JobBatch<Job> &b, u32 blocks);
+template<>
+void launch_batch<GhostXyzhJob>(cudaStream_t s, const JobBatch<GhostXyzhJob> &b, u32 blocks) {
+    ghost_xyzh_batch_kernel<<<blocks, 256, 0, s>>>(b);
+}
+template<>
+void launch_batch<PackFieldsJob>(cudaStream_t s, const JobBatch<PackFieldsJob> &b, u32 blocks) {
+    pack_fields_batch_kernel<<<blocks, 256, 0, s>>>(b);
+}
+template<>
+void launch_batch<PackAlphaJob>(cudaStream_t s, const JobBatch<PackAlphaJob> &b, u32 blocks) {
+    pack_alpha_batch_kernel<<<blocks, 256, 0, s>>>(b);
+}
+template<>
+void launch_batch<UnpackGhostJob>(cudaStream_t s, const JobBatch<UnpackGhostJob> &b, u32 blocks) {
+    unpack_ghost_batch_kernel<<<blocks, 256, 0, s>>>(b);
+}
+template<class Job>
+void Batcher<Job>::flush() {
+    if (!b.n)
+        return;
+    b.first_block[b.n] = blocks;
+    launch_batch<Job>(s, b, blocks);
+    SB_COUNT_LAUNCH();
+    SB_LAUNCH_CHECK();
+    b.n    = 0;
+    blocks = 0;
+}
+template struct Batcher<GhostXyzhJob>;
+template struct Batcher<PackFieldsJob>;
+template struct Batcher<PackAlphaJob>;
+template struct Batcher<UnpackGhostJob>;
 
 /// field packs.  ids == nullptr: identity (real particles of the patch itself)
 /// A.d = h ; B = (v, u) ; C.b = omega ; D = (a, 0) when `axyz` is given

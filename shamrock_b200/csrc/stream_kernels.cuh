@@ -27,6 +27,76 @@ void ghost_select_count(cudaStream_t s, u32 n, const f64 *xyz, u32 nbox, const f
 void ghost_select_scatter(cudaStream_t s, u32 n, const u64 *mask, u32 nbox, const u32 *block_offsets, const u64 *d_base,
                           u32 *ids_pool);
 void gather_field(cudaStream_t s, u32 cnt, int nvar, const u32 *ids, const f64 *src, f64 *dst);
+// ---- batched interface kernels -------------------------------------------------------------------------
+// A patch has up to 26 interfaces and a rank many patches: a launch per interface and exchange costs more than
+// the copies themselves (a few hundred ghosts each).  The jobs of up to BATCH_JOBS interfaces travel in the
+// kernel parameters (a __grid_constant__ struct: no table in device memory, no copy) and one launch serves them
+// all; a block finds its job by the first-block prefix.
+constexpr int BATCH_JOBS = 40;
+struct GhostXyzhJob { ///< A_dst[k] = (xyz[ids[k]] + offset, h[ids[k]]), ids == nullptr: identity
+    const u32 *ids;
+    const f64 *xyz, *h;
+    Pack4 *dst;
+    f64 ox, oy, oz;
+    u32 count;
+};
+struct PackFieldsJob { ///< pack_fields of one interface / patch
+    const u32 *ids, *dst_map;
+    const f64 *h, *vxyz, *uint_, *omega, *axyz;
+    Pack4 *A, *B, *C, *D;
+    u32 count;
+};
+struct PackAlphaJob { ///< pack_alpha of one interface / patch
+    const u32 *ids, *dst_map;
+    const f64 *alpha, *omega;
+    Pack4 *C;
+    u32 count;
+};
+struct UnpackGhostJob { ///< unpack_ghost_fields of one received interface
+    const Pack4 *sA, *sB, *sC, *sD;
+    const u32 *dst_map;
+    Pack4 *A, *B, *C, *D;
+    u32 count;
+};
+template<class Job>
+struct JobBatch {
+    Job job[BATCH_JOBS];
+    u32 first_block[BATCH_JOBS + 1];
+    int n;
+};
+/// collects jobs and launches one kernel per BATCH_JOBS of them (and at flush / destruction)
+template<class Job>
+struct Batcher {
+    cudaStream_t s;
+    JobBatch<Job> b;
+    u32 blocks = 0;
+    explicit Batcher(cudaStream_t st) : s(st) { b.n = 0; }
+    void add(const Job &j) {
+        if (!j.count)
+            return;
+        b.job[b.n]         = j;
+        b.first_block[b.n] = blocks;
+        blocks += (j.count + 255) / 256;
+        if (++b.n == BATCH_JOBS)
+            flush();
+    }
+    void flush();
+    ~Batcher() { flush(); }
+};
+
+/// every field of a patch data layout in ONE launch: row k of the destination (from row dst_off on) = row
+/// ids[k] (ids == nullptr: src_off + k) of the source, field by field
+struct RowTable {
+    const f64 *src[12];
+    f64 *dst[12];
+    int nvar[12];
+    int nf;
+};
+void rows_gather(cudaStream_t s, u32 cnt, const u32 *ids, const RowTable &t, u32 src_off, u32 dst_off);
+/// pos = exclusive scan of flag: set[pos[i]] = i where flag[i], cleared[i - pos[i]] = i elsewhere (both ascending)
+void split_ids(cudaStream_t s, u32 n, const u8 *flag, const u32 *pos, u32 *set_ids, u32 *cleared_ids);
+/// out = the ids[j], in order, whose key[ids[j]] == val (one block: meant for the few objects that change patch)
+void select_equal(cudaStream_t s, u32 n, const u32 *ids, const u32 *key, u32 val, u32 *out);
 void pack_xyzh(cudaStream_t s, u32 n, const f64 *xyz, const f64 *h, Pack4 *A);
 void ghost_xyzh(cudaStream_t s, u32 cnt, const u32 *ids, const f64 *xyz, const f64 *h, const f64 off[3], Pack4 *A_dst);
 /// dst_map / src_map (optional) redirect record k to slot map[k] (Morton-sorted storage)

@@ -833,6 +833,14 @@ void morton_sort_permutation(
 void tree_build(
     cudaStream_t s, TreeBuffers &t, const f64 *d_xyz, size_t stride, u32 M, const f64 *bmin,
     const f64 *bmax, bool auto_bbox, u32 reduction_level, int sort_mode, f64 field_scale, DevBuf<f64> *field_out) {
+    tree_build_begin(s, t, d_xyz, stride, M, bmin, bmax, auto_bbox, reduction_level, sort_mode);
+    SB_CUDA_CHECK(cudaStreamSynchronize(s));
+    tree_build_finish(s, t, d_xyz, stride, field_scale, field_out);
+}
+
+void tree_build_begin(
+    cudaStream_t s, TreeBuffers &t, const f64 *d_xyz, size_t stride, u32 M, const f64 *bmin,
+    const f64 *bmax, bool auto_bbox, u32 reduction_level, int sort_mode) {
     if (M == 0)
         throw std::invalid_argument("obj_cnt is 0, cannot build a CompressedLeafBVH");
     t.M  = M;
@@ -890,7 +898,11 @@ void tree_build(
     // the leaf count (and the bbox) are needed on the host
     d2h_small(s, t.h_scalars.p, t.scalars.p, sizeof(u64));
     d2h_small(s, t.h_scalars.p + 1, t.bbox.p, 6 * sizeof(f64));
-    SB_CUDA_CHECK(cudaStreamSynchronize(s));
+    SB_LAUNCH_CHECK();
+}
+
+void tree_build_finish(
+    cudaStream_t s, TreeBuffers &t, const f64 *d_xyz, size_t stride, f64 field_scale, DevBuf<f64> *field_out) {
     t.L = u32(t.h_scalars.p[0]);
     std::memcpy(t.bmin, t.h_scalars.p + 1, 3 * sizeof(f64));
     std::memcpy(t.bmax, t.h_scalars.p + 4, 3 * sizeof(f64));

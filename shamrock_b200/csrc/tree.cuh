@@ -33,6 +33,15 @@ void tree_build(
     cudaStream_t s, TreeBuffers &t, const f64 *d_xyz, size_t stride_dbl, u32 M, const f64 *bmin,
     const f64 *bmax, bool auto_bbox, u32 reduction_level, int sort_mode, f64 field_scale = 0.,
     DevBuf<f64> *field_out = nullptr);
+/// the same in two pieces around ONE stream synchronisation of the caller (several trees: enqueue all, synchronise
+/// once, finish all): `begin` runs up to the leaf compression and starts the read-back of the leaf count,
+/// `finish` (after the synchronisation) builds the Karras tree and the boxes
+void tree_build_begin(
+    cudaStream_t s, TreeBuffers &t, const f64 *d_xyz, size_t stride_dbl, u32 M, const f64 *bmin,
+    const f64 *bmax, bool auto_bbox, u32 reduction_level, int sort_mode);
+void tree_build_finish(
+    cudaStream_t s, TreeBuffers &t, const f64 *d_xyz, size_t stride_dbl, f64 field_scale = 0.,
+    DevBuf<f64> *field_out = nullptr);
 // field_out (optional; stride_dbl >= 4): the objects are (x, y, z, f) records and the AABB pass also leaves
 // field_out[node] = field_scale * max f of the node's objects ([I+L]) — tree_field_max without its own pass
 

@@ -14,16 +14,56 @@ ref (paths relative to /root/reference/src):
   shamrock/include/shamrock/io/LegacyVtkWriter.hpp:160-420, shammodels/common/.../io/VTKDumpUtils.hpp:42-160,
   shammodels/sph/src/modules/io/VTKDump.cpp:36-178        legacy VTK: header text, big-endian f32 / i32 sections
 
-Parity pin: the container is checked on the reference's own test of it (src/tests/phantom_read_test.cpp:
-read -> gen_file -> `cmp`): tests/test_io_formats.py feeds files written HERE to the library's reader / writer
-and requires byte-identical copies, and compares the library's model dumps with the bytes built here.  No Phantom
-or VTK file of the reference is available offline, so byte compatibility with files written by the reference
-binary itself is not pinned ("parity unpinned" for the reference-written file; pinned for the format as its
-source states it).  Where the reference writes uninitialised memory (isink, polyk2 and, for the adiabatic EOS,
+Parity pin: (1) the record layer — byte counts, argument order, fixed strings, string arrays, value arrays of all
+eight element types — against the REFERENCE'S OWN CODE run here: oracle/_ref/fortran_io_ref is a driver compiled
+against shambase/fortran_io.hpp where it lies (ref_fortran_io.cpp, `make -C oracle ref`); a dump it writes with
+FortranIOFile equals the bytes gen_file() below builds for the same content, it reads the dumps written by this
+module and by the library, and its copy of them is byte-identical (tests/test_io_formats.py).  (2) the container on
+the reference's own test of it (src/tests/phantom_read_test.cpp: read -> gen_file -> `cmp`) through the library's
+reader / writer.  (3) the model's header tables and particle block, and the VTK file, on the reference's source
+only: PhantomDump.cpp / Model.cpp / VTKDump.cpp need SYCL and cannot be compiled here, and no Phantom or VTK file
+written by the reference exists offline — for the CONTENT of a model dump the comparison with a reference-written
+file stays "parity unpinned".  Where the reference writes uninitialised memory (isink, polyk2 and, for the adiabatic EOS,
 polyk of EOSPhConfig) 0 is used."""
+import os
 import struct
+import subprocess
 
 import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_BIN = os.path.join(_HERE, "_ref", "fortran_io_ref")
+
+
+def ref_binary(build=True):
+    """oracle/_ref/fortran_io_ref: the driver around the REFERENCE's FortranIOFile (ref_fortran_io.cpp), built from
+    /root/reference where that exists (this container); elsewhere the prebuilt file that travelled, or None"""
+    src = os.path.join(_HERE, "ref_fortran_io.cpp")
+    hdr = "/root/reference/src/shambase/include/shambase/fortran_io.hpp"
+    if build and os.path.exists(hdr) and (
+            not os.path.exists(REF_BIN) or os.path.getmtime(REF_BIN) < os.path.getmtime(src)):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+    return REF_BIN if os.path.exists(REF_BIN) else None
+
+
+def ref_synthetic_dump():
+    """the content `fortran_io_ref write` puts into its file (ref_fortran_io.cpp), as a PhantomDump of this module"""
+    ph = PhantomDump()
+    ph.fileid = "FT:Phantom reference-IO pin".ljust(100)
+    for t, name in enumerate(TYPES):
+        fl = name in ("fort_real", "f32", "f64")
+        for k in range(t + 1):
+            ph.add(name, f"tag_{t}_{k}", (k + 1) * (t + 2) * (0.5 if fl else 1))
+    for b, (tot, counts) in enumerate(((37, (1, 1, 1, 1, 1, 2, 2, 1)), (3, (0, 0, 0, 0, 0, 3, 0, 0)))):
+        arrays = {}
+        i = np.arange(tot)
+        for t, name in enumerate(TYPES):
+            fl = name in ("fort_real", "f32", "f64")
+            for j in range(counts[t]):
+                v = ((7 * i + 3 * j + t) % 101 - 50) * (0.25 if fl else 1)
+                arrays.setdefault(name, []).append((f"arr_{b}_{t}_{j}", v))
+        ph.blocks.append({"tot_count": tot, "arrays": arrays})
+    return ph
 
 TYPES = ("fort_int", "i8", "i16", "i32", "i64", "fort_real", "f32", "f64")
 DTYPE = {"fort_int": "<i4", "i8": "i1", "i16": "<i2", "i32": "<i4", "i64": "<i8", "fort_real": "<f8", "f32": "<f4",

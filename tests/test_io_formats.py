@@ -134,3 +134,48 @@ def test_damaged_files_are_refused(tmp_path, damage):
     f.write_bytes(bytes(raw))
     with pytest.raises(_capi.ShamB200Error):
         _capi.phantom_copy(f, tmp_path / "out")
+
+
+# ---- the record layer against the reference's own FortranIOFile (oracle/_ref/fortran_io_ref) --------------------
+def _ref(args):
+    import subprocess
+
+    exe = O.ref_binary()
+    if exe is None:
+        pytest.skip("oracle/_ref/fortran_io_ref is not built (needs /root/reference)")
+    r = subprocess.run([exe] + [str(a) for a in args], capture_output=True, text=True)
+    return r.returncode, r.stderr
+
+
+def test_reference_io_writes_what_the_oracle_writes(tmp_path):
+    """a dump written record by record with the reference's FortranIOFile == gen_file() of the restatement"""
+    f = tmp_path / "ref.phdump"
+    assert _ref(["write", f]) == (0, "")
+    raw = f.read_bytes()
+    assert raw == O.ref_synthetic_dump().gen_file()
+    # the library reads the reference-written file and writes it back unchanged
+    _capi.phantom_copy(f, tmp_path / "lib.phdump")
+    assert (tmp_path / "lib.phdump").read_bytes() == raw
+    assert _capi.phantom_header_int(f, "tag_1_1") == 6 and _capi.phantom_header_float(f, "tag_6_2") == 12.0
+
+
+@pytest.mark.parametrize("seed,n0,n1", [(0, 257, 3), (2, 0, 0), (3, 4099, 17)])
+def test_reference_io_reads_what_oracle_and_library_write(tmp_path, seed, n0, n1):
+    """phantom_read_test.cpp with the reference's record IO: read every record with FortranIOFile, write it again"""
+    a, b, c = tmp_path / "oracle.phdump", tmp_path / "lib.phdump", tmp_path / "ref.phdump"
+    raw = synthetic_dump(seed, n0, n1).gen_file()
+    a.write_bytes(raw)
+    _capi.phantom_copy(a, b)  # written by the library
+    assert _ref(["copy", b, c]) == (0, "")
+    assert c.read_bytes() == raw
+
+
+def test_reference_io_refuses_what_the_library_refuses(tmp_path):
+    raw = bytearray(synthetic_dump().gen_file())
+    raw[28:32] = struct.pack("<i", 25)  # closing byte count of the first record
+    f = tmp_path / "bad.phdump"
+    f.write_bytes(bytes(raw))
+    rc, err = _ref(["copy", f, tmp_path / "out"])
+    assert rc == 2 and "invalid" in err
+    with pytest.raises(_capi.ShamB200Error):
+        _capi.phantom_copy(f, tmp_path / "out2")

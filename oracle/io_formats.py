@@ -46,6 +46,18 @@ def ref_binary(build=True):
     return REF_BIN if os.path.exists(REF_BIN) else None
 
 
+def ref_bmi(values):
+    """expand_bits<u32,2>, expand_bits<u64,2>, contract_bits<u32,2>, contract_bits<u64,2> of the reference
+    (shammath/sfc/bmi.hpp through oracle/_ref/bmi_ref, ref_bmi.cpp) for every value; None if the driver is absent"""
+    ref_binary()
+    exe = os.path.join(_HERE, "_ref", "bmi_ref")
+    if not os.path.exists(exe):
+        return None
+    out = subprocess.run([exe], input="\n".join(str(int(v)) for v in values), capture_output=True, text=True,
+                         check=True).stdout
+    return np.array([[int(t) for t in line.split()] for line in out.strip().splitlines()], dtype=np.uint64)
+
+
 def ref_synthetic_dump():
     """the content `fortran_io_ref write` puts into its file (ref_fortran_io.cpp), as a PhantomDump of this module"""
     ph = PhantomDump()

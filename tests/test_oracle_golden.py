@@ -179,3 +179,28 @@ def test_sph_kernel_identities(kern, R):
     for r in (0.1, 0.5, 1.3):  # W(r,h) = norm f(r/h)/h^3, dW = norm df(r/h)/h^4
         assert po.kernel_eval(kern, "W_3d", r, h) == norm * po.kernel_eval(kern, "f", r / h) / (h * h * h)
         assert po.kernel_eval(kern, "dW_3d", r, h) == norm * po.kernel_eval(kern, "df", r / h) / (h * h * h * h)
+
+
+def test_bit_interleave_against_the_reference_code_itself():
+    """shammath/sfc/bmi.hpp compiled where it lies (oracle/_ref/bmi_ref): the Morton codes of the oracle are
+    expand(x) * 4 + expand(y) * 2 + expand(z) of the reference's own expand_bits (morton.hpp:59-64,127-132), and the
+    bit spreading of the Hilbert restatement (oracle/load_balance.py) is the reference's expand_bits<u64, 2>"""
+    from oracle import io_formats as io
+    from oracle import load_balance as lb
+    from oracle import pyoracle as po
+
+    rng = np.random.default_rng(5)
+    vals = np.concatenate([[0, 1, 2, 1023, 1024, 2**21 - 1], rng.integers(0, 2**21, 200)]).astype(np.uint64)
+    ref = io.ref_bmi(vals)
+    if ref is None:
+        pytest.skip("oracle/_ref/bmi_ref is not built (needs /root/reference)")
+    assert [lb.expand_bits_u64_2(int(v)) for v in vals] == [int(r) for r in ref[:, 1]]
+    assert np.array_equal(io.ref_bmi(ref[:, 1])[:, 3], vals)  # contract_bits undoes expand_bits
+    for bits, nbit, col in ((32, 10, 0), (64, 21, 1)):
+        n = 1 << nbit
+        ijk = rng.integers(0, n, size=(300, 3))
+        ijk[:4] = [[0, 0, 0], [n - 1, n - 1, n - 1], [n - 1, 0, 0], [0, 0, n - 1]]
+        xyz = (ijk + 0.5) / n  # cell centres of the unit box
+        codes = po.morton_codes(xyz, (0, 0, 0), (1, 1, 1), len(xyz), bits=bits)
+        ex = [io.ref_bmi(ijk[:, c])[:, col] for c in range(3)]
+        assert np.array_equal(codes.astype(np.uint64), ex[0] * np.uint64(4) + ex[1] * np.uint64(2) + ex[2])

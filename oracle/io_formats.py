@@ -58,6 +58,18 @@ def ref_bmi(values):
     return np.array([[int(t) for t in line.split()] for line in out.strip().splitlines()], dtype=np.uint64)
 
 
+def ref_units(unit_time, unit_length, unit_mass):
+    """(G, year, au, sol_mass) of the reference's shamunits::Constants in these code units (oracle/_ref/units_ref,
+    ref_units.cpp); None if the driver is absent"""
+    ref_binary()
+    exe = os.path.join(_HERE, "_ref", "units_ref")
+    if not os.path.exists(exe):
+        return None
+    out = subprocess.run([exe, repr(float(unit_time)), repr(float(unit_length)), repr(float(unit_mass))],
+                         capture_output=True, text=True, check=True).stdout
+    return tuple(float(t) for t in out.split())
+
+
 def ref_synthetic_dump():
     """the content `fortran_io_ref write` puts into its file (ref_fortran_io.cpp), as a PhantomDump of this module"""
     ph = PhantomDump()

@@ -293,7 +293,8 @@ class Constants:
         self.u = unit_system
 
     def G(self):
-        return 6.6743e-11 * self.u.unit_mass * self.u.unit_time**2 / self.u.unit_length**3
+        # Constants<T>::Si::G = 6.6743015e-11 in the reference (shamunits/Constants.hpp:86), not CODATA's 6.67430e-11
+        return 6.6743015e-11 * self.u.unit_mass * self.u.unit_time**2 / self.u.unit_length**3
 
     def year(self):
         return 31557600.0 / self.u.unit_time

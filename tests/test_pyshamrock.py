@@ -95,3 +95,17 @@ def test_reference_ci_case_through_the_api(fp_mode):
     assert n == 646
     for k, v in rel.items():
         assert abs(v) < 1e-11, (k, v)
+
+
+def test_constants_against_the_reference_code_itself():
+    """shamunits/{UnitSystem,Constants}.hpp compiled where they lie (oracle/_ref/units_ref): the constants the disc
+    script reads (examples/sph/run_circular_disc_central_pot.py:40-50) in SI and in its code units (yr, au, Msun)"""
+    from oracle import io_formats as io
+
+    si = shamrock.Constants(shamrock.UnitSystem())
+    for ut, ul, um in ((1.0, 1.0, 1.0), (3600 * 24 * 365, si.au(), si.sol_mass()), (7.0, 1e3, 2.5e-4)):
+        ref = io.ref_units(ut, ul, um)
+        if ref is None:
+            pytest.skip("oracle/_ref/units_ref is not built (needs /root/reference)")
+        c = shamrock.Constants(shamrock.UnitSystem(unit_time=ut, unit_length=ul, unit_mass=um))
+        assert np.allclose([c.G(), c.year(), c.au(), c.sol_mass()], ref, rtol=1e-14, atol=0)

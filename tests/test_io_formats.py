@@ -179,3 +179,26 @@ def test_reference_io_refuses_what_the_library_refuses(tmp_path):
     assert rc == 2 and "invalid" in err
     with pytest.raises(_capi.ShamB200Error):
         _capi.phantom_copy(f, tmp_path / "out2")
+
+
+def test_model_shaped_dump_through_library_and_reference_io(tmp_path):
+    """what Model::make_phantom_dump writes (oracle restatement of Model.cpp:1491-1638; the CUDA model's file equals
+    these bytes: tests/test_gpu_io_formats.py) is read by the library's configuration path and by the reference's
+    record IO class"""
+    rng = np.random.default_rng(1)
+    n = 1000
+    fields = dict(xyz=rng.normal(size=(n, 3)), vxyz=rng.normal(size=(n, 3)), hpart=rng.uniform(0.01, 0.02, n),
+                  uint=rng.uniform(1, 2, n), alpha_AV=rng.uniform(0, 1, n), divv=rng.normal(size=n))
+    cfg = dict(eos="lp07", gamma=5 / 3, cs0=0.05, q=0.25, r0=2.0, av_has_alpha=True, time=0.125, dt=1e-3, hfact=1.2,
+               cfl_cour=0.3, cfl_force=0.25, gpart_mass=1e-6, periodic=True, bmin=(-1, -2, -3), bmax=(1, 2, 3))
+    f = tmp_path / "model.phdump"
+    raw = O.make_phantom_dump(fields, cfg).gen_file()
+    f.write_bytes(raw)
+    assert _capi.phantom_header_int(f, "nparttot") == n and _capi.phantom_header_float(f, "hfact") == 1.2
+    assert _capi.phantom_header_float(f, "ymax") == 1.0  # Phantom2Shamrock.cpp:203-209: bmax.x()
+    c = _capi.phantom_gen_config(f)
+    assert (c.eos, c.eos_q, c.eos_r0, c.bc, c.gpart_mass) == (2, 0.25, 1.0, 1, 1e-6)
+    assert c.cs0 == np.sqrt(2.0 / 3.0 * (1.5 * (0.05 * 0.05 / 4.0)))  # polyk = cs0² / r0², RK2 = 1.5 polyk
+    assert c.alpha_u == 1.0  # the writer's "alphau" entry
+    rc, err = _ref(["copy", f, tmp_path / "copy"])
+    assert (rc, err) == (0, "") and (tmp_path / "copy").read_bytes() == raw

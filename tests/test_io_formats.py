@@ -202,3 +202,19 @@ def test_model_shaped_dump_through_library_and_reference_io(tmp_path):
     assert c.alpha_u == 1.0  # the writer's "alphau" entry
     rc, err = _ref(["copy", f, tmp_path / "copy"])
     assert (rc, err) == (0, "") and (tmp_path / "copy").read_bytes() == raw
+
+
+def test_error_behaviour_of_the_file_level_calls(tmp_path):
+    missing = tmp_path / "nothing.phdump"
+    for call in (lambda: _capi.phantom_copy(missing, tmp_path / "o"), lambda: _capi.phantom_gen_config(missing),
+                 lambda: _capi.phantom_header_int(missing, "ieos"), lambda: _capi.phantom_compare(missing, missing)):
+        with pytest.raises(_capi.ShamB200Error, match="cannot open"):
+            call()
+    f = tmp_path / "d.phdump"
+    ph = synthetic_dump()
+    ph.tables["fort_real"] = [e for e in ph.tables["fort_real"] if e[0].strip() != "C_cour"]
+    f.write_bytes(ph.gen_file())
+    with pytest.raises(_capi.ShamB200Error, match="C_cour"):  # read_header_float: the entry cannot be found
+        _capi.phantom_gen_config(f)
+    L = _capi.lib()
+    assert L.shamb200_phantom_copy(None, None) == -1 and b"null" in L.shamb200_last_error()
